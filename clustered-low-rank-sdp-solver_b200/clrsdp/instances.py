@@ -1,0 +1,238 @@
+"""Instance generators: inputs of the hot path in the layout `prepareabc` produces (MPMP.jl:385-406).
+
+* `synthetic_clustered_sdp` — BASELINE configs 3 and 5: a manufactured, strictly feasible
+  clustered low-rank SDP (rank-1 constraints, m = 1, one block per cluster). All data are dyadic
+  rationals built from a counter-based PRNG, so the instance is bit-identical on every machine and is
+  converted to the working precision without rounding (for p >= 192).
+* `sphere_packing_2point` — BASELINE configs 1 and 2: the binary sphere-packing bound of
+  examples/SpherePacking.jl:28-114, restating the univariate `Pi = nothing` path of `prepareabc`
+  (MPMP.jl:250-254, 283-312, 345-376, 387-400) with mpmath.
+Neither touches the oracle or the GPU; they only produce `Constraint` objects and `b`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .solver import Constraint
+from .wire import MpArray
+
+FRAC_BITS = 40  # all synthetic data are integers / 2^40
+
+
+def _rand_scaled(rng: np.random.Generator, shape, lo: float, hi: float) -> np.ndarray:
+    """integers r with r/2^40 uniform in [lo, hi)"""
+    return rng.integers(int(lo * 2 ** FRAC_BITS), int(hi * 2 ** FRAC_BITS), size=shape, dtype=np.int64)
+
+
+def synthetic_clustered_sdp(J=64, delta=64, K=128, n_y=256, prec=256, seed=20261018, j_offset=0, j_total=None,
+                            yrank=4):
+    """Manufactured strictly feasible pair.
+
+    Cluster j: sample points t_k = Chebyshev nodes on [-1,1] (MPMP.jl:184-191), vectors
+    v_k = w_k * [T_0(t_k) .. T_{delta-1}(t_k)] with w_k in [0.5,1.5), H = +1, B_j in [-1,1)^{K x n_y}.
+    A primal point x0 in [0.5,1.5) (so X0 = sum x0_k v_k v_k^T > 0 as K >= delta) and a dual point
+    (y0 in [-1,1), Y0 = I + G G^T, G delta x yrank in [-1/8,1/8)) define b := B^T x0 and
+    c := Tr(A_* Y0) + B y0. Both problems are then strictly feasible, so the gap closes.
+
+    `j_offset/j_total` generate clusters j_offset .. j_offset+J-1 of a j_total-cluster problem (each
+    cluster draws from its own PRNG stream), for sharding over ranks: b is the FULL problem's b.
+    Returns (constraints, b, info) with info holding x0,y0 for tests.
+    """
+    nlimb = prec // 32
+    j_total = j_total if j_total is not None else j_offset + J
+    assert K >= delta
+    kk = np.arange(1, K + 1)
+    t = np.cos((2 * kk - 1) / (2.0 * K) * np.pi)            # create_sample_points_chebyshev(K-1)
+    Tm = np.cos(np.outer(np.arccos(t), np.arange(delta)))     # T_i(t_k), K x delta
+    y0 = _rand_scaled(np.random.default_rng([seed, 10 ** 6]), n_y, -1.0, 1.0)
+    y0_obj = y0.astype(object)
+    b_int = np.zeros(n_y, dtype=object)                       # scale 2^-80
+    constraints = []
+    x0_all = []
+    for j in range(j_total):
+        rng = np.random.default_rng([seed, j])
+        w = rng.uniform(0.5, 1.5, size=K)
+        V = np.round(Tm * w[:, None] * 2 ** FRAC_BITS).astype(np.int64)   # K x delta, scale 2^-40
+        B = _rand_scaled(rng, (K, n_y), -1.0, 1.0)
+        x0 = _rand_scaled(rng, K, 0.5, 1.5)
+        G = _rand_scaled(rng, (delta, yrank), -0.125, 0.125)
+        b_int += B.astype(object).T.dot(x0.astype(object))
+        if not (j_offset <= j < j_offset + J):
+            continue
+        Vo, Go = V.astype(object), G.astype(object)
+        vv = (Vo * Vo).sum(axis=1)                               # |v_k|^2, scale 2^-80
+        gv = Vo.dot(Go)                                          # G^T v_k, scale 2^-80
+        gg = (gv * gv).sum(axis=1)                               # scale 2^-160
+        By = B.astype(object).dot(y0_obj)                        # scale 2^-80
+        c_int = (vv + By) * (1 << 80) + gg                       # scale 2^-160
+        constraints.append(Constraint(
+            V=[MpArray.from_scaled_int64(V, -FRAC_BITS, nlimb).reshape(K, delta)],
+            ranks=[np.ones(K, dtype=np.int32)],
+            H=[MpArray.from_scaled_int64(np.ones(K, dtype=np.int64), 0, nlimb)],
+            B=MpArray.from_scaled_int64(B, -FRAC_BITS, nlimb).reshape(K, n_y),
+            c=MpArray.from_ints(list(c_int), -160, nlimb),
+        ))
+        x0_all.append(x0)
+    b = MpArray.from_ints(list(b_int), -80, nlimb)
+    info = dict(x0=x0_all, y0=y0, J=J, delta=delta, K=K, n_y=n_y, prec=prec, seed=seed)
+    return constraints, b, info
+
+
+# ----------------------------------------------------------------------------------------------------
+# sphere packing (examples/SpherePacking.jl) — mpmath restatement of the input generation
+# ----------------------------------------------------------------------------------------------------
+def _poly_eval(coeffs, x):
+    r = 0
+    for c in reversed(coeffs):
+        r = r * x + c
+    return r
+
+
+def laguerrebasis_polys(k, alpha, scale, mp):
+    """Coefficient lists (ascending powers of x) of laguerrebasis(k, alpha, scale*x) (MPMP.jl:43-54)."""
+    def padd(a, b):
+        n = max(len(a), len(b))
+        return [(a[i] if i < len(a) else 0) + (b[i] if i < len(b) else 0) for i in range(n)]
+
+    def pscal(a, s):
+        return [c * s for c in a]
+
+    def pmulx(a, s):  # a(x) * (s*x)
+        return [mp.mpf(0)] + [c * s for c in a]
+
+    v = [[mp.mpf(1)]]
+    if k == 0:
+        return v
+    v.append(padd([1 + alpha], pmulx([mp.mpf(-1)], scale)))
+    for l in range(2, k + 1):
+        # v[l+1] = 1/l * ((2l-1+alpha-x) v[l] - (l+alpha-1) v[l-1])
+        t1 = padd(pscal(v[l - 1], 2 * l - 1 + alpha), pscal(pmulx(v[l - 1], scale), -1))
+        t2 = pscal(v[l - 2], -(l + alpha - 1))
+        v.append(pscal(padd(t1, t2), mp.mpf(1) / l))
+    return v
+
+
+def sphere_packing_2point(n=3, d=8, r=None, prec=512, N=2):
+    """The SDP of examples/SpherePacking.jl:28-110 for N=2 radii, as (constraints, b, omega).
+
+    Variables y = (M, a_{ij,k} for k=0:2d for i=1:N for j=1:i) (:54, :89); objective max -M (:88-89).
+    The seven constraints (:56-66), their sample points (:69-72), weights G (:75-78), the rescaled
+    Laguerre basis (:81-83), degrees (:86) and the cluster reordering (:99-105) follow the example;
+    `prepareabc`'s default path turns each into (A,B,c,H).
+    """
+    import mpmath
+    assert N == 2
+    nlimb = prec // 32
+    mp = mpmath.mp.clone()
+    mp.prec = prec + 64
+    if r is None:
+        r = [mp.mpf(1), mp.sqrt(2) - 1]
+    r = [mp.mpf(v) for v in r]
+    pi = mp.pi
+    pairs = [(i, j) for i in range(N) for j in range(i + 1)]            # for i=1:N for j=1:i
+    n_a = (2 * d + 1) * len(pairs)
+    n_y = 1 + n_a
+
+    def a_index(k, pi_idx):  # column of a_{pair,k} in y (after M)
+        return 1 + k * len(pairs) + pi_idx
+
+    def spherevolume(nn, rr):
+        return mp.sqrt(pi) ** nn / mp.gamma(mp.mpf(nn) / 2 + 1) * rr ** nn
+
+    # basis: laguerrebasis(d, n/2-1, 2*pi*x), each divided by its max coefficient (:81-83)
+    q = laguerrebasis_polys(d, mp.mpf(n) / 2 - 1, 2 * pi, mp)
+    q = [[c / max(p) for c in p] for p in q]
+    deg_q = list(range(d + 1))
+    # Laguerre polynomials for the f constraints: k!/pi^k L_k^{n/2-1}(pi x)
+    lag = laguerrebasis_polys(2 * d, mp.mpf(n) / 2 - 1, pi, mp)
+    fcoef = [mp.factorial(k) / pi ** k for k in range(2 * d + 1)]
+
+    def samples_1d(dd):  # create_sample_points_1d (MPMP.jl:173-182)
+        const = -mp.sqrt(pi) / (64 * (dd + 1) * mp.log(3 - 2 * mp.sqrt(2)))
+        return [const * (-1 + 4 * k) ** 2 for k in range(dd + 1)]
+
+    def prepare(m, Mfun, G, deg_G, xs, delta):
+        """prepareabc default path: Mfun(x) -> (M0 (m x m), list over y-index of m x m matrices)."""
+        K = len(xs)
+        last_deg = []
+        for e in range(delta // 2 + 1):  # (:296-303)
+            idx = [i for i, dg in enumerate(deg_q) if dg == e]
+            last_deg.append(idx[-1] + 1 if idx else last_deg[-1])
+        V, H, ranks = [], [], []
+        for l, g in enumerate(G):
+            nvec = last_deg[(delta - deg_G[l]) // 2]
+            vl, hl = [], []
+            for xk in xs:
+                gv = g(xk)
+                sq = mp.sqrt(abs(gv))
+                vl.extend(_poly_eval(q[dd], xk) * sq for dd in range(nvec))       # (:365-374)
+                hl.append(mp.sign(gv))                                            # (:307-312)
+            # threshold pruning (:378-383) never triggers here: |H| = 1
+            V.append(MpArray.from_mpf(vl, nlimb).reshape(K, nvec))
+            H.append(MpArray.from_mpf(hl, nlimb))
+            ranks.append(np.ones(K, dtype=np.int32))
+        Brows, crows = [], []
+        evals = [Mfun(xk) for xk in xs]
+        for rr in range(m):          # for r = 1:m for s = 1:r for k  (:387-400)
+            for ss in range(rr + 1):
+                for k in range(K):
+                    M0, Mi = evals[k]
+                    Brows.extend(-Mi[i][rr][ss] for i in range(n_y))
+                    crows.append(M0[rr][ss])
+        dimS = m * (m + 1) // 2 * K
+        return Constraint(V=V, ranks=ranks, H=H, B=MpArray.from_mpf(Brows, nlimb).reshape(dimS, n_y),
+                          c=MpArray.from_mpf(crows, nlimb))
+
+    zero2 = lambda: [[mp.mpf(0)] * N for _ in range(N)]
+
+    def E(i, j, val):
+        Z = zero2()
+        Z[i][j] = val
+        Z[j][i] = val
+        return Z
+
+    def M0fun(x):  # (:56-57)
+        M0 = [[-mp.sqrt(spherevolume(n, r[i]) * spherevolume(n, r[j])) for j in range(N)] for i in range(N)]
+        Mi = [zero2() for _ in range(n_y)]
+        for pi_idx, (i, j) in enumerate(pairs):
+            Mi[a_index(0, pi_idx)] = E(i, j, mp.mpf(1))
+        return M0, Mi
+
+    def M1fun(x):  # (:59)
+        Mi = [zero2() for _ in range(n_y)]
+        for k in range(2 * d + 1):
+            for pi_idx, (i, j) in enumerate(pairs):
+                Mi[a_index(k, pi_idx)] = E(i, j, x ** k)
+        return zero2(), Mi
+
+    def M2fun(pair_idx):  # (:61-62)
+        def f(x):
+            Mi = [[[mp.mpf(0)]] for _ in range(n_y)]
+            for k in range(2 * d + 1):
+                Mi[a_index(k, pair_idx)] = [[-fcoef[k] * _poly_eval(lag[k], x)]]
+            return [[mp.mpf(0)]], Mi
+        return f
+
+    def M3fun(i):  # (:64-65)
+        pair_idx = pairs.index((i, i))
+        def f(x):
+            Mi = [[[mp.mpf(0)]] for _ in range(n_y)]
+            Mi[0] = [[mp.mpf(1)]]
+            for k in range(2 * d + 1):
+                Mi[a_index(k, pair_idx)] = [[-fcoef[k] * _poly_eval(lag[k], mp.mpf(0))]]
+            return [[mp.mpf(0)]], Mi
+        return f
+
+    one = lambda x: mp.mpf(1)
+    cons = [prepare(N, M0fun, [one], [0], [mp.mpf(0)], 0),
+            prepare(N, M1fun, [one, lambda x: x], [0, 1], samples_1d(2 * d), 2 * d)]
+    for pair_idx, (i, j) in enumerate(pairs):
+        shift = (r[i] + r[j]) ** 2
+        xs = [v + shift for v in samples_1d(2 * d)]
+        cons.append(prepare(1, M2fun(pair_idx), [one, (lambda s: (lambda x: x - s))(shift)], [0, 1], xs, 2 * d))
+    for i in range(N):
+        cons.append(prepare(1, M3fun(i), [one], [0], [mp.mpf(0)], 0))
+    ordering = [3, 6, 5, 7, 4, 1, 2]  # (:102), 1-based
+    cons = [cons[o - 1] for o in ordering]
+    b = MpArray.from_mpf([mp.mpf(-1)] + [mp.mpf(0)] * n_a, nlimb)  # (:89)
+    return cons, b, dict(n=n, d=d, prec=prec, n_y=n_y, omega=mp.mpf(100))
