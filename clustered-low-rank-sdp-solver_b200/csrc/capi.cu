@@ -1,0 +1,196 @@
+// capi.cu — the extern "C" surface declared in include/clrsdp.h. Exceptions never cross the boundary:
+// every entry point maps them to a status code and keeps the message for clrsdp_last_error.
+#include <cstring>
+
+#include "solver.cuh"
+
+struct clrsdp_solver {
+  clr::Solver* s = nullptr;
+  std::string err;
+};
+
+#define CAPI extern "C" __attribute__((visibility("default")))
+
+template <class F>
+static int guard(clrsdp_handle h, F f) {
+  if (!h || !h->s) return CLRSDP_ERR_BAD_ARG;
+  try {
+    return f(*h->s);
+  } catch (const clr::SolverError& e) {
+    h->err = e.what();
+    return e.code;
+  } catch (const clr::CudaError& e) {
+    h->err = e.what();
+    return CLRSDP_ERR_CUDA;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return CLRSDP_ERR_BAD_ARG;
+  }
+}
+
+CAPI int clrsdp_create(clrsdp_handle* h, int prec_bits, int device) {
+  if (!h) return CLRSDP_ERR_BAD_ARG;
+  *h = nullptr;
+  clrsdp_solver* w = new clrsdp_solver();
+  try {
+    w->s = new clr::Solver(prec_bits, device);
+  } catch (const clr::SolverError& e) {
+    int code = e.code;
+    fprintf(stderr, "clrsdp_create: %s\n", e.what());
+    delete w;
+    return code;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "clrsdp_create: %s\n", e.what());
+    delete w;
+    return CLRSDP_ERR_CUDA;
+  }
+  *h = w;
+  return CLRSDP_OK;
+}
+CAPI int clrsdp_destroy(clrsdp_handle h) {
+  if (h) {
+    delete h->s;
+    delete h;
+  }
+  return CLRSDP_OK;
+}
+CAPI const char* clrsdp_last_error(clrsdp_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+CAPI int clrsdp_set_structure(clrsdp_handle h, int J, int n_y, const int* m, const int* L, const int* n_samples,
+                              const int* delta, const int* ranks) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!m || !L || !n_samples || !delta || !ranks) return (int)CLRSDP_ERR_BAD_ARG;
+    s.set_structure(J, n_y, m, L, n_samples, delta, ranks);
+    return 0;
+  });
+}
+CAPI int clrsdp_upload_cluster(clrsdp_handle h, int j, const clrsdp_mp* V, const clrsdp_mp* H, const clrsdp_mp* B,
+                               const clrsdp_mp* c) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!V || !H || !B || !c) return (int)CLRSDP_ERR_BAD_ARG;
+    s.upload_cluster(j, V, H, B, c);
+    return 0;
+  });
+}
+CAPI int clrsdp_upload_objective(clrsdp_handle h, const clrsdp_mp* b, const clrsdp_mp* b0) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!b) return (int)CLRSDP_ERR_BAD_ARG;
+    s.upload_objective(b, b0);
+    return 0;
+  });
+}
+CAPI int clrsdp_set_params(clrsdp_handle h, const clrsdp_mp* rp, const clrsdp_int_params* ip) {
+  return guard(h, [&](clr::Solver& s) {
+    s.set_params(rp, ip);
+    return 0;
+  });
+}
+CAPI int clrsdp_init_point(clrsdp_handle h) {
+  return guard(h, [&](clr::Solver& s) {
+    s.init_point();
+    return 0;
+  });
+}
+CAPI int clrsdp_upload_point(clrsdp_handle h, const clrsdp_mp* x, const clrsdp_mp* X, const clrsdp_mp* y,
+                             const clrsdp_mp* Y) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!x || !X || !y || !Y) return (int)CLRSDP_ERR_BAD_ARG;
+    s.upload_point(x, X, y, Y);
+    return 0;
+  });
+}
+CAPI int clrsdp_download_point(clrsdp_handle h, clrsdp_mp_out* x, clrsdp_mp_out* X, clrsdp_mp_out* y,
+                               clrsdp_mp_out* Y) {
+  return guard(h, [&](clr::Solver& s) {
+    s.download_point(x, X, y, Y);
+    return 0;
+  });
+}
+CAPI int clrsdp_prepare(clrsdp_handle h, clrsdp_iter_info* info) {
+  return guard(h, [&](clr::Solver& s) { return s.prepare(info); });
+}
+CAPI int clrsdp_iterate(clrsdp_handle h, clrsdp_iter_info* info) {
+  return guard(h, [&](clr::Solver& s) { return s.iterate(info); });
+}
+CAPI int clrsdp_solve(clrsdp_handle h, clrsdp_iter_info* rows, int max_rows, int* n_rows) {
+  return guard(h, [&](clr::Solver& s) { return s.solve(rows, max_rows, n_rows); });
+}
+CAPI int64_t clrsdp_fetch(clrsdp_handle h, const char* name, int j, int l, clrsdp_mp_out* out) {
+  if (!h || !h->s || !name) return CLRSDP_ERR_BAD_ARG;
+  try {
+    return h->s->fetch(name, j, l, out);
+  } catch (const clr::SolverError& e) {
+    h->err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return CLRSDP_ERR_CUDA;
+  }
+}
+CAPI int clrsdp_op_gemm(clrsdp_handle h, int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B,
+                        clrsdp_mp_out* C) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!A || !B || !C || batch <= 0 || M <= 0 || N <= 0 || K <= 0) return (int)CLRSDP_ERR_BAD_ARG;
+    s.op_gemm(batch, M, N, K, A, B, C);
+    return 0;
+  });
+}
+CAPI int clrsdp_op_gemm_planes(clrsdp_handle h, int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B,
+                               int32_t* planes, int* n_planes, int32_t* row_exp, int32_t* col_exp) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!A || !B || !planes || !n_planes || !row_exp || !col_exp) return (int)CLRSDP_ERR_BAD_ARG;
+    s.op_gemm_planes(batch, M, N, K, A, B, planes, n_planes, row_exp, col_exp);
+    return 0;
+  });
+}
+CAPI int clrsdp_op_cholesky(clrsdp_handle h, int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L,
+                            clrsdp_mp_out* Linv) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!A) return (int)CLRSDP_ERR_BAD_ARG;
+    return s.op_cholesky(batch, n, A, L, Linv);
+  });
+}
+CAPI int clrsdp_op_lambda_min(clrsdp_handle h, int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lam) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!A || !lam) return (int)CLRSDP_ERR_BAD_ARG;
+    s.op_lambda_min(batch, n, A, lam);
+    return 0;
+  });
+}
+CAPI int clrsdp_op_elementwise(clrsdp_handle h, int op, const clrsdp_mp* a, const clrsdp_mp* b, clrsdp_mp_out* c) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!a || !c) return (int)CLRSDP_ERR_BAD_ARG;
+    s.op_elementwise(op, a, b, c);
+    return 0;
+  });
+}
+CAPI int clrsdp_comm_unique_id(uint8_t id[128]) {
+  (void)id;
+  return CLRSDP_ERR_NCCL;  // multi-GPU sharding arrives with SURVEY §8e; see DESIGN.md
+}
+CAPI int clrsdp_comm_init(clrsdp_handle h, int n_ranks, int rank, const uint8_t id[128]) {
+  (void)h, (void)n_ranks, (void)rank, (void)id;
+  return CLRSDP_ERR_NCCL;
+}
+CAPI int64_t clrsdp_launch_count(clrsdp_handle h) { return (h && h->s) ? h->s->ctx.launches : 0; }
+CAPI int clrsdp_profile_reset(clrsdp_handle h, int enable) {
+  return guard(h, [&](clr::Solver& s) {
+    s.ctx.resolve();
+    s.ctx.prof.clear();
+    s.ctx.profiling = enable != 0;
+    return 0;
+  });
+}
+CAPI int clrsdp_profile_query(clrsdp_handle h, const char* pattern, double* ms, int64_t* launches, double* work) {
+  return guard(h, [&](clr::Solver& s) {
+    s.ctx.resolve();
+    double t = 0, w = 0;
+    int64_t n = 0;
+    for (auto& kv : s.ctx.prof)
+      if (!pattern || kv.first.find(pattern) != std::string::npos) t += kv.second.ms, n += kv.second.launches, w += kv.second.work;
+    if (ms) *ms = t;
+    if (launches) *launches = n;
+    if (work) *work = w;
+    return 0;
+  });
+}

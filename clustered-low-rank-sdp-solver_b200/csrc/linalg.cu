@@ -1,0 +1,995 @@
+// linalg.cu — CUDA-core multiprecision kernels (see linalg.cuh). One thread owns one number in registers;
+// tensors are planar in HBM so that a warp's 32 numbers are one coalesced line per limb plane.
+#include "linalg.cuh"
+
+#include <algorithm>
+
+namespace clr {
+using mp::Num;
+
+#define DISPATCH_NL(nl, ...)                                  \
+  switch (nl) {                                               \
+    case 4: { constexpr int NL = 4; __VA_ARGS__; } break;     \
+    case 8: { constexpr int NL = 8; __VA_ARGS__; } break;     \
+    case 12: { constexpr int NL = 12; __VA_ARGS__; } break;   \
+    case 16: { constexpr int NL = 16; __VA_ARGS__; } break;   \
+    default: throw SolverError(-1, "unsupported precision");  \
+  }
+
+// Out-of-line wrappers: the latency-bound kernels below have dozens of call sites of the (fully unrolled)
+// limb loops; keeping each operation a real function keeps the code (and compile time) bounded. The
+// HBM-bound elementwise kernels keep the inlined versions.
+template <int NL> __device__ __noinline__ Num<NL> nadd(const Num<NL>& a, const Num<NL>& b) { return mp::add(a, b); }
+template <int NL> __device__ __noinline__ Num<NL> nsub(const Num<NL>& a, const Num<NL>& b) { return mp::sub(a, b); }
+template <int NL> __device__ __noinline__ Num<NL> nmul(const Num<NL>& a, const Num<NL>& b) { return mp::mul(a, b); }
+template <int NL> __device__ __noinline__ Num<NL> ndiv(const Num<NL>& a, const Num<NL>& b) { return mp::div(a, b); }
+template <int NL> __device__ __noinline__ Num<NL> nrecip(const Num<NL>& a) { return mp::recip(a); }
+template <int NL> __device__ __noinline__ Num<NL> nsqrt(const Num<NL>& a) { return mp::sqrt(a); }
+template <int NL> __device__ __noinline__ Num<NL> nsqrt_rsqrt(const Num<NL>& a, Num<NL>& r) { return mp::sqrt_rsqrt(a, r); }
+template <int NL> __device__ __noinline__ int ncmp(const Num<NL>& a, const Num<NL>& b) { return mp::cmp(a, b); }
+
+// =========================================================================================================
+// shared-memory / shuffle helpers for mp numbers
+// =========================================================================================================
+template <int NL>
+__device__ __forceinline__ void smem_put(uint32_t* s, int slot, const Num<NL>& x) {
+  uint32_t* p = s + (size_t)slot * (NL + 2);
+#pragma unroll
+  for (int k = 0; k < NL; k++) p[k] = x.m[k];
+  p[NL] = (uint32_t)x.e;
+  p[NL + 1] = x.neg;
+}
+template <int NL>
+__device__ __forceinline__ Num<NL> smem_get(const uint32_t* s, int slot) {
+  const uint32_t* p = s + (size_t)slot * (NL + 2);
+  Num<NL> x;
+#pragma unroll
+  for (int k = 0; k < NL; k++) x.m[k] = p[k];
+  x.e = (int32_t)p[NL];
+  x.neg = p[NL + 1];
+  return x;
+}
+template <int NL>
+__device__ __forceinline__ Num<NL> shfl_xor_num(const Num<NL>& v, int o) {
+  Num<NL> r;
+#pragma unroll
+  for (int k = 0; k < NL; k++) r.m[k] = __shfl_xor_sync(0xffffffffu, v.m[k], o);
+  r.e = __shfl_xor_sync(0xffffffffu, v.e, o);
+  r.neg = __shfl_xor_sync(0xffffffffu, v.neg, o);
+  return r;
+}
+enum { RED_ADD = 0, RED_MAX = 1, RED_MIN = 2 };
+template <int NL, int OP>
+__device__ __forceinline__ Num<NL> red_op(const Num<NL>& a, const Num<NL>& b) {
+  if (OP == RED_ADD) return nadd(a, b);
+  if (OP == RED_MAX) return ncmp(a, b) >= 0 ? a : b;
+  return ncmp(a, b) <= 0 ? a : b;
+}
+// block-wide reduction; the result is returned to every thread. scratch: 33*(NL+2) words.
+// Every thread of the block must call it (it contains __syncthreads).
+template <int NL, int OP>
+__device__ Num<NL> block_reduce(Num<NL> v, uint32_t* scratch) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
+#pragma unroll 1
+  for (int o = 16; o; o >>= 1) {
+    Num<NL> t = shfl_xor_num(v, o);
+    v = red_op<NL, OP>(v, t);
+  }
+  __syncthreads();
+  if (lane == 0) smem_put<NL>(scratch, warp, v);
+  __syncthreads();
+  if (warp == 0) {
+    // lanes beyond nwarp replicate slot 0 for max/min (idempotent) and contribute zero for add
+    Num<NL> z = smem_get<NL>(scratch, lane < nwarp ? lane : 0);
+    if (OP == RED_ADD && lane >= nwarp) z = mp::zero<NL>();
+#pragma unroll 1
+    for (int o = 16; o; o >>= 1) {
+      Num<NL> t = shfl_xor_num(z, o);
+      z = red_op<NL, OP>(z, t);
+    }
+    if (lane == 0) smem_put<NL>(scratch, 32, z);
+  }
+  __syncthreads();
+  return smem_get<NL>(scratch, 32);
+}
+template <int NL>
+__device__ __forceinline__ Num<NL> ldm(const mp::Tensor& t, int64_t i) { return mp::load<NL>(t.w, t.n, (size_t)i); }
+template <int NL>
+__device__ __forceinline__ void stm(const mp::Tensor& t, int64_t i, const Num<NL>& x) { mp::store<NL>(t.w, t.n, (size_t)i, x); }
+
+// =========================================================================================================
+// Cholesky (upper factor), one CTA per matrix, threads (column c, part)
+// =========================================================================================================
+template <int NL>
+__global__ void chol_kernel(mp::Tensor A, const int64_t* __restrict__ offA, mp::Tensor U,
+                            const int64_t* __restrict__ offU, mp::Tensor rdiag, int n, int* __restrict__ status) {
+  extern __shared__ uint32_t sm[];
+  __shared__ int bad;
+  const int b = blockIdx.x, c = threadIdx.x, part = threadIdx.y, P = blockDim.y;
+  const int64_t oa = offA[b], ou = offU[b];
+  if (threadIdx.x == 0 && threadIdx.y == 0) bad = 0;
+  // U <- upper triangle of A, zeros below
+  for (int r = part; r < n; r += P)
+    if (c < n) stm<NL>(U, ou + (int64_t)r * n + c, (r <= c) ? ldm<NL>(A, oa + (int64_t)r * n + c) : mp::zero<NL>());
+  __syncthreads();
+  for (int k = 0; k < n; k++) {
+    if (c == 0 && part == 0) {
+      Num<NL> a = ldm<NL>(U, ou + (int64_t)k * n + k);
+      if (mp::is_zero(a) || a.neg) {
+        bad = 1;
+      } else {
+        Num<NL> rinv;
+        Num<NL> d = nsqrt_rsqrt(a, rinv);
+        stm<NL>(U, ou + (int64_t)k * n + k, d);
+        stm<NL>(rdiag, (int64_t)b * n + k, rinv);
+        smem_put<NL>(sm, 0, rinv);
+      }
+    }
+    __syncthreads();
+    if (bad) break;
+    if (part == 0 && c > k && c < n) {
+      Num<NL> rinv = smem_get<NL>(sm, 0);
+      stm<NL>(U, ou + (int64_t)k * n + c, nmul(ldm<NL>(U, ou + (int64_t)k * n + c), rinv));
+    }
+    __syncthreads();
+    if (c > k && c < n) {
+      Num<NL> ukc = ldm<NL>(U, ou + (int64_t)k * n + c);
+      for (int r = k + 1 + part; r <= c; r += P) {
+        Num<NL> ukr = ldm<NL>(U, ou + (int64_t)k * n + r);
+        int64_t at = ou + (int64_t)r * n + c;
+        stm<NL>(U, at, nsub(ldm<NL>(U, at), nmul(ukr, ukc)));
+      }
+    }
+    __syncthreads();
+  }
+  if (c == 0 && part == 0) status[b] = bad;
+}
+
+// V = U^-1 (upper) by right-looking back substitution; Linv = V^T written alongside.
+template <int NL>
+__global__ void trinv_kernel(mp::Tensor U, const int64_t* __restrict__ offU, mp::Tensor rdiag, mp::Tensor V,
+                             const int64_t* __restrict__ offV, mp::Tensor Linv, const int64_t* __restrict__ offL,
+                             int n, int want_V) {
+  const int b = blockIdx.x, c = threadIdx.x, part = threadIdx.y, P = blockDim.y;
+  const int64_t ou = offU[b], ov = offV[b], ol = offL ? offL[b] : 0;
+  for (int r = part; r < n; r += P)
+    if (c < n) {
+      stm<NL>(V, ov + (int64_t)r * n + c, mp::zero<NL>());
+      if (offL && c > r) stm<NL>(Linv, ol + (int64_t)r * n + c, mp::zero<NL>());
+    }
+  __syncthreads();
+  for (int k = n - 1; k >= 0; k--) {
+    if (part == 0 && c >= k && c < n) {
+      Num<NL> acc = ldm<NL>(V, ov + (int64_t)k * n + c);
+      Num<NL> rk = ldm<NL>(rdiag, (int64_t)b * n + k);
+      Num<NL> v = (c == k) ? nsub(mp::one<NL>(), acc) : mp::neg(acc);
+      v = nmul(v, rk);
+      stm<NL>(V, ov + (int64_t)k * n + c, v);
+      if (offL) stm<NL>(Linv, ol + (int64_t)c * n + k, v);
+    }
+    __syncthreads();
+    if (c >= k && c < n) {
+      Num<NL> vkc = ldm<NL>(V, ov + (int64_t)k * n + c);
+      for (int i = part; i < k; i += P) {
+        Num<NL> uik = ldm<NL>(U, ou + (int64_t)i * n + k);
+        int64_t at = ov + (int64_t)i * n + c;
+        stm<NL>(V, at, nadd(ldm<NL>(V, at), nmul(uik, vkc)));
+      }
+    }
+    __syncthreads();
+  }
+  (void)want_V;
+}
+
+static dim3 tri_block(int n) {
+  int cx = ((n + 31) / 32) * 32;
+  cx = std::min(cx, 1024);
+  int p = std::max(1, 1024 / cx);
+  return dim3(cx, p, 1);
+}
+
+void chol_upper(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& U, mp::Tensor rdiag, int* d_status) {
+  if (A.n > 1024) throw SolverError(-1, "chol_upper: n > 1024 not supported");
+  dim3 blk = tri_block(A.n);
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("chol");
+    chol_kernel<NL><<<A.batch, blk, (NL + 2) * sizeof(uint32_t), ctx.stream>>>(A.t, A.d_off, U.t, U.d_off, rdiag, A.n,
+                                                                               d_status);
+    ctx.end(tk);
+  });
+}
+void tri_inverse(Ctx& ctx, int nl, const MatBatch& U, mp::Tensor rdiag, const MatBatch& V, const MatBatch* Linv) {
+  dim3 blk = tri_block(U.n);
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("trinv");
+    trinv_kernel<NL><<<U.batch, blk, 0, ctx.stream>>>(U.t, U.d_off, rdiag, V.t, V.d_off, Linv ? Linv->t : V.t,
+                                                      Linv ? Linv->d_off : nullptr, U.n, 1);
+    ctx.end(tk);
+  });
+}
+
+// =========================================================================================================
+// smallest eigenvalue of a symmetric matrix: Householder tridiagonalisation, then multisection with Sturm
+// counts + Newton polish on the characteristic polynomial
+// =========================================================================================================
+// number of sign changes in the Sturm sequence p_0..p_n of T - x I, stopped at the first one
+// (returns true iff at least one eigenvalue is < x)
+template <int NL>
+__device__ bool any_eig_below(const uint32_t* dsm, const uint32_t* e2sm, int n, const Num<NL>& x) {
+  Num<NL> p2 = mp::one<NL>();
+  Num<NL> p1 = nsub(smem_get<NL>(dsm, 0), x);
+  if (mp::is_zero(p1) || p1.neg) return true;
+  for (int i = 1; i < n; i++) {
+    Num<NL> a = nsub(smem_get<NL>(dsm, i), x);
+    Num<NL> p = nsub(nmul(a, p1), nmul(smem_get<NL>(e2sm, i - 1), p2));
+    if (mp::is_zero(p) || p.neg) return true;  // all previous p_i > 0, so this is the first sign change
+    p2 = p1;
+    p1 = p;
+    // rescale to keep exponents bounded
+    if (p1.e > (1 << 20) || p1.e < -(1 << 20)) {
+      p2.e -= p1.e;
+      p1.e = 0;
+    }
+  }
+  return false;
+}
+
+template <int NL>
+__global__ void lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Tensor out, int64_t out_off) {
+  extern __shared__ uint32_t sm[];
+  // smem layout (in Num slots of NL+2 words): v[n], q[n], d[n], e2[n], red[33], misc[8], partial[P*CX]
+  const int CX = blockDim.x, P = blockDim.y;
+  uint32_t* vsm = sm;
+  uint32_t* qsm = vsm + (size_t)n * (NL + 2);
+  uint32_t* dsm = qsm + (size_t)n * (NL + 2);
+  uint32_t* e2sm = dsm + (size_t)n * (NL + 2);
+  uint32_t* red = e2sm + (size_t)n * (NL + 2);
+  uint32_t* misc = red + 33 * (NL + 2);
+  uint32_t* part_sm = misc + 8 * (NL + 2);
+  __shared__ int flag, first_t;
+  const int b = blockIdx.x, c = threadIdx.x, part = threadIdx.y;
+  const int tid = part * CX + c, nthr = CX * P;
+  const int64_t ow = offW[b];
+  auto Wat = [&](int r, int cc) { return ow + (int64_t)r * n + cc; };
+
+  if (n == 1) {
+    if (tid == 0) stm<NL>(out, out_off + b, ldm<NL>(W, ow));
+    return;
+  }
+  // ---- Householder tridiagonalisation (symmetric full storage, both triangles kept up to date) ----
+  for (int k = 0; k + 2 < n; k++) {
+    Num<NL> xc = mp::zero<NL>();
+    if (part == 0 && c > k && c < n) xc = ldm<NL>(W, Wat(k, c));
+    Num<NL> sq = (part == 0 && c > k + 1 && c < n) ? nmul(xc, xc) : mp::zero<NL>();
+    Num<NL> tail = block_reduce<NL, RED_ADD>(sq, red);
+    if (tid == 0) {
+      Num<NL> x1 = ldm<NL>(W, Wat(k, k + 1));
+      if (mp::is_zero(tail)) {
+        flag = 1;  // column already tridiagonal
+        smem_put<NL>(e2sm, k, nmul(x1, x1));
+      } else {
+        flag = 0;
+        Num<NL> sigma = nadd(tail, nmul(x1, x1));
+        Num<NL> alpha = nsqrt(sigma);
+        if (!x1.neg) alpha = mp::neg(alpha);
+        Num<NL> beta = mp::mul_2exp(nsub(sigma, nmul(alpha, x1)), 1);  // v^T v
+        Num<NL> binv = nrecip(beta);
+        smem_put<NL>(misc, 0, alpha);
+        smem_put<NL>(misc, 1, binv);
+        smem_put<NL>(e2sm, k, sigma);  // alpha^2
+      }
+    }
+    __syncthreads();
+    if (flag) continue;
+    if (part == 0 && c > k && c < n) {
+      Num<NL> v = xc;
+      if (c == k + 1) v = nsub(v, smem_get<NL>(misc, 0));
+      smem_put<NL>(vsm, c, v);
+    }
+    __syncthreads();
+    // p = 2/beta * A v  (restricted to the trailing block), partial sums over row parts
+    if (c > k && c < n) {
+      Num<NL> acc = mp::zero<NL>();
+      for (int j = k + 1 + part; j < n; j += P) acc = nadd(acc, nmul(ldm<NL>(W, Wat(j, c)), smem_get<NL>(vsm, j)));
+      smem_put<NL>(part_sm, part * CX + c, acc);
+    }
+    __syncthreads();
+    Num<NL> pc = mp::zero<NL>(), vc = mp::zero<NL>();
+    if (part == 0 && c > k && c < n) {
+      for (int q = 0; q < P; q++) pc = nadd(pc, smem_get<NL>(part_sm, q * CX + c));
+      pc = mp::mul_2exp(nmul(pc, smem_get<NL>(misc, 1)), 1);
+      vc = smem_get<NL>(vsm, c);
+    }
+    Num<NL> vp = block_reduce<NL, RED_ADD>(nmul(vc, pc), red);
+    if (part == 0 && c > k && c < n) {
+      Num<NL> Kc = nmul(vp, smem_get<NL>(misc, 1));  // v^T p / beta
+      smem_put<NL>(qsm, c, nsub(pc, nmul(Kc, vc)));
+    }
+    __syncthreads();
+    if (c > k && c < n) {
+      Num<NL> qc = smem_get<NL>(qsm, c), vcc = smem_get<NL>(vsm, c);
+      for (int j = k + 1 + part; j < n; j += P) {
+        Num<NL> upd = nadd(nmul(smem_get<NL>(vsm, j), qc), nmul(smem_get<NL>(qsm, j), vcc));
+        int64_t at = Wat(j, c);
+        stm<NL>(W, at, nsub(ldm<NL>(W, at), upd));
+      }
+    }
+    __syncthreads();
+  }
+  // diagonal and squared sub-diagonal of the tridiagonal matrix
+  for (int i = tid; i < n; i += nthr) smem_put<NL>(dsm, i, ldm<NL>(W, Wat(i, i)));
+  if (tid == 0) {
+    Num<NL> x1 = ldm<NL>(W, Wat(n - 2, n - 1));
+    smem_put<NL>(e2sm, n - 2, nmul(x1, x1));
+  }
+  __syncthreads();
+  // ---- Gershgorin interval (thread 0) ----
+  if (tid == 0) {
+    Num<NL> lo = mp::zero<NL>(), hi = mp::zero<NL>(), nrm = mp::zero<NL>();
+    for (int i = 0; i < n; i++) {
+      Num<NL> rad = mp::zero<NL>();
+      if (i > 0) rad = nadd(rad, nsqrt(smem_get<NL>(e2sm, i - 1)));
+      if (i + 1 < n) rad = nadd(rad, nsqrt(smem_get<NL>(e2sm, i)));
+      Num<NL> di = smem_get<NL>(dsm, i);
+      Num<NL> a1 = nsub(di, rad), a2 = nadd(di, rad);
+      if (i == 0 || ncmp(a1, lo) < 0) lo = a1;
+      if (i == 0 || ncmp(a2, hi) > 0) hi = a2;
+    }
+    nrm = mp::cmp_abs(lo, hi) > 0 ? mp::fabs(lo) : mp::fabs(hi);
+    Num<NL> pad = mp::mul_2exp(nrm, -20);
+    if (mp::is_zero(nrm)) pad = mp::from_pow2<NL>(-1000);
+    smem_put<NL>(misc, 2, nsub(lo, pad));
+    smem_put<NL>(misc, 3, nadd(hi, pad));
+    smem_put<NL>(misc, 4, nrm);
+    flag = 0;
+  }
+  __syncthreads();
+  int Tp = 1, lg = 0;
+  while (Tp * 2 <= nthr) Tp *= 2, lg++;
+  bool newton_allowed = true;
+  // invariant: no eigenvalue below lo, at least one below hi
+  for (int round = 0; round < 200; round++) {
+    Num<NL> lo = smem_get<NL>(misc, 2), hi = smem_get<NL>(misc, 3);
+    Num<NL> width = nsub(hi, lo);
+    Num<NL> scale = mp::cmp_abs(lo, hi) > 0 ? mp::fabs(lo) : mp::fabs(hi);
+    // converged when the interval is below 2^-(p-3) relative (or cannot shrink any more)
+    if (mp::is_zero(width) || width.neg || width.e <= scale.e - (32 * NL - 3)) break;
+    bool narrow_enough = width.e <= scale.e - 40;
+    if (narrow_enough && newton_allowed) {
+      // ---- Newton from the left end on p_n(x) = det(T - xI): monotone, quadratic for a simple root ----
+      if (tid == 0) {
+        Num<NL> x = lo;
+        int ok = 0;
+        for (int it = 0; it < 10; it++) {
+          Num<NL> p2 = mp::one<NL>(), dp2 = mp::zero<NL>();
+          Num<NL> p1 = nsub(smem_get<NL>(dsm, 0), x), dp1 = mp::neg(mp::one<NL>());
+          for (int i = 1; i < n; i++) {
+            Num<NL> a = nsub(smem_get<NL>(dsm, i), x), e2 = smem_get<NL>(e2sm, i - 1);
+            Num<NL> p = nsub(nmul(a, p1), nmul(e2, p2));
+            Num<NL> dp = nsub(nsub(nmul(a, dp1), p1), nmul(e2, dp2));
+            p2 = p1, dp2 = dp1, p1 = p, dp1 = dp;
+            if (p1.e > (1 << 20) || p1.e < -(1 << 20)) {
+              int s = p1.e;
+              p1.e -= s;
+              if (!mp::is_zero(p2)) p2.e -= s;
+              if (!mp::is_zero(dp1)) dp1.e -= s;
+              if (!mp::is_zero(dp2)) dp2.e -= s;
+            }
+          }
+          if (mp::is_zero(p1)) { ok = 1; break; }
+          if (mp::is_zero(dp1)) break;
+          Num<NL> step = ndiv(p1, dp1);  // x_new = x - p/p'
+          Num<NL> xn = nsub(x, step);
+          if (ncmp(xn, x) < 0 || ncmp(xn, hi) > 0) break;  // left the bracket: not the simple-root regime
+          bool tiny = mp::is_zero(step) || step.e <= xn.e - (32 * NL - 6);
+          x = xn;
+          if (tiny) { ok = 1; break; }
+        }
+        if (ok) {
+          // verify: there must be an eigenvalue below x(1 + 2^-(p-8))
+          Num<NL> eps = mp::mul_2exp(mp::fabs(x), -(32 * NL - 8));
+          if (mp::is_zero(eps)) eps = mp::mul_2exp(smem_get<NL>(misc, 4), -(32 * NL));
+          Num<NL> xu = nadd(x, eps), xl = nsub(x, eps);
+          if (any_eig_below<NL>(dsm, e2sm, n, xu) && !any_eig_below<NL>(dsm, e2sm, n, xl)) {
+            smem_put<NL>(misc, 2, x);
+            smem_put<NL>(misc, 3, x);
+            flag = 2;
+          } else {
+            flag = 1;
+          }
+        } else {
+          flag = 1;
+        }
+      }
+      __syncthreads();
+      int f = flag;
+      __syncthreads();
+      if (f == 2) break;
+      newton_allowed = false;
+      continue;
+    }
+    // ---- one multisection round: Tp probes, keep the first sub-interval that contains an eigenvalue ----
+    if (tid == 0) first_t = Tp - 1;
+    __syncthreads();
+    Num<NL> w = mp::mul_2exp(width, -lg);
+    Num<NL> xt = hi;
+    if (tid < Tp - 1) {
+      xt = nadd(lo, nmul(w, mp::from_int<NL>(tid + 1)));
+      if (any_eig_below<NL>(dsm, e2sm, n, xt)) atomicMin(&first_t, tid);
+    }
+    __syncthreads();
+    int ft = first_t;
+    if (tid == ft) smem_put<NL>(misc, 3, xt);
+    if (ft > 0 && tid == ft - 1) smem_put<NL>(misc, 2, xt);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    Num<NL> lo = smem_get<NL>(misc, 2), hi = smem_get<NL>(misc, 3);
+    stm<NL>(out, out_off + b, mp::mul_2exp(nadd(lo, hi), -1));
+  }
+}
+
+size_t lambda_min_work_elems(int, int) { return 1; }
+void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, int64_t out_off, mp::Tensor) {
+  if (W.n > 512) throw SolverError(-1, "lambda_min: n > 512 not supported");
+  int cx = std::min(1024, ((W.n + 31) / 32) * 32);
+  int P = std::max(1, 512 / cx);
+  dim3 blk(cx, P, 1);
+  DISPATCH_NL(nl, {
+    size_t words = (size_t)(4 * W.n + 33 + 8 + P * cx) * (NL + 2);
+    static bool attr[17] = {false};
+    if (!attr[NL]) {
+      CLR_CUDA(cudaFuncSetAttribute(lambda_min_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr[NL] = true;
+    }
+    int tk = ctx.begin("lambda_min");
+    lambda_min_kernel<NL><<<W.batch, blk, words * sizeof(uint32_t), ctx.stream>>>(W.t, W.d_off, W.n, out, out_off);
+    ctx.end(tk);
+  });
+}
+
+// =========================================================================================================
+// elementwise kernels
+// =========================================================================================================
+template <int NL>
+__global__ void lincomb_kernel(mp::Tensor out, int64_t oo, mp::Tensor a, int64_t ao, int sa, mp::Tensor b, int64_t bo,
+                               int sb, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    Num<NL> r = mp::zero<NL>();
+    if (sa) {
+      r = ldm<NL>(a, ao + i);
+      if (sa < 0) r = mp::neg(r);
+    }
+    if (sb) {
+      Num<NL> y = ldm<NL>(b, bo + i);
+      r = sb > 0 ? mp::add(r, y) : mp::sub(r, y);
+    }
+    stm<NL>(out, oo + i, r);
+  }
+}
+template <int NL>
+__global__ void axpy_kernel(mp::Tensor y, int64_t yo, mp::Tensor x, int64_t xo, mp::Tensor scal, int slot, int64_t n) {
+  Num<NL> s = ldm<NL>(scal, slot);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    stm<NL>(y, yo + i, mp::add(ldm<NL>(y, yo + i), mp::mul(s, ldm<NL>(x, xo + i))));
+}
+// per-block kernels: thread per element of a batch of n x n blocks
+template <int NL>
+__global__ void residual_R_kernel(mp::Tensor R, const int64_t* __restrict__ off, int batch, int n, mp::Tensor scal,
+                                  int slot, mp::Tensor T1, mp::Tensor T2, int has2) {
+  Num<NL> s = ldm<NL>(scal, slot);
+  int64_t total = (int64_t)batch * n * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / ((int64_t)n * n));
+    int rem = (int)(idx % ((int64_t)n * n));
+    int i = rem / n, j = rem % n;
+    int64_t at = off[b] + rem;
+    Num<NL> r = (i == j) ? s : mp::zero<NL>();
+    r = mp::sub(r, ldm<NL>(T1, at));
+    if (has2) r = mp::sub(r, ldm<NL>(T2, at));
+    stm<NL>(R, at, r);
+  }
+}
+template <int NL>
+__global__ void symmetrize_kernel(mp::Tensor out, const int64_t* __restrict__ off, int batch, int n, mp::Tensor in) {
+  int64_t total = (int64_t)batch * n * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / ((int64_t)n * n));
+    int rem = (int)(idx % ((int64_t)n * n));
+    int i = rem / n, j = rem % n;
+    if (i > j) continue;
+    int64_t o = off[b];
+    Num<NL> r = mp::mul_2exp(mp::add(ldm<NL>(in, o + (int64_t)i * n + j), ldm<NL>(in, o + (int64_t)j * n + i)), -1);
+    stm<NL>(out, o + (int64_t)i * n + j, r);
+    if (i != j) stm<NL>(out, o + (int64_t)j * n + i, r);
+  }
+}
+template <int NL>
+__global__ void set_identity_kernel(mp::Tensor M, const int64_t* __restrict__ off, int batch, int n, mp::Tensor scal,
+                                    int slot) {
+  Num<NL> s = ldm<NL>(scal, slot);
+  int64_t total = (int64_t)batch * n * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / ((int64_t)n * n));
+    int rem = (int)(idx % ((int64_t)n * n));
+    stm<NL>(M, off[b] + rem, (rem / n == rem % n) ? s : mp::zero<NL>());
+  }
+}
+static int ew_grid(Ctx& ctx, int64_t n, int threads = 128) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, threads), (int64_t)ctx.sm_count * 32));
+}
+void ew_lincomb(Ctx& ctx, int nl, mp::Tensor out, int64_t oo, mp::Tensor a, int64_t ao, int sa, mp::Tensor b,
+                int64_t bo, int sb, int64_t n) {
+  if (n <= 0) return;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("ew_lincomb", (double)n * 4.0 * (NL + 1) * (1 + (sa != 0) + (sb != 0)));
+    lincomb_kernel<NL><<<ew_grid(ctx, n), 128, 0, ctx.stream>>>(out, oo, a, ao, sa, b, bo, sb, n);
+    ctx.end(tk);
+  });
+}
+template <int NL>
+__global__ void binary_kernel(int op, mp::Tensor c, mp::Tensor a, mp::Tensor b, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    Num<NL> x = ldm<NL>(a, i), y = ldm<NL>(b, i), z;
+    switch (op) {
+      case '+': z = mp::add(x, y); break;
+      case '-': z = mp::sub(x, y); break;
+      case '*': z = mp::mul(x, y); break;
+      case '/': z = mp::div(x, y); break;
+      default: z = mp::sqrt(x); break;
+    }
+    stm<NL>(c, i, z);
+  }
+}
+void ew_binary(Ctx& ctx, int nl, int op, mp::Tensor c, mp::Tensor a, mp::Tensor b, int64_t n) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("ew_binary");
+    binary_kernel<NL><<<ew_grid(ctx, n), 128, 0, ctx.stream>>>(op, c, a, b, n);
+    ctx.end(tk);
+  });
+}
+void ew_zero(Ctx& ctx, int nl, mp::Tensor t, int64_t off, int64_t n) { ew_lincomb(ctx, nl, t, off, t, off, 0, t, off, 0, n); }
+void ew_axpy(Ctx& ctx, int nl, mp::Tensor y, int64_t yo, mp::Tensor x, int64_t xo, mp::Tensor scal, int slot,
+             int64_t n) {
+  if (n <= 0) return;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("ew_axpy", (double)n * 4.0 * (NL + 1) * 3);
+    axpy_kernel<NL><<<ew_grid(ctx, n), 128, 0, ctx.stream>>>(y, yo, x, xo, scal, slot, n);
+    ctx.end(tk);
+  });
+}
+void ew_residual_R(Ctx& ctx, int nl, const MatBatch& R, mp::Tensor scal, int slot, mp::Tensor T1, const mp::Tensor* T2) {
+  int64_t total = (int64_t)R.batch * R.n * R.n;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("ew_residual_R", (double)total * 4.0 * (NL + 1) * (T2 ? 3 : 2));
+    residual_R_kernel<NL><<<ew_grid(ctx, total), 128, 0, ctx.stream>>>(R.t, R.d_off, R.batch, R.n, scal, slot, T1,
+                                                                       T2 ? *T2 : T1, T2 ? 1 : 0);
+    ctx.end(tk);
+  });
+}
+void ew_symmetrize(Ctx& ctx, int nl, const MatBatch& out, mp::Tensor in) {
+  int64_t total = (int64_t)out.batch * out.n * out.n;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("ew_symmetrize", (double)total * 4.0 * (NL + 1) * 2);
+    symmetrize_kernel<NL><<<ew_grid(ctx, total), 128, 0, ctx.stream>>>(out.t, out.d_off, out.batch, out.n, in);
+    ctx.end(tk);
+  });
+}
+void ew_set_identity(Ctx& ctx, int nl, const MatBatch& M, mp::Tensor scal, int slot) {
+  int64_t total = (int64_t)M.batch * M.n * M.n;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("ew_set_identity");
+    set_identity_kernel<NL><<<ew_grid(ctx, total), 128, 0, ctx.stream>>>(M.t, M.d_off, M.batch, M.n, scal, slot);
+    ctx.end(tk);
+  });
+}
+
+// =========================================================================================================
+// reductions: grid-stride partials -> one partial per CTA -> final CTA
+// =========================================================================================================
+constexpr int RED_BLOCKS = 592;  // 4 CTAs per SM on 148 SMs
+size_t reduce_work_elems() { return RED_BLOCKS; }
+enum { RK_DOT = 0, RK_DOT_SUM = 1, RK_MAXABS = 2, RK_MIN = 3, RK_SUM = 4 };
+
+template <int NL, int KIND>
+__global__ void reduce_stage1(mp::Tensor a, int64_t ao, mp::Tensor da, mp::Tensor b, int64_t bo, mp::Tensor db,
+                              int64_t n, mp::Tensor work) {
+  extern __shared__ uint32_t sm[];
+  constexpr int OP = (KIND == RK_MAXABS) ? RED_MAX : (KIND == RK_MIN ? RED_MIN : RED_ADD);
+  Num<NL> acc = mp::zero<NL>();
+  bool have = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    Num<NL> v;
+    if (KIND == RK_DOT) v = nmul(ldm<NL>(a, ao + i), ldm<NL>(b, bo + i));
+    if (KIND == RK_DOT_SUM)
+      v = nmul(nadd(ldm<NL>(a, ao + i), ldm<NL>(da, ao + i)), nadd(ldm<NL>(b, bo + i), ldm<NL>(db, bo + i)));
+    if (KIND == RK_MAXABS) v = mp::fabs(ldm<NL>(a, ao + i));
+    if (KIND == RK_MIN || KIND == RK_SUM) v = ldm<NL>(a, ao + i);
+    if (KIND == RK_MIN)
+      acc = have ? red_op<NL, OP>(acc, v) : v;
+    else
+      acc = red_op<NL, OP>(acc, v);
+    have = true;
+  }
+  if (KIND == RK_MIN) {
+    // threads without data must not inject a zero: borrow the value of element 0 (idempotent for min)
+    if (!have) acc = ldm<NL>(a, ao);
+  }
+  Num<NL> r = block_reduce<NL, OP>(acc, sm);
+  if (threadIdx.x == 0) stm<NL>(work, blockIdx.x, r);
+}
+template <int NL, int OP>
+__global__ void reduce_stage2(mp::Tensor work, int nparts, mp::Tensor scal, int slot) {
+  extern __shared__ uint32_t sm[];
+  Num<NL> acc = ldm<NL>(work, threadIdx.x < nparts ? threadIdx.x : 0);
+  if (OP == RED_ADD && threadIdx.x >= nparts) acc = mp::zero<NL>();
+  for (int i = threadIdx.x + blockDim.x; i < nparts; i += blockDim.x) acc = red_op<NL, OP>(acc, ldm<NL>(work, i));
+  Num<NL> r = block_reduce<NL, OP>(acc, sm);
+  if (threadIdx.x == 0) stm<NL>(scal, slot, r);
+}
+template <int NL, int KIND>
+static void reduce_launch(Ctx& ctx, mp::Tensor a, int64_t ao, mp::Tensor da, mp::Tensor b, int64_t bo, mp::Tensor db,
+                          int64_t n, mp::Tensor scal, int slot, mp::Tensor work, const char* name, int nin) {
+  constexpr int OP = (KIND == RK_MAXABS) ? RED_MAX : (KIND == RK_MIN ? RED_MIN : RED_ADD);
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(RED_BLOCKS, ceil_div(n, 128)));
+  size_t smem = 33 * (NL + 2) * sizeof(uint32_t);
+  int tk = ctx.begin(name, (double)n * 4.0 * (NL + 1) * nin);
+  reduce_stage1<NL, KIND><<<grid, 128, smem, ctx.stream>>>(a, ao, da, b, bo, db, n, work);
+  ctx.end(tk);
+  tk = ctx.begin("reduce_final");
+  reduce_stage2<NL, OP><<<1, 256, smem, ctx.stream>>>(work, grid, scal, slot);
+  ctx.end(tk);
+}
+void reduce_dot(Ctx& ctx, int nl, mp::Tensor a, int64_t ao, mp::Tensor b, int64_t bo, int64_t n, mp::Tensor scal,
+                int slot, mp::Tensor work) {
+  DISPATCH_NL(nl, (reduce_launch<NL, RK_DOT>(ctx, a, ao, a, b, bo, b, n, scal, slot, work, "reduce_dot", 2)));
+}
+void reduce_dot_sum(Ctx& ctx, int nl, mp::Tensor a, mp::Tensor da, mp::Tensor b, mp::Tensor db, int64_t n,
+                    mp::Tensor scal, int slot, mp::Tensor work) {
+  DISPATCH_NL(nl, (reduce_launch<NL, RK_DOT_SUM>(ctx, a, 0, da, b, 0, db, n, scal, slot, work, "reduce_dot_sum", 4)));
+}
+void reduce_maxabs(Ctx& ctx, int nl, mp::Tensor a, int64_t ao, int64_t n, mp::Tensor scal, int slot, mp::Tensor work) {
+  DISPATCH_NL(nl, (reduce_launch<NL, RK_MAXABS>(ctx, a, ao, a, a, 0, a, n, scal, slot, work, "reduce_maxabs", 1)));
+}
+void reduce_min(Ctx& ctx, int nl, mp::Tensor a, int64_t ao, int64_t n, mp::Tensor scal, int slot, mp::Tensor work) {
+  DISPATCH_NL(nl, (reduce_launch<NL, RK_MIN>(ctx, a, ao, a, a, 0, a, n, scal, slot, work, "reduce_min", 1)));
+}
+
+// =========================================================================================================
+// GEMV: one warp per (row, K-part); lanes stride K; partials summed by a second kernel when K is split
+// =========================================================================================================
+struct GemvDev {
+  mp::Tensor A, x, out, work;
+  int64_t a0, x0, oo, rs, ks;
+  int rows, K, nparts;
+  const int* row_item;
+  const int64_t* aoff;
+  const int64_t* xoff;
+  const int* row0;
+  const int* itemK;
+  int item_trans;
+};
+template <int NL>
+__global__ void gemv_kernel(GemvDev g) {
+  int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= g.rows * g.nparts) return;
+  int r = warp / g.nparts, part = warp % g.nparts;
+  int64_t ab = g.a0, xb = g.x0;
+  int rl = r, K = g.K;
+  int64_t rs = g.rs, ks = g.ks;
+  if (g.row_item) {
+    int it = g.row_item[r];
+    ab = g.aoff[it];
+    xb = g.xoff[it];
+    rl = r - g.row0[it];
+    K = g.itemK[it];
+    rs = g.item_trans ? 1 : K;
+    ks = g.item_trans ? K : 1;
+  }
+  int chunk = (K + g.nparts - 1) / g.nparts;
+  int k0 = part * chunk, k1 = min(K, k0 + chunk);
+  Num<NL> acc = mp::zero<NL>();
+  for (int k = k0 + lane; k < k1; k += 32)
+    acc = nadd(acc, nmul(ldm<NL>(g.A, ab + (int64_t)rl * rs + (int64_t)k * ks), ldm<NL>(g.x, xb + k)));
+#pragma unroll 1
+  for (int o = 16; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
+  if (lane == 0) {
+    if (g.nparts == 1)
+      stm<NL>(g.out, g.oo + r, acc);
+    else
+      stm<NL>(g.work, (int64_t)part * g.rows + r, acc);
+  }
+}
+template <int NL>
+__global__ void gemv_sum_kernel(GemvDev g) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= g.rows) return;
+  Num<NL> acc = mp::zero<NL>();
+  for (int p = 0; p < g.nparts; p++) acc = nadd(acc, ldm<NL>(g.work, (int64_t)p * g.rows + r));
+  stm<NL>(g.out, g.oo + r, acc);
+}
+static int gemv_parts(int rows, int K) {
+  if ((int64_t)rows >= 148 * 8 || K <= 256) return 1;
+  int p = std::min(ceil_div(K, 128), ceil_div(148 * 16, std::max(rows, 1)));
+  return std::max(1, p);
+}
+size_t gemv_work_elems(int rows, int K) { return (size_t)rows * gemv_parts(rows, K); }
+void gemv(Ctx& ctx, int nl, const GemvArgs& a, mp::Tensor work) {
+  if (a.rows <= 0) return;
+  GemvDev g{a.A, a.x, a.out, work, a.a0, a.x0, a.oo, a.rs, a.ks, a.rows, a.K, 1, a.d_row_item, a.d_aoff, a.d_xoff,
+            a.d_row0, a.d_K, a.item_trans};
+  g.nparts = a.d_row_item ? 1 : gemv_parts(a.rows, a.K);
+  DISPATCH_NL(nl, {
+    int64_t warps = (int64_t)a.rows * g.nparts;
+    int tk = ctx.begin("gemv", (double)a.rows * a.K * 4.0 * (NL + 1));
+    gemv_kernel<NL><<<ceil_div(warps * 32, 128), 128, 0, ctx.stream>>>(g);
+    ctx.end(tk);
+    if (g.nparts > 1) {
+      tk = ctx.begin("gemv_sum");
+      gemv_sum_kernel<NL><<<ceil_div(a.rows, 128), 128, 0, ctx.stream>>>(g);
+      ctx.end(tk);
+    }
+  });
+}
+
+// =========================================================================================================
+// structure-aware kernels
+// =========================================================================================================
+__device__ __forceinline__ void tri_decode(int pr, int& r, int& s) {  // pr = s + r(r+1)/2, s <= r
+  r = 0;
+  while ((r + 1) * (r + 2) / 2 <= pr) r++;
+  s = pr - r * (r + 1) / 2;
+}
+
+// thread per (cluster, ver, hor) with ver <= hor
+template <int NL>
+__global__ void schur_kernel(StructTables st, mp::Tensor Px, mp::Tensor Py, mp::Tensor H, mp::Tensor S, int64_t total,
+                             const int* __restrict__ task_cluster_start) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    // find the cluster by binary search over the prefix of dimS^2 (c_Soff)
+    int lo = 0, hi = st.J - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (st.c_Soff[mid] <= idx) lo = mid; else hi = mid - 1;
+    }
+    const int j = lo;
+    const int dimS = st.c_dimS[j], K = st.c_K[j], m = st.c_m[j];
+    int64_t rem = idx - st.c_Soff[j];
+    int ver = (int)(rem / dimS), hor = (int)(rem % dimS);
+    if (ver > hor) continue;
+    int r1, s1, r2, s2;
+    tri_decode(hor / K, r1, s1);
+    tri_decode(ver / K, r2, s2);
+    int k1 = hor % K, k2 = ver % K;
+    Num<NL> acc = mp::zero<NL>();
+    for (int l = 0; l < st.c_L[j]; l++) {
+      int bk = st.c_blk0[j] + l;
+      int Nv = st.b_Nv[bk];
+      const int* rsum = st.rank_sums + st.b_rs0[bk];
+      int64_t po = st.b_Poff[bk], ho = st.b_Hoff[bk];
+      int ld = m * Nv;
+      for (int a1 = rsum[k1]; a1 < rsum[k1 + 1]; a1++)
+        for (int a2 = rsum[k2]; a2 < rsum[k2 + 1]; a2++) {
+          int r1s = a1 + Nv * r1, r2s = a2 + Nv * r2, s1s = a1 + Nv * s1, s2s = a2 + Nv * s2;
+          Num<NL> tot;
+          if (m == 1) {
+            // all four terms coincide (MPMP.jl:1373-1392 with r=s): tot = 4 Px[a1][a2] Py[a2][a1]
+            tot = mp::mul_2exp(nmul(ldm<NL>(Px, po + (int64_t)a1 * ld + a2), ldm<NL>(Py, po + (int64_t)a2 * ld + a1)), 2);
+          } else {
+            tot = nmul(ldm<NL>(Px, po + (int64_t)s1s * ld + r2s), ldm<NL>(Py, po + (int64_t)s2s * ld + r1s));
+            tot = nadd(tot, nmul(ldm<NL>(Px, po + (int64_t)r1s * ld + r2s), ldm<NL>(Py, po + (int64_t)s2s * ld + s1s)));
+            tot = nadd(tot, nmul(ldm<NL>(Px, po + (int64_t)s1s * ld + s2s), ldm<NL>(Py, po + (int64_t)r2s * ld + r1s)));
+            tot = nadd(tot, nmul(ldm<NL>(Px, po + (int64_t)r1s * ld + s2s), ldm<NL>(Py, po + (int64_t)r2s * ld + s1s)));
+          }
+          tot = nmul(ldm<NL>(H, ho + a1), tot);
+          tot = nmul(ldm<NL>(H, ho + a2), tot);
+          acc = nadd(acc, mp::mul_2exp(tot, -2));
+        }
+    }
+    int64_t so = st.c_Soff[j];
+    stm<NL>(S, so + (int64_t)ver * dimS + hor, acc);
+    if (ver != hor) stm<NL>(S, so + (int64_t)hor * dimS + ver, acc);
+  }
+  (void)task_cluster_start;
+}
+void schur_assemble(Ctx& ctx, int nl, const StructTables& st, mp::Tensor Px, mp::Tensor Py, mp::Tensor H, mp::Tensor S,
+                    int64_t S_total) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("schur_assemble", (double)S_total * 4.0 * (NL + 1) * 2.0);
+    schur_kernel<NL><<<ew_grid(ctx, S_total), 128, 0, ctx.stream>>>(st, Px, Py, H, S, S_total, nullptr);
+    ctx.end(tk);
+  });
+}
+
+// thread per x entry (j, r, s, k)
+template <int NL, int MODE>
+__global__ void trace_kernel(StructTables st, mp::Tensor A, mp::Tensor B, mp::Tensor H, mp::Tensor out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st.sumS) return;
+  int j = st.x_cluster[i];
+  int K = st.c_K[j], m = st.c_m[j];
+  int loc = i - st.c_xoff[j];
+  int r, s;
+  tri_decode(loc / K, r, s);
+  int k = loc % K;
+  Num<NL> acc = mp::zero<NL>();
+  for (int l = 0; l < st.c_L[j]; l++) {
+    int bk = st.c_blk0[j] + l;
+    int Nv = st.b_Nv[bk], dl = st.b_delta[bk];
+    const int* rsum = st.rank_sums + st.b_rs0[bk];
+    int64_t ho = st.b_Hoff[bk];
+    for (int a = rsum[k]; a < rsum[k + 1]; a++) {
+      Num<NL> val;
+      if (MODE == 0) {  // from pairings: Py[(r,a),(s,a)]
+        int ld = m * Nv;
+        val = ldm<NL>(A, st.b_Poff[bk] + (int64_t)(r * Nv + a) * ld + (s * Nv + a));
+      } else {  // sum_i Vt[a][i] * Tt[(r*m+s)*Nv + a][i]
+        int64_t vo = st.b_Voff[bk] + (int64_t)a * dl, to = st.b_Toff[bk] + ((int64_t)(r * m + s) * Nv + a) * dl;
+        val = mp::zero<NL>();
+        for (int q = 0; q < dl; q++) val = nadd(val, nmul(ldm<NL>(A, vo + q), ldm<NL>(B, to + q)));
+      }
+      acc = nadd(acc, nmul(ldm<NL>(H, ho + a), val));
+    }
+  }
+  stm<NL>(out, i, acc);
+}
+void trace_from_pairings(Ctx& ctx, int nl, const StructTables& st, mp::Tensor Py, mp::Tensor H, mp::Tensor out) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("trace_pairings");
+    trace_kernel<NL, 0><<<ceil_div(st.sumS, 128), 128, 0, ctx.stream>>>(st, Py, Py, H, out);
+    ctx.end(tk);
+  });
+}
+void trace_from_ZV(Ctx& ctx, int nl, const StructTables& st, mp::Tensor Vt, mp::Tensor Tt, mp::Tensor H, mp::Tensor out) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("trace_ZV");
+    trace_kernel<NL, 1><<<ceil_div(st.sumS, 64), 64, 0, ctx.stream>>>(st, Vt, Tt, H, out);
+    ctx.end(tk);
+  });
+}
+
+// thread per VD element: VD[blk][pair][i][v]
+template <int NL>
+__global__ void scale_vectors_kernel(StructTables st, mp::Tensor Vt, mp::Tensor H, mp::Tensor a, mp::Tensor VD,
+                                     int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = st.n_blocks - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (st.b_VDoff[mid] <= idx) lo = mid; else hi = mid - 1;
+    }
+    int bk = lo, j = st.b_cluster[bk];
+    int Nv = st.b_Nv[bk], dl = st.b_delta[bk], K = st.c_K[j];
+    int64_t rem = idx - st.b_VDoff[bk];
+    int v = (int)(rem % Nv);
+    int i = (int)((rem / Nv) % dl);
+    int pair = (int)(rem / ((int64_t)Nv * dl));
+    int k = st.samp[st.b_Hoff[bk] + v];
+    Num<NL> w = nmul(ldm<NL>(a, st.c_xoff[j] + pair * K + k), ldm<NL>(H, st.b_Hoff[bk] + v));
+    stm<NL>(VD, idx, nmul(w, ldm<NL>(Vt, st.b_Voff[bk] + (int64_t)v * dl + i)));
+  }
+}
+void scale_vectors(Ctx& ctx, int nl, const StructTables& st, mp::Tensor Vt, mp::Tensor H, mp::Tensor a, mp::Tensor VD,
+                   int64_t VD_total) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("scale_vectors", (double)VD_total * 4.0 * (NL + 1) * 2.0);
+    scale_vectors_kernel<NL><<<ew_grid(ctx, VD_total), 128, 0, ctx.stream>>>(st, Vt, H, a, VD, VD_total);
+    ctx.end(tk);
+  });
+}
+
+// thread per block element (I <= J): gathers the (r,s) sub-block products, halves off-diagonal blocks,
+// mirrors, and adds sign*E
+template <int NL>
+__global__ void assemble_kernel(StructTables st, mp::Tensor QP, mp::Tensor out, mp::Tensor E, int sign, int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = st.n_blocks - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (st.b_off[mid] <= idx) lo = mid; else hi = mid - 1;
+    }
+    int bk = lo, j = st.b_cluster[bk];
+    int dl = st.b_delta[bk], nb = st.c_m[j] * dl;
+    int64_t rem = idx - st.b_off[bk];
+    int I = (int)(rem / nb), Jc = (int)(rem % nb);
+    if (I > Jc) continue;
+    int s = I / dl, i = I % dl, r = Jc / dl, i2 = Jc % dl;
+    int pair = s + r * (r + 1) / 2;
+    Num<NL> v = ldm<NL>(QP, st.b_QPoff[bk] + (int64_t)pair * dl * dl + (int64_t)i * dl + i2);
+    if (r != s) v = mp::mul_2exp(v, -1);
+    int64_t a1 = st.b_off[bk] + (int64_t)I * nb + Jc, a2 = st.b_off[bk] + (int64_t)Jc * nb + I;
+    Num<NL> e1 = ldm<NL>(E, a1);
+    stm<NL>(out, a1, sign > 0 ? nadd(v, e1) : nsub(v, e1));
+    if (I != Jc) {
+      Num<NL> e2 = ldm<NL>(E, a2);
+      stm<NL>(out, a2, sign > 0 ? nadd(v, e2) : nsub(v, e2));
+    }
+  }
+}
+void assemble_weighted(Ctx& ctx, int nl, const StructTables& st, mp::Tensor QP, mp::Tensor out, mp::Tensor E, int sign,
+                       int64_t blk_total, const int*) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("assemble_weighted", (double)blk_total * 4.0 * (NL + 1) * 3.0);
+    assemble_kernel<NL><<<ew_grid(ctx, blk_total), 128, 0, ctx.stream>>>(st, QP, out, E, sign, blk_total);
+    ctx.end(tk);
+  });
+}
+
+// =========================================================================================================
+// driver scalars (single thread; the reference does these in Arb on the host, MPMP.jl:755-756 etc.)
+// =========================================================================================================
+template <int NL>
+__global__ void scalar_kernel(int prog, mp::Tensor sc, int* flags, double* dout) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  auto G = [&](int s) { return ldm<NL>(sc, s); };
+  auto Pp = [&](int s, const Num<NL>& v) { stm<NL>(sc, s, v); };
+  const Num<NL> one = mp::one<NL>();
+  if (prog == SP_MU) {  // mu = dot(X,Y)/size(X,1); mu_p = pd_feas ? 0 : beta_inf*mu   (:755-756)
+    Num<NL> mu = ndiv(G(SL_DOT_XY), G(SL_NTOT));
+    Pp(SL_MU, mu);
+    Pp(SL_MU_P, flags[0] ? mp::zero<NL>() : nmul(G(SL_BETA_INF), mu));
+  } else if (prog == SP_BETA) {  // (:832-837)
+    Num<NL> r = ndiv(G(SL_DOT_SUM), nmul(G(SL_MU), G(SL_NTOT)));
+    Num<NL> beta = ncmp(r, one) < 0 ? nmul(r, r) : r;
+    Num<NL> bc;
+    if (flags[0]) {
+      bc = ncmp(G(SL_BETA_FEAS), beta) > 0 ? G(SL_BETA_FEAS) : beta;
+      if (ncmp(bc, one) > 0) bc = one;
+    } else {
+      bc = ncmp(G(SL_BETA_INF), beta) > 0 ? G(SL_BETA_INF) : beta;
+    }
+    Pp(SL_BETA_C, bc);
+    Pp(SL_MU_C, nmul(bc, G(SL_MU)));
+  } else if (prog == SP_ALPHA) {  // (:1893-1897) for X and Y, then (:871-874)
+    Num<NL> ng = mp::neg(G(SL_GAMMA));
+    Num<NL> ap = ncmp(G(SL_LAM_X), ng) > 0 ? one : ndiv(ng, G(SL_LAM_X));
+    Num<NL> ad = ncmp(G(SL_LAM_Y), ng) > 0 ? one : ndiv(ng, G(SL_LAM_Y));
+    if (flags[0]) {
+      if (ncmp(ad, ap) < 0) ap = ad;
+      ad = ap;
+    }
+    Pp(SL_ALPHA_P, ap);
+    Pp(SL_ALPHA_D, ad);
+  } else if (prog == SP_OBJECTIVES || prog == SP_OBJECTIVES_INIT) {  // objectives and gap (:1027-1034, :1067-1078)
+    Num<NL> po = nadd(G(SL_CX), G(SL_B0)), dobj = nadd(G(SL_BY), G(SL_B0));
+    Pp(SL_P_OBJ, po);
+    Pp(SL_D_OBJ, dobj);
+    if (prog == SP_OBJECTIVES_INIT) po = G(SL_CX), dobj = G(SL_BY);  // gap of the initial point: no b0 (:1067-1074)
+    Num<NL> num = mp::fabs(nsub(po, dobj)), den = mp::fabs(nadd(po, dobj));
+    if (ncmp(one, den) > 0) den = one;
+    Pp(SL_GAP, ndiv(num, den));
+  } else if (prog == SP_ERRORS) {  // errors, feasibility, termination (:1058-1064, :1147-1185)
+    Num<NL> pe = ncmp(G(SL_PERR_P), G(SL_PERR_p)) > 0 ? G(SL_PERR_P) : G(SL_PERR_p);
+    Pp(SL_PRIMAL_ERR, pe);
+    Pp(SL_DUAL_ERR, G(SL_DERR));
+    bool pf = ncmp(pe, G(SL_PERR_THR)) < 0, df = ncmp(G(SL_DERR), G(SL_DERR_THR)) < 0;
+    bool gap_opt = ncmp(G(SL_GAP), G(SL_GAP_THR)) < 0;
+    flags[0] = (pf && df) ? 1 : 0;
+    int term = 0;
+    if (flags[2] && pf)
+      term = 1;
+    else if (flags[3] && df)
+      term = 2;
+    else if (pf && df && gap_opt)
+      term = 3;
+    flags[1] = term;
+  }
+  if (dout)
+    for (int s = 0; s < SL_COUNT; s++) dout[s] = mp::to_double(G(s));
+}
+void scalar_program(Ctx& ctx, int nl, int prog, mp::Tensor scal, int* d_flags, double* d_out) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("scalar_program");
+    scalar_kernel<NL><<<1, 32, 0, ctx.stream>>>(prog, scal, d_flags, d_out);
+    ctx.end(tk);
+  });
+}
+
+}  // namespace clr

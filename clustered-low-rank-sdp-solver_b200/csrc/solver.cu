@@ -1,0 +1,1083 @@
+// solver.cu — orchestration of one interior-point iteration on the GPU (MPMP.jl:742-954) + the C ABI.
+// Host code only launches kernels; all arithmetic (including the driver scalars mu, beta, alpha) runs
+// on the device. One stream, no host synchronisation inside an iteration except the final read-back
+// of the log row.
+#include "solver.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+namespace clr {
+
+static double now_s() {
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------------------------------
+Solver::Solver(int prec_bits, int device) : nl(prec_bits / 32), prec(prec_bits) {
+  if (prec_bits % 32 || !(nl == 4 || nl == 8 || nl == 12 || nl == 16))
+    throw SolverError(CLRSDP_ERR_BAD_ARG, "precision must be 128, 256, 384 or 512 bits");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw SolverError(CLRSDP_ERR_CUDA, "no CUDA device: the hot path has no CPU fallback");
+  if (device < 0 || device >= ndev) throw SolverError(CLRSDP_ERR_BAD_ARG, "bad device ordinal");
+  ctx.device = device;
+  CLR_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CLR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    throw SolverError(CLRSDP_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                           ", this library is built for sm_100a (B200) only");
+  ctx.sm_count = prop.multiProcessorCount;
+  CLR_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+  gemm_.reset(new GemmEngine(ctx, nl));
+  scal.alloc(SL_COUNT, nl);
+  work.alloc(4096, nl);
+  d_flags.ensure(4 * sizeof(int));
+  d_scal_out.ensure(SL_COUNT * sizeof(double));
+  CLR_CUDA(cudaMemsetAsync(d_flags.p, 0, 4 * sizeof(int), ctx.stream));
+  ew_zero(ctx, nl, scal.t(), 0, SL_COUNT);
+  // the real-valued parameters (MPMP.jl:602-609) arrive at full precision through set_params
+  memset(h_scal, 0, sizeof(h_scal));
+  memset(h_flags, 0, sizeof(h_flags));
+}
+
+Solver::~Solver() {
+  cudaSetDevice(ctx.device);
+  for (auto e : ev_) cudaEventDestroy(e);
+  for (auto e : ctx.pool) cudaEventDestroy(e);
+  if (ctx.stream) cudaStreamDestroy(ctx.stream);
+}
+
+// ---- wire <-> device -------------------------------------------------------------------------------
+void Solver::to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpBuf& dst, int64_t dst_off) {
+  if (count <= 0) return;
+  std::vector<uint32_t> stage((size_t)(nl + 1) * count);
+  for (int k = 0; k < nl; k++)
+    memcpy(&stage[(size_t)k * count], src->limb + (size_t)k * src->n + src_off, (size_t)count * 4);
+  uint32_t* hdr = &stage[(size_t)nl * count];
+  for (int64_t i = 0; i < count; i++) {
+    int8_t s = src->sign[src_off + i];
+    if (s == 0) {
+      hdr[i] = mp::pack_hdr(mp::EXP_ZERO, 0);
+      for (int k = 0; k < nl; k++) stage[(size_t)k * count + i] = 0;
+    } else {
+      hdr[i] = mp::pack_hdr((int32_t)src->exp[src_off + i], s < 0 ? 1u : 0u);
+    }
+  }
+  for (int k = 0; k <= nl; k++)
+    CLR_CUDA(cudaMemcpyAsync(dst.w() + (size_t)k * dst.n + dst_off, &stage[(size_t)k * count], (size_t)count * 4,
+                             cudaMemcpyHostToDevice, ctx.stream));
+  CLR_CUDA(cudaStreamSynchronize(ctx.stream));  // staging buffer goes out of scope
+}
+void Solver::to_host(const MpBuf& src, int64_t src_off, int64_t count, clrsdp_mp_out* dst, int64_t dst_off) {
+  if (count <= 0) return;
+  std::vector<uint32_t> stage((size_t)(nl + 1) * count);
+  for (int k = 0; k <= nl; k++)
+    CLR_CUDA(cudaMemcpyAsync(&stage[(size_t)k * count], src.w() + (size_t)k * src.n + src_off, (size_t)count * 4,
+                             cudaMemcpyDeviceToHost, ctx.stream));
+  CLR_CUDA(cudaStreamSynchronize(ctx.stream));
+  const uint32_t* hdr = &stage[(size_t)nl * count];
+  for (int64_t i = 0; i < count; i++) {
+    int32_t e = ((int32_t)hdr[i]) >> 1;
+    bool z = (e == mp::EXP_ZERO);
+    dst->sign[dst_off + i] = z ? 0 : ((hdr[i] & 1u) ? -1 : 1);
+    dst->exp[dst_off + i] = z ? 0 : e;
+    for (int k = 0; k < nl; k++) dst->limb[(size_t)k * dst->n + dst_off + i] = z ? 0u : stage[(size_t)k * count + i];
+  }
+}
+
+// ---- structure ------------------------------------------------------------------------------------
+void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const int* K, const int* delta,
+                           const int* ranks) {
+  if (J_ <= 0 || n_y_ <= 0) throw SolverError(CLRSDP_ERR_BAD_ARG, "set_structure: J and n_y must be positive");
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  J = J_;
+  n_y = n_y_;
+  blocks_.clear();
+  clusters_.clear();
+  bgroups_.clear();
+  cgroups_.clear();
+  blkN = vtN = hN = pN = tN = vdN = qpN = sN = 0;
+  sumS = ntot = 0;
+  int di = 0, ri = 0, rs_total = 0;
+  std::map<std::tuple<int, int, int>, int> bkey;
+  std::map<int, int> ckey;
+  for (int j = 0; j < J; j++) {
+    HostCluster c;
+    c.m = m[j];
+    c.L = L[j];
+    c.K = K[j];
+    if (c.m <= 0 || c.L <= 0 || c.K <= 0) throw SolverError(CLRSDP_ERR_BAD_ARG, "set_structure: bad m/L/n_samples");
+    c.dimS = c.m * (c.m + 1) / 2 * c.K;
+    c.blk0 = (int)blocks_.size();
+    c.xoff = sumS;
+    c.Soff = sN;
+    sN += (int64_t)c.dimS * c.dimS;
+    sumS += c.dimS;
+    auto it = ckey.find(c.dimS);
+    if (it == ckey.end()) {
+      ckey[c.dimS] = (int)cgroups_.size();
+      cgroups_.emplace_back();
+      cgroups_.back().dimS = c.dimS;
+      it = ckey.find(c.dimS);
+    }
+    c.group = it->second;
+    c.idx_in_group = (int)cgroups_[c.group].clusters.size();
+    cgroups_[c.group].clusters.push_back(j);
+    for (int l = 0; l < c.L; l++) {
+      HostBlock bk;
+      bk.j = j;
+      bk.l = l;
+      bk.m = c.m;
+      bk.delta = delta[di++];
+      bk.nb = c.m * bk.delta;
+      bk.np = c.m * (c.m + 1) / 2;
+      bk.ranks.assign(ranks + ri, ranks + ri + c.K);
+      ri += c.K;
+      bk.rank_sums.assign(c.K + 1, 0);
+      for (int k = 0; k < c.K; k++) {
+        if (bk.ranks[k] < 0) throw SolverError(CLRSDP_ERR_BAD_ARG, "set_structure: negative rank");
+        bk.rank_sums[k + 1] = bk.rank_sums[k] + bk.ranks[k];
+      }
+      bk.Nv = bk.rank_sums[c.K];
+      if (bk.delta <= 0 || bk.Nv <= 0) throw SolverError(CLRSDP_ERR_BAD_ARG, "set_structure: empty block");
+      bk.off = blkN;
+      blkN += (int64_t)bk.nb * bk.nb;
+      bk.Voff = vtN;
+      vtN += (int64_t)bk.Nv * bk.delta;
+      bk.Hoff = hN;
+      hN += bk.Nv;
+      bk.Poff = pN;
+      pN += (int64_t)(c.m * bk.Nv) * (c.m * bk.Nv);
+      bk.Toff = tN;
+      tN += (int64_t)c.m * c.m * bk.Nv * bk.delta;
+      bk.VDoff = vdN;
+      vdN += (int64_t)bk.np * bk.delta * bk.Nv;
+      bk.QPoff = qpN;
+      qpN += (int64_t)bk.np * bk.delta * bk.delta;
+      bk.rs0 = rs_total;
+      rs_total += c.K + 1;
+      ntot += bk.nb;
+      auto key = std::make_tuple(c.m, bk.delta, bk.Nv);
+      auto bt = bkey.find(key);
+      if (bt == bkey.end()) {
+        bkey[key] = (int)bgroups_.size();
+        bgroups_.emplace_back();
+        BlockGroup& g = bgroups_.back();
+        g.m = c.m, g.delta = bk.delta, g.nb = bk.nb, g.Nv = bk.Nv, g.np = bk.np;
+        bt = bkey.find(key);
+      }
+      bk.group = bt->second;
+      bk.idx_in_group = (int)bgroups_[bk.group].blocks.size();
+      bgroups_[bk.group].blocks.push_back((int)blocks_.size());
+      blocks_.push_back(bk);
+    }
+    clusters_.push_back(c);
+  }
+  // arenas
+  for (MpBuf* t : {&X, &Y, &Xinv, &R, &P, &Z, &dX, &dY, &XY, &T1, &T2, &Ux, &Vx, &Linvx, &Linvy, &dX_pred, &dY_pred})
+    t->alloc(blkN, nl);
+  Vt.alloc(vtN, nl);
+  H.alloc(hN, nl);
+  Px.alloc(pN, nl);
+  Py.alloc(pN, nl);
+  Tt.alloc(tN, nl);
+  VD.alloc(vdN, nl);
+  QP.alloc(qpN, nl);
+  for (MpBuf* t : {&S, &Us, &Vs, &Linvs}) t->alloc(sN, nl);
+  Bmat.alloc((int64_t)sumS * n_y, nl);
+  Wt.alloc((int64_t)sumS * n_y, nl);
+  for (MpBuf* t : {&Q, &Uq, &Vq, &Linvq}) t->alloc((int64_t)n_y * n_y, nl);
+  for (MpBuf* t : {&x, &dx, &d, &c, &rhs, &tvec, &tmpx, &trx, &dx_pred}) t->alloc(sumS, nl);
+  for (MpBuf* t : {&y, &dy, &p, &b, &tmpy, &zvec, &dyr, &dy_pred}) t->alloc(n_y, nl);
+  int64_t maxrd = n_y;
+  for (auto& g : bgroups_) maxrd = std::max<int64_t>(maxrd, (int64_t)g.blocks.size() * g.nb);
+  for (auto& g : cgroups_) maxrd = std::max<int64_t>(maxrd, (int64_t)g.clusters.size() * g.dimS);
+  rdiag.alloc(maxrd, nl);
+  lam.alloc(blocks_.size(), nl);
+  work.alloc(std::max<size_t>({(size_t)4096, reduce_work_elems(), gemv_work_elems(n_y, sumS), gemv_work_elems(sumS, n_y)}), nl);
+  n_status = 2 * (int)blocks_.size() + J + 1;  // X blocks, Y blocks, S_j, Q
+  d_status.ensure(sizeof(int) * n_status);
+  h_status.assign(n_status, 0);
+  uploaded_.assign(J, 0);
+  structure_set = true;
+  have_point = prepared = tables_ready = false;
+  upload_tables();
+}
+
+template <class T>
+static void up(DevBuf& d, const std::vector<T>& h, cudaStream_t s) {
+  upload(d, h, s);
+}
+
+void Solver::upload_tables() {
+  std::vector<int> c_m, c_K, c_L, c_blk0, c_xoff, c_dimS, b_delta, b_Nv, b_cluster, b_rs0, rank_sums, samp, x_cluster;
+  std::vector<int64_t> c_Soff, b_Hoff, b_Poff, b_Voff, b_Toff, b_VDoff, b_QPoff, b_off;
+  for (auto& c : clusters_) {
+    c_m.push_back(c.m), c_K.push_back(c.K), c_L.push_back(c.L), c_blk0.push_back(c.blk0), c_xoff.push_back(c.xoff);
+    c_dimS.push_back(c.dimS), c_Soff.push_back(c.Soff);
+  }
+  for (auto& bk : blocks_) {
+    b_delta.push_back(bk.delta), b_Nv.push_back(bk.Nv), b_cluster.push_back(bk.j), b_rs0.push_back(bk.rs0);
+    b_Hoff.push_back(bk.Hoff), b_Poff.push_back(bk.Poff), b_Voff.push_back(bk.Voff), b_Toff.push_back(bk.Toff);
+    b_VDoff.push_back(bk.VDoff), b_QPoff.push_back(bk.QPoff), b_off.push_back(bk.off);
+    rank_sums.insert(rank_sums.end(), bk.rank_sums.begin(), bk.rank_sums.end());
+    for (int k = 0; k < clusters_[bk.j].K; k++)
+      for (int r = 0; r < bk.ranks[k]; r++) samp.push_back(k);
+  }
+  std::vector<int> row_item, row0, itemK;
+  std::vector<int64_t> linv_off, x_off64;
+  for (int j = 0; j < J; j++) {
+    for (int i = 0; i < clusters_[j].dimS; i++) x_cluster.push_back(j), row_item.push_back(j);
+    row0.push_back(clusters_[j].xoff);
+    itemK.push_back(clusters_[j].dimS);
+    linv_off.push_back(clusters_[j].Soff);
+    x_off64.push_back(clusters_[j].xoff);
+  }
+  cudaStream_t s = ctx.stream;
+  up(d_c_m, c_m, s), up(d_c_K, c_K, s), up(d_c_L, c_L, s), up(d_c_blk0, c_blk0, s), up(d_c_xoff, c_xoff, s);
+  up(d_c_dimS, c_dimS, s), up(d_c_Soff, c_Soff, s);
+  up(d_b_delta, b_delta, s), up(d_b_Nv, b_Nv, s), up(d_b_cluster, b_cluster, s), up(d_b_rs0, b_rs0, s);
+  up(d_b_Hoff, b_Hoff, s), up(d_b_Poff, b_Poff, s), up(d_b_Voff, b_Voff, s), up(d_b_Toff, b_Toff, s);
+  up(d_b_VDoff, b_VDoff, s), up(d_b_QPoff, b_QPoff, s), up(d_b_off, b_off, s);
+  up(d_rank_sums, rank_sums, s), up(d_samp, samp, s), up(d_x_cluster, x_cluster, s);
+  up(d_row_item, row_item, s), up(d_row0, row0, s), up(d_itemK, itemK, s), up(d_linv_off, linv_off, s),
+      up(d_x_off64, x_off64, s);
+  std::vector<int64_t> qoff = {0};
+  up(d_qoff, qoff, s);
+  st_ = StructTables();
+  st_.J = J, st_.n_y = n_y, st_.n_blocks = (int)blocks_.size(), st_.sumS = sumS;
+  st_.c_m = d_c_m.as<int>(), st_.c_K = d_c_K.as<int>(), st_.c_L = d_c_L.as<int>(), st_.c_blk0 = d_c_blk0.as<int>();
+  st_.c_xoff = d_c_xoff.as<int>(), st_.c_Soff = d_c_Soff.as<int64_t>(), st_.c_dimS = d_c_dimS.as<int>();
+  st_.b_delta = d_b_delta.as<int>(), st_.b_Nv = d_b_Nv.as<int>(), st_.b_cluster = d_b_cluster.as<int>();
+  st_.b_rs0 = d_b_rs0.as<int>(), st_.b_Hoff = d_b_Hoff.as<int64_t>(), st_.b_Poff = d_b_Poff.as<int64_t>();
+  st_.b_Voff = d_b_Voff.as<int64_t>(), st_.b_Toff = d_b_Toff.as<int64_t>(), st_.b_VDoff = d_b_VDoff.as<int64_t>();
+  st_.b_QPoff = d_b_QPoff.as<int64_t>(), st_.b_off = d_b_off.as<int64_t>();
+  st_.rank_sums = d_rank_sums.as<int>(), st_.samp = d_samp.as<int>(), st_.x_cluster = d_x_cluster.as<int>();
+  // per-group batch tables
+  for (auto& g : bgroups_) {
+    int nblk = (int)g.blocks.size(), m = g.m;
+    std::vector<int64_t> offBlk, g1A, g1C, g2B, g2C, waA, waC;
+    std::vector<int> g1rB, g2rA, warB;
+    for (int q = 0; q < nblk; q++) {
+      const HostBlock& bk = blocks_[g.blocks[q]];
+      offBlk.push_back(bk.off);
+      for (int sidx = 0; sidx < m; sidx++)
+        for (int r = 0; r < m; r++) {  // item (blk, s, r): rows i of the (r,s) sub-block
+          g1A.push_back(bk.off + (int64_t)(r * g.delta) * g.nb + sidx * g.delta);
+          g1C.push_back(bk.Toff + (int64_t)(r * m + sidx) * g.Nv * g.delta);
+          g1rB.push_back(q * g.Nv);
+        }
+      for (int r = 0; r < m; r++) {  // item (blk, r)
+        g2B.push_back(bk.Toff + (int64_t)r * m * g.Nv * g.delta);
+        g2C.push_back(bk.Poff + (int64_t)r * g.Nv * (m * g.Nv));
+        g2rA.push_back(q * g.Nv);
+      }
+      for (int pr = 0; pr < g.np; pr++) {  // item (blk, pair)
+        waA.push_back(bk.VDoff + (int64_t)pr * g.delta * g.Nv);
+        waC.push_back(bk.QPoff + (int64_t)pr * g.delta * g.delta);
+        warB.push_back(q * g.delta);
+      }
+    }
+    up(g.offBlk, offBlk, s), up(g.g1_offA, g1A, s), up(g.g1_offC, g1C, s), up(g.g1_rowB, g1rB, s);
+    up(g.g2_offB, g2B, s), up(g.g2_offC, g2C, s), up(g.g2_rowA, g2rA, s);
+    up(g.wa_offA, waA, s), up(g.wa_offC, waC, s), up(g.wa_rowB, warB, s);
+  }
+  for (auto& g : cgroups_) {
+    std::vector<int64_t> offS, offBt, offW;
+    for (int j : g.clusters) {
+      offS.push_back(clusters_[j].Soff);
+      offBt.push_back((int64_t)clusters_[j].xoff * n_y);
+      offW.push_back(clusters_[j].xoff);
+    }
+    up(g.offS, offS, s), up(g.offBt, offBt, s), up(g.offW, offW, s);
+  }
+  CLR_CUDA(cudaStreamSynchronize(s));
+  // n = size(X,1) as an mp scalar
+  {
+    int8_t sg = 1;
+    int64_t ex = 0;
+    std::vector<uint32_t> limbs(nl, 0);
+    int v = ntot, bl = 0;
+    while ((1ll << bl) <= v) bl++;
+    uint64_t top = (uint64_t)v << (64 - bl);
+    limbs[nl - 1] = (uint32_t)(top >> 32);
+    limbs[nl - 2] = (uint32_t)top;
+    ex = bl;
+    clrsdp_mp one{&sg, &ex, limbs.data(), 1};
+    to_device(&one, 0, 1, scal, SL_NTOT);
+  }
+  tables_ready = true;
+}
+
+void Solver::upload_cluster(int j, const clrsdp_mp* V, const clrsdp_mp* Hh, const clrsdp_mp* B, const clrsdp_mp* cc) {
+  if (!structure_set || j < 0 || j >= J) throw SolverError(CLRSDP_ERR_BAD_ARG, "upload_cluster: bad cluster index");
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  const HostCluster& cl = clusters_[j];
+  int64_t vneed = 0, hneed = 0;
+  for (int l = 0; l < cl.L; l++) {
+    vneed += (int64_t)blocks_[cl.blk0 + l].Nv * blocks_[cl.blk0 + l].delta;
+    hneed += blocks_[cl.blk0 + l].Nv;
+  }
+  if (V->n != vneed || Hh->n != hneed || B->n != (int64_t)cl.dimS * n_y || cc->n != cl.dimS)
+    throw SolverError(CLRSDP_ERR_BAD_ARG, "upload_cluster: array sizes do not match the structure");
+  // blocks of a cluster are contiguous in the V and H arenas, in upload order
+  to_device(V, 0, vneed, Vt, blocks_[cl.blk0].Voff);
+  to_device(Hh, 0, hneed, H, blocks_[cl.blk0].Hoff);
+  to_device(B, 0, B->n, Bmat, (int64_t)cl.xoff * n_y);
+  to_device(cc, 0, cl.dimS, c, cl.xoff);
+  uploaded_[j] = 1;
+  bool all = true;
+  for (int u : uploaded_) all = all && u;
+  if (all) build_static_slices();
+}
+
+void Solver::build_static_slices() {
+  for (auto& g : bgroups_) {
+    int nblk = (int)g.blocks.size();
+    std::vector<int64_t> voff;
+    for (int q : g.blocks) voff.push_back(blocks_[q].Voff);
+    DevBuf dv;
+    upload(dv, voff, ctx.stream);
+    OperandDesc a;
+    a.src = Vt.t();
+    a.d_off = dv.as<int64_t>();
+    a.batch = nblk;
+    a.rows = g.Nv, a.K = g.delta, a.rs = g.delta, a.ks = 1;  // rows = vectors
+    gemm_->slice(a, g.sVt);
+    a.rows = g.delta, a.K = g.Nv, a.rs = 1, a.ks = g.delta;  // rows = basis index, K = vectors
+    gemm_->slice(a, g.sVr);
+    ctx.sync();
+  }
+  for (auto& g : cgroups_) {
+    OperandDesc a;
+    a.src = Bmat.t();
+    a.d_off = g.offBt.as<int64_t>();
+    a.batch = (int)g.clusters.size();
+    a.rows = n_y, a.K = g.dimS, a.rs = 1, a.ks = n_y;  // rows = columns of B_j
+    gemm_->slice(a, g.sBt);
+  }
+  ctx.sync();
+}
+
+void Solver::upload_objective(const clrsdp_mp* bb, const clrsdp_mp* b0) {
+  if (!structure_set || bb->n != n_y) throw SolverError(CLRSDP_ERR_BAD_ARG, "upload_objective: b must have n_y entries");
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  to_device(bb, 0, n_y, b, 0);
+  if (b0 && b0->n >= 1)
+    to_device(b0, 0, 1, scal, SL_B0);
+  else
+    ew_zero(ctx, nl, scal.t(), SL_B0, 1);
+}
+
+void Solver::set_params(const clrsdp_mp* rp, const clrsdp_int_params* ipp) {
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  if (rp) {
+    if (rp->n != CLRSDP_P_COUNT) throw SolverError(CLRSDP_ERR_BAD_ARG, "set_params: expected 8 real parameters");
+    const int slots[CLRSDP_P_COUNT] = {SL_BETA_INF, SL_BETA_FEAS, SL_GAMMA,    SL_OMEGA_P,
+                                       SL_OMEGA_D,  SL_GAP_THR,   SL_PERR_THR, SL_DERR_THR};
+    for (int i = 0; i < CLRSDP_P_COUNT; i++) to_device(rp, i, 1, scal, slots[i]);
+  }
+  if (ipp) ip = *ipp;
+  int fl[4] = {0, 0, ip.need_primal_feasible, ip.need_dual_feasible};
+  CLR_CUDA(cudaMemcpyAsync(d_flags.as<int>() + 2, fl + 2, 2 * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+  ctx.sync();
+}
+
+// ---- point ----------------------------------------------------------------------------------------
+void Solver::init_point() {  // MPMP.jl:660-686
+  if (!structure_set) throw SolverError(CLRSDP_ERR_STATE, "init_point before set_structure");
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  ew_zero(ctx, nl, x.t(), 0, sumS);
+  ew_zero(ctx, nl, y.t(), 0, n_y);
+  for (auto& g : bgroups_) {
+    ew_set_identity(ctx, nl, blkbatch(g, X), scal.t(), SL_OMEGA_P);
+    ew_set_identity(ctx, nl, blkbatch(g, Y), scal.t(), SL_OMEGA_D);
+  }
+  have_point = true;
+  prepared = false;
+}
+void Solver::upload_point(const clrsdp_mp* xx, const clrsdp_mp* XX, const clrsdp_mp* yy, const clrsdp_mp* YY) {
+  if (!structure_set) throw SolverError(CLRSDP_ERR_STATE, "upload_point before set_structure");
+  if (xx->n != sumS || yy->n != n_y || XX->n != blkN || YY->n != blkN)
+    throw SolverError(CLRSDP_ERR_BAD_ARG, "upload_point: sizes do not match the structure");
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  to_device(xx, 0, sumS, x, 0);
+  to_device(yy, 0, n_y, y, 0);
+  to_device(XX, 0, blkN, X, 0);
+  to_device(YY, 0, blkN, Y, 0);
+  have_point = true;
+  prepared = false;
+}
+void Solver::download_point(clrsdp_mp_out* xx, clrsdp_mp_out* XX, clrsdp_mp_out* yy, clrsdp_mp_out* YY) {
+  if (!have_point) throw SolverError(CLRSDP_ERR_STATE, "download_point: no point");
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  if (xx) to_host(x, 0, sumS, xx, 0);
+  if (yy) to_host(y, 0, n_y, yy, 0);
+  if (XX) to_host(X, 0, blkN, XX, 0);
+  if (YY) to_host(Y, 0, blkN, YY, 0);
+}
+
+// ---- operand helpers ------------------------------------------------------------------------------
+OperandDesc Solver::rows_of(BlockGroup& g, MpBuf& t) {
+  OperandDesc a;
+  a.src = t.t();
+  a.d_off = g.offBlk.as<int64_t>();
+  a.batch = (int)g.blocks.size();
+  a.rows = g.nb, a.K = g.nb, a.rs = g.nb, a.ks = 1;
+  return a;
+}
+OperandDesc Solver::cols_of(BlockGroup& g, MpBuf& t) {
+  OperandDesc a = rows_of(g, t);
+  a.rs = 1, a.ks = g.nb;
+  return a;
+}
+OutDesc Solver::out_blk(BlockGroup& g, MpBuf& t, bool transposed) {
+  OutDesc o;
+  o.dst = t.t();
+  o.d_off = g.offBlk.as<int64_t>();
+  o.rs = transposed ? 1 : g.nb;
+  o.cs = transposed ? g.nb : 1;
+  return o;
+}
+static GemmPlan plan_of(int batch, int M, int N, const int* rowA = nullptr, const int* rowB = nullptr) {
+  GemmPlan p;
+  p.batch = batch, p.M = M, p.N = N, p.d_rowA = rowA, p.d_rowB = rowB;
+  return p;
+}
+
+// XY = X*Y per block (kept: both residual_R calls use it, MPMP.jl:1195,1209)
+void Solver::block_products_XY() {
+  for (auto& g : bgroups_) {
+    gemm_->slice(rows_of(g, X), g.sX);
+    gemm_->slice(rows_of(g, Y), g.sY);  // Y symmetric: its rows are its columns
+    gemm_->multiply(g.sX, g.sY, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, XY));
+  }
+}
+
+// X^-1 per block through the Cholesky factor (spd_inv!, MPMP.jl:764-801): X = U^T U, V = U^-1, X^-1 = V V^T
+void Solver::invert_X() {
+  int sbase = 0;
+  for (auto& g : bgroups_) {
+    MatBatch A = blkbatch(g, X), U = blkbatch(g, Ux), V = blkbatch(g, Vx), Li = blkbatch(g, Linvx);
+    chol_upper(ctx, nl, A, U, rdiag.t(), d_status.as<int>() + sbase);
+    tri_inverse(ctx, nl, U, rdiag.t(), V, &Li);
+    gemm_->slice(rows_of(g, Vx), g.sA);
+    gemm_->multiply(g.sA, g.sA, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, Xinv));
+    sbase += (int)g.blocks.size();
+  }
+}
+
+// Tt[(blk, r, s)][b][i] = sum_i' M[(r,i),(s,i')] V[i',b]   (first product of the pairings, MPMP.jl:1291-1296,
+// and of trace_A, :1558)
+void Solver::first_gemm_Tt(BlockGroup& g, MpBuf& M, Slice* cached) {
+  int nblk = (int)g.blocks.size(), m = g.m;
+  const Slice* As = cached;
+  if (!(m == 1 && cached)) {
+    OperandDesc a;
+    a.src = M.t();
+    a.d_off = g.g1_offA.as<int64_t>();
+    a.batch = nblk * m * m;
+    a.rows = g.delta, a.K = g.delta, a.rs = g.nb, a.ks = 1;
+    gemm_->slice(a, g.sB);
+    As = &g.sB;
+  }
+  OutDesc o;
+  o.dst = Tt.t();
+  o.d_off = g.g1_offC.as<int64_t>();
+  o.rs = 1, o.cs = g.delta;  // C[i][b] -> Tt[b*delta + i]
+  gemm_->multiply(*As, g.sVt, plan_of(nblk * m * m, g.delta, g.Nv, nullptr, g.g1_rowB.as<int>()), o);
+}
+
+// bilinear pairings  P[(r,a),(s,b)] = v_a^T M[r,s] v_b  (MPMP.jl:1274-1318)
+void Solver::pairings(MpBuf& M, bool is_xinv, MpBuf& Pout) {
+  for (auto& g : bgroups_) {
+    int nblk = (int)g.blocks.size(), m = g.m;
+    Slice* cached = nullptr;
+    if (m == 1) {
+      Slice& s = is_xinv ? g.sXinv : g.sY;
+      if (is_xinv) gemm_->slice(rows_of(g, M), s);  // sY was sliced for X*Y already
+      cached = &s;
+    } else if (is_xinv) {
+      gemm_->slice(rows_of(g, M), g.sXinv);  // still needed by the search directions
+    }
+    first_gemm_Tt(g, M, cached);
+    OperandDesc bdesc;
+    bdesc.src = Tt.t();
+    bdesc.d_off = g.g2_offB.as<int64_t>();
+    bdesc.batch = nblk * m;
+    bdesc.rows = m * g.Nv, bdesc.K = g.delta, bdesc.rs = g.delta, bdesc.ks = 1;
+    gemm_->slice(bdesc, g.sB);
+    OutDesc o;
+    o.dst = Pout.t();
+    o.d_off = g.g2_offC.as<int64_t>();
+    o.rs = m * g.Nv, o.cs = 1;
+    gemm_->multiply(g.sVt, g.sB, plan_of(nblk * m, g.Nv, m * g.Nv, g.g2_rowA.as<int>(), nullptr), o);
+  }
+}
+
+// out = sum_i a_i A_i + sign*E  (compute_weighted_A!, MPMP.jl:1621-1678, fused with :1115 / :1784)
+void Solver::weighted_A(MpBuf& a, MpBuf& out, MpBuf& E, int sign) {
+  scale_vectors(ctx, nl, st_, Vt.t(), H.t(), a.t(), VD.t(), vdN);
+  for (auto& g : bgroups_) {
+    int nblk = (int)g.blocks.size();
+    OperandDesc ad;
+    ad.src = VD.t();
+    ad.d_off = g.wa_offA.as<int64_t>();
+    ad.batch = nblk * g.np;
+    ad.rows = g.delta, ad.K = g.Nv, ad.rs = g.Nv, ad.ks = 1;
+    gemm_->slice(ad, g.sB);
+    OutDesc o;
+    o.dst = QP.t();
+    o.d_off = g.wa_offC.as<int64_t>();
+    o.rs = g.delta, o.cs = 1;
+    gemm_->multiply(g.sB, g.sVr, plan_of(nblk * g.np, g.delta, g.delta, nullptr, g.wa_rowB.as<int>()), o);
+  }
+  assemble_weighted(ctx, nl, st_, QP.t(), out.t(), E.t(), sign, blkN, nullptr);
+}
+
+// compute_residuals (MPMP.jl:1107-1144)
+void Solver::compute_residuals(bool from_pairings) {
+  weighted_A(x, P, X, -1);  // P = sum x_i A_i - X
+  // d = c - B y - Tr(A_* Y)
+  GemvArgs g1;
+  g1.A = Bmat.t(), g1.x = y.t(), g1.out = tmpx.t();
+  g1.rs = n_y, g1.ks = 1, g1.rows = sumS, g1.K = n_y;
+  gemv(ctx, nl, g1, work.t());
+  if (from_pairings) {
+    trace_from_pairings(ctx, nl, st_, Py.t(), H.t(), trx.t());
+  } else {  // general method on Y (loop initialisation, :727)
+    for (auto& g : bgroups_) first_gemm_Tt(g, Y, nullptr);
+    trace_from_ZV(ctx, nl, st_, Vt.t(), Tt.t(), H.t(), trx.t());
+  }
+  ew_lincomb(ctx, nl, d.t(), 0, c.t(), 0, 1, tmpx.t(), 0, -1, sumS);
+  ew_lincomb(ctx, nl, d.t(), 0, d.t(), 0, 1, trx.t(), 0, -1, sumS);
+  // p = b - B^T x
+  GemvArgs g2;
+  g2.A = Bmat.t(), g2.x = x.t(), g2.out = tmpy.t();
+  g2.rs = 1, g2.ks = n_y, g2.rows = n_y, g2.K = sumS;
+  gemv(ctx, nl, g2, work.t());
+  ew_lincomb(ctx, nl, p.t(), 0, b.t(), 0, 1, tmpy.t(), 0, -1, n_y);
+  // errors (max-abs) of this P, p, d: used by the log row now and, stale, by terminate() after the update
+  reduce_maxabs(ctx, nl, P.t(), 0, blkN, scal.t(), SL_PERR_P, work.t());
+  reduce_maxabs(ctx, nl, p.t(), 0, n_y, scal.t(), SL_PERR_p, work.t());
+  reduce_maxabs(ctx, nl, d.t(), 0, sumS, scal.t(), SL_DERR, work.t());
+}
+
+// compute_T_decomposition (MPMP.jl:1417-1514) with Cholesky instead of LU (S and Q are SPD, :1430-1432)
+void Solver::decomposition() {
+  mark(CLRSDP_T_SCHUR);
+  pairings(Xinv, true, Px);
+  pairings(Y, false, Py);
+  schur_assemble(ctx, nl, st_, Px.t(), Py.t(), H.t(), S.t(), sN);
+  mark(-1 - CLRSDP_T_SCHUR);
+  mark(CLRSDP_T_CHOL_S);
+  int sbase = 2 * (int)blocks_.size();
+  for (auto& g : cgroups_) {
+    MatBatch A{S.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
+    MatBatch U{Us.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
+    MatBatch V{Vs.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
+    MatBatch Li{Linvs.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
+    chol_upper(ctx, nl, A, U, rdiag.t(), d_status.as<int>() + sbase);
+    tri_inverse(ctx, nl, U, rdiag.t(), V, &Li);
+    sbase += (int)g.clusters.size();
+  }
+  mark(-1 - CLRSDP_T_CHOL_S);
+  mark(CLRSDP_T_CINVB);
+  // Wt[a][(j,i)] = (L_j^-1 B_j)[i][a]
+  for (auto& g : cgroups_) {
+    OperandDesc bd;
+    bd.src = Linvs.t();
+    bd.d_off = g.offS.as<int64_t>();
+    bd.batch = (int)g.clusters.size();
+    bd.rows = g.dimS, bd.K = g.dimS, bd.rs = g.dimS, bd.ks = 1;
+    gemm_->slice(bd, g.sLinv);
+    OutDesc o;
+    o.dst = Wt.t();
+    o.d_off = g.offW.as<int64_t>();
+    o.rs = sumS, o.cs = 1;
+    gemm_->multiply(g.sBt, g.sLinv, plan_of((int)g.clusters.size(), n_y, g.dimS), o);
+  }
+  mark(-1 - CLRSDP_T_CINVB);
+  mark(CLRSDP_T_Q);
+  {  // Q = sum_j W_j^T W_j = Wt Wt^T  (the reference forms B^T U^-1 * L^-1 B, :1467-1495)
+    static thread_local Slice sW;
+    OperandDesc a;
+    a.src = Wt.t();
+    a.batch = 1, a.rows = n_y, a.K = sumS, a.rs = sumS, a.ks = 1;
+    gemm_->slice(a, sW);
+    OutDesc o;
+    o.dst = Q.t();
+    o.rs = n_y, o.cs = 1;
+    gemm_->multiply(sW, sW, plan_of(1, n_y, n_y), o);
+  }
+  mark(-1 - CLRSDP_T_Q);
+  mark(CLRSDP_T_CHOL_Q);
+  {
+    MatBatch A{Q.t(), d_qoff.as<int64_t>(), 1, n_y}, U{Uq.t(), d_qoff.as<int64_t>(), 1, n_y};
+    MatBatch V{Vq.t(), d_qoff.as<int64_t>(), 1, n_y}, Li{Linvq.t(), d_qoff.as<int64_t>(), 1, n_y};
+    chol_upper(ctx, nl, A, U, rdiag.t(), d_status.as<int>() + 2 * (int)blocks_.size() + J);
+    tri_inverse(ctx, nl, U, rdiag.t(), V, &Li);
+  }
+  mark(-1 - CLRSDP_T_CHOL_Q);
+}
+
+// compute_search_direction (MPMP.jl:1682-1824)
+void Solver::search_direction() {
+  mark(CLRSDP_T_Z);
+  for (auto& g : bgroups_) {  // Z = sym(X^-1 (P Y - R))
+    int nblk = (int)g.blocks.size();
+    gemm_->slice(rows_of(g, P), g.sA);
+    mp::Tensor Rt = R.t();
+    gemm_->multiply(g.sA, g.sY, plan_of(nblk, g.nb, g.nb), out_blk(g, T1), EPI_MINUS_SUB, &Rt);
+    gemm_->slice(cols_of(g, T1), g.sB);
+    gemm_->multiply(g.sXinv, g.sB, plan_of(nblk, g.nb, g.nb), out_blk(g, T2));
+    ew_symmetrize(ctx, nl, blkbatch(g, Z), T2.t());
+  }
+  mark(-1 - CLRSDP_T_Z);
+  mark(CLRSDP_T_RHS_X);
+  for (auto& g : bgroups_) first_gemm_Tt(g, Z, nullptr);
+  trace_from_ZV(ctx, nl, st_, Vt.t(), Tt.t(), H.t(), trx.t());
+  ew_lincomb(ctx, nl, rhs.t(), 0, d.t(), 0, -1, trx.t(), 0, -1, sumS);  // rhs_x = -d - Tr(A_* Z)
+  mark(-1 - CLRSDP_T_RHS_X);
+  mark(CLRSDP_T_SYS);
+  {
+    // t_j = L_j^-1 rhs_j
+    GemvArgs a;
+    a.A = Linvs.t(), a.x = rhs.t(), a.out = tvec.t();
+    a.rows = sumS, a.K = 0;
+    a.d_row_item = d_row_item.as<int>(), a.d_aoff = d_linv_off.as<int64_t>(), a.d_xoff = d_x_off64.as<int64_t>();
+    a.d_row0 = d_row0.as<int>(), a.d_K = d_itemK.as<int>();
+    a.item_trans = 0;  // A_item[r][k], leading dimension = K_item
+    gemv(ctx, nl, a, work.t());
+    // tmpy = sum_j W_j^T t_j = Wt t
+    GemvArgs w;
+    w.A = Wt.t(), w.x = tvec.t(), w.out = tmpy.t();
+    w.rs = sumS, w.ks = 1, w.rows = n_y, w.K = sumS;
+    gemv(ctx, nl, w, work.t());
+    ew_lincomb(ctx, nl, dyr.t(), 0, p.t(), 0, 1, tmpy.t(), 0, -1, n_y);  // p - sum_j B^T U^-1 t_j (:1761)
+    // dy = Q^-1 dyr = Lq^-T (Lq^-1 dyr)
+    GemvArgs q1;
+    q1.A = Linvq.t(), q1.x = dyr.t(), q1.out = zvec.t();
+    q1.rs = n_y, q1.ks = 1, q1.rows = n_y, q1.K = n_y;
+    gemv(ctx, nl, q1, work.t());
+    GemvArgs q2 = q1;
+    q2.x = zvec.t(), q2.out = dy.t();
+    q2.rs = 1, q2.ks = n_y;
+    gemv(ctx, nl, q2, work.t());
+    // u = t + W dy ; dx_j = L_j^-T u_j
+    GemvArgs wd;
+    wd.A = Wt.t(), wd.x = dy.t(), wd.out = tmpx.t();
+    wd.rs = 1, wd.ks = sumS, wd.rows = sumS, wd.K = n_y;
+    gemv(ctx, nl, wd, work.t());
+    ew_lincomb(ctx, nl, tmpx.t(), 0, tvec.t(), 0, 1, tmpx.t(), 0, 1, sumS);
+    GemvArgs bt = a;
+    bt.x = tmpx.t(), bt.out = dx.t();
+    bt.item_trans = 1;  // A_item[k][r]
+    gemv(ctx, nl, bt, work.t());
+  }
+  mark(-1 - CLRSDP_T_SYS);
+  mark(CLRSDP_T_DX);
+  weighted_A(dx, dX, P, +1);  // dX = sum dx_i A_i + P
+  mark(-1 - CLRSDP_T_DX);
+  mark(CLRSDP_T_DY);
+  for (auto& g : bgroups_) {  // dY = sym(X^-1 (R - dX Y))
+    int nblk = (int)g.blocks.size();
+    gemm_->slice(rows_of(g, dX), g.sA);
+    mp::Tensor Rt = R.t();
+    gemm_->multiply(g.sA, g.sY, plan_of(nblk, g.nb, g.nb), out_blk(g, T1), EPI_SUB_FROM, &Rt);
+    gemm_->slice(cols_of(g, T1), g.sB);
+    gemm_->multiply(g.sXinv, g.sB, plan_of(nblk, g.nb, g.nb), out_blk(g, T2));
+    ew_symmetrize(ctx, nl, blkbatch(g, dY), T2.t());
+  }
+  mark(-1 - CLRSDP_T_DY);
+}
+
+// compute_step_length (MPMP.jl:1829-1898): lambda_min( L^-1 dM L^-T ) over all blocks -> scal[slot]
+void Solver::step_length(MpBuf& Linv, MpBuf& dM, int slot) {
+  for (auto& g : bgroups_) {
+    int nblk = (int)g.blocks.size();
+    gemm_->slice(rows_of(g, dM), g.sA);
+    gemm_->slice(rows_of(g, Linv), g.sLinv);
+    // T[i][j] = sum_k dM[i][k] Linv[j][k], stored transposed
+    gemm_->multiply(g.sA, g.sLinv, plan_of(nblk, g.nb, g.nb), out_blk(g, T1, true));
+    gemm_->slice(rows_of(g, T1), g.sB);
+    gemm_->multiply(g.sLinv, g.sB, plan_of(nblk, g.nb, g.nb), out_blk(g, T2));
+    ew_symmetrize(ctx, nl, blkbatch(g, T1), T2.t());
+    // lam[] is indexed by position in group order
+    int64_t base = 0;
+    for (auto& g2 : bgroups_) {
+      if (&g2 == &g) break;
+      base += (int64_t)g2.blocks.size();
+    }
+    lambda_min(ctx, nl, blkbatch(g, T1), lam.t(), base, work.t());
+  }
+  reduce_min(ctx, nl, lam.t(), 0, (int64_t)blocks_.size(), scal.t(), slot, work.t());
+}
+
+// ---- timing marks: bucket >= 0 begins a bucket, -1-bucket ends it -----------------------------------
+void Solver::mark(int code) {
+  cudaEvent_t e;
+  if (ev_marks_.size() < ev_.size()) {
+    e = ev_[ev_marks_.size()];
+  } else {
+    CLR_CUDA(cudaEventCreate(&e));
+    ev_.push_back(e);
+  }
+  CLR_CUDA(cudaEventRecord(e, ctx.stream));
+  if (code >= 0)
+    ev_marks_.emplace_back(code, +1);
+  else
+    ev_marks_.emplace_back(-1 - code, -1);
+}
+
+int Solver::check_status() {
+  CLR_CUDA(cudaMemcpyAsync(h_status.data(), d_status.p, sizeof(int) * n_status, cudaMemcpyDeviceToHost, ctx.stream));
+  CLR_CUDA(cudaMemcpyAsync(h_scal, d_scal_out.p, sizeof(h_scal), cudaMemcpyDeviceToHost, ctx.stream));
+  CLR_CUDA(cudaMemcpyAsync(h_flags, d_flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  int nb = (int)blocks_.size();
+  for (int i = 0; i < nb; i++)
+    if (h_status[i]) return CLRSDP_ERR_NOT_PD_X;
+  for (int i = nb; i < 2 * nb; i++)
+    if (h_status[i]) return CLRSDP_ERR_NOT_PD_Y;
+  for (int i = 2 * nb; i < 2 * nb + J; i++)
+    if (h_status[i]) return CLRSDP_ERR_SINGULAR_S;
+  if (h_status[2 * nb + J]) return CLRSDP_ERR_SINGULAR_Q;
+  return 0;
+}
+
+// loop initialisation (MPMP.jl:716-736)
+int Solver::prepare(clrsdp_iter_info* info) {
+  if (!have_point) return CLRSDP_ERR_STATE;
+  for (int u : uploaded_)
+    if (!u) return CLRSDP_ERR_STATE;
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  double t0 = now_s();
+  CLR_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int) * n_status, ctx.stream));
+  int zero2[2] = {0, 0};
+  CLR_CUDA(cudaMemcpyAsync(d_flags.p, zero2, 2 * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+  iter = 1;
+  ew_zero(ctx, nl, scal.t(), SL_ALPHA_P, 1);
+  ew_zero(ctx, nl, scal.t(), SL_ALPHA_D, 1);
+  reduce_dot(ctx, nl, X.t(), 0, Y.t(), 0, blkN, scal.t(), SL_DOT_XY, work.t());
+  scalar_program(ctx, nl, SP_MU, scal.t(), d_flags.as<int>(), nullptr);
+  reduce_dot(ctx, nl, c.t(), 0, x.t(), 0, sumS, scal.t(), SL_CX, work.t());
+  reduce_dot(ctx, nl, b.t(), 0, y.t(), 0, n_y, scal.t(), SL_BY, work.t());
+  compute_residuals(false);
+  // the initial duality gap is computed WITHOUT b0 (MPMP.jl:725 -> :1067-1074)
+  scalar_program(ctx, nl, SP_OBJECTIVES_INIT, scal.t(), d_flags.as<int>(), nullptr);
+  scalar_program(ctx, nl, SP_ERRORS, scal.t(), d_flags.as<int>(), d_scal_out.as<double>());
+  int st = check_status();
+  prepared = (st == 0);
+  if (info) {
+    memset(info, 0, sizeof(*info));
+    info->iter = iter;
+    info->status = st;
+    info->terminate = h_flags[1];
+    info->pd_feasible = h_flags[0];
+    info->mu = h_scal[SL_MU];
+    info->p_obj = info->p_obj_new = h_scal[SL_P_OBJ];
+    info->d_obj = info->d_obj_new = h_scal[SL_D_OBJ];
+    info->gap = info->gap_new = h_scal[SL_GAP];
+    info->P_err = h_scal[SL_PERR_P];
+    info->p_err = h_scal[SL_PERR_p];
+    info->d_err = h_scal[SL_DERR];
+    info->primal_err_new = h_scal[SL_PRIMAL_ERR];
+    info->dual_err_new = h_scal[SL_DUAL_ERR];
+    info->seconds = now_s() - t0;
+  }
+  return st;
+}
+
+// one pass of the while-body (MPMP.jl:754-953)
+int Solver::iterate(clrsdp_iter_info* info) {
+  if (!prepared) return CLRSDP_ERR_STATE;
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  double t0 = now_s();
+  ev_marks_.clear();
+  clrsdp_iter_info row;
+  memset(&row, 0, sizeof(row));
+  row.iter = iter;
+  // values printed in this iteration's row come from the start of the iteration (:923-937)
+  row.p_obj = h_scal[SL_P_OBJ];
+  row.d_obj = h_scal[SL_D_OBJ];
+  row.gap = h_scal[SL_GAP];
+  // step 3
+  reduce_dot(ctx, nl, X.t(), 0, Y.t(), 0, blkN, scal.t(), SL_DOT_XY, work.t());
+  scalar_program(ctx, nl, SP_MU, scal.t(), d_flags.as<int>(), nullptr);
+  // step 4: R = mu_p I - X Y
+  mark(CLRSDP_T_R);
+  block_products_XY();
+  for (auto& g : bgroups_) ew_residual_R(ctx, nl, blkbatch(g, R), scal.t(), SL_MU_P, XY.t(), nullptr);
+  mark(-1 - CLRSDP_T_R);
+  mark(CLRSDP_T_XINV);
+  invert_X();
+  mark(-1 - CLRSDP_T_XINV);
+  mark(CLRSDP_T_DECOMP);
+  decomposition();
+  mark(-1 - CLRSDP_T_DECOMP);
+  mark(CLRSDP_T_RES);
+  compute_residuals(true);
+  mark(-1 - CLRSDP_T_RES);
+  mark(CLRSDP_T_PREDICTOR);
+  search_direction();
+  mark(-1 - CLRSDP_T_PREDICTOR);
+  ew_lincomb(ctx, nl, dX_pred.t(), 0, dX.t(), 0, 1, dX.t(), 0, 0, blkN);
+  ew_lincomb(ctx, nl, dY_pred.t(), 0, dY.t(), 0, 1, dY.t(), 0, 0, blkN);
+  ew_lincomb(ctx, nl, dx_pred.t(), 0, dx.t(), 0, 1, dx.t(), 0, 0, sumS);
+  ew_lincomb(ctx, nl, dy_pred.t(), 0, dy.t(), 0, 1, dy.t(), 0, 0, n_y);
+  // step 5
+  reduce_dot_sum(ctx, nl, X.t(), dX.t(), Y.t(), dY.t(), blkN, scal.t(), SL_DOT_SUM, work.t());
+  scalar_program(ctx, nl, SP_BETA, scal.t(), d_flags.as<int>(), nullptr);
+  // step 6: R = mu_c I - X Y - dX dY
+  mark(CLRSDP_T_R);
+  for (auto& g : bgroups_) {
+    gemm_->slice(rows_of(g, dX), g.sA);
+    gemm_->slice(rows_of(g, dY), g.sB);  // dY symmetric
+    gemm_->multiply(g.sA, g.sB, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, T1));
+    mp::Tensor t1 = T1.t();
+    ew_residual_R(ctx, nl, blkbatch(g, R), scal.t(), SL_MU_C, XY.t(), &t1);
+  }
+  mark(-1 - CLRSDP_T_R);
+  mark(CLRSDP_T_CORRECTOR);
+  search_direction();
+  mark(-1 - CLRSDP_T_CORRECTOR);
+  // step 7
+  mark(CLRSDP_T_ALPHA);
+  step_length(Linvx, dX, SL_LAM_X);
+  {
+    int sbase = (int)blocks_.size();  // status slots of the Y blocks follow those of the X blocks
+    for (auto& g : bgroups_) {
+      MatBatch A = blkbatch(g, Y), U = blkbatch(g, Ux), V = blkbatch(g, Vx), Li = blkbatch(g, Linvy);
+      chol_upper(ctx, nl, A, U, rdiag.t(), d_status.as<int>() + sbase);
+      tri_inverse(ctx, nl, U, rdiag.t(), V, &Li);
+      sbase += (int)g.blocks.size();
+    }
+  }
+  step_length(Linvy, dY, SL_LAM_Y);
+  scalar_program(ctx, nl, SP_ALPHA, scal.t(), d_flags.as<int>(), nullptr);
+  mark(-1 - CLRSDP_T_ALPHA);
+  // step 8
+  ew_axpy(ctx, nl, x.t(), 0, dx.t(), 0, scal.t(), SL_ALPHA_P, sumS);
+  ew_axpy(ctx, nl, y.t(), 0, dy.t(), 0, scal.t(), SL_ALPHA_D, n_y);
+  ew_axpy(ctx, nl, X.t(), 0, dX.t(), 0, scal.t(), SL_ALPHA_P, blkN);
+  ew_axpy(ctx, nl, Y.t(), 0, dY.t(), 0, scal.t(), SL_ALPHA_D, blkN);
+  // new objectives; errors are the ones computed from P,p,d BEFORE the update (:940-944)
+  reduce_dot(ctx, nl, c.t(), 0, x.t(), 0, sumS, scal.t(), SL_CX, work.t());
+  reduce_dot(ctx, nl, b.t(), 0, y.t(), 0, n_y, scal.t(), SL_BY, work.t());
+  scalar_program(ctx, nl, SP_OBJECTIVES, scal.t(), d_flags.as<int>(), nullptr);
+  scalar_program(ctx, nl, SP_ERRORS, scal.t(), d_flags.as<int>(), d_scal_out.as<double>());
+  int st = check_status();
+  iter += 1;
+  row.status = st;
+  row.mu = h_scal[SL_MU];
+  row.P_err = h_scal[SL_PERR_P];
+  row.p_err = h_scal[SL_PERR_p];
+  row.d_err = h_scal[SL_DERR];
+  row.alpha_p = h_scal[SL_ALPHA_P];
+  row.alpha_d = h_scal[SL_ALPHA_D];
+  row.beta_c = h_scal[SL_BETA_C];
+  row.p_obj_new = h_scal[SL_P_OBJ];
+  row.d_obj_new = h_scal[SL_D_OBJ];
+  row.gap_new = h_scal[SL_GAP];
+  row.primal_err_new = h_scal[SL_PRIMAL_ERR];
+  row.dual_err_new = h_scal[SL_DUAL_ERR];
+  row.pd_feasible = h_flags[0];
+  row.terminate = h_flags[1];
+  if (row.terminate == CLRSDP_RUNNING && iter >= ip.maxiterations) row.terminate = CLRSDP_MAXITER;
+  // timing buckets from the CUDA events
+  {
+    std::vector<int> open(CLRSDP_T_COUNT, -1);
+    for (size_t i = 0; i < ev_marks_.size(); i++) {
+      int bkt = ev_marks_[i].first;
+      if (ev_marks_[i].second > 0) {
+        open[bkt] = (int)i;
+      } else if (open[bkt] >= 0) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_[open[bkt]], ev_[i]);
+        row.timings[bkt] += ms * 1e-3;
+        open[bkt] = -1;
+      }
+    }
+  }
+  row.seconds = now_s() - t0;
+  if (st) prepared = false;
+  if (info) *info = row;
+  return st;
+}
+
+int Solver::solve(clrsdp_iter_info* rows, int max_rows, int* n_rows) {
+  clrsdp_iter_info pi;
+  int st = prepare(&pi);
+  int n = 0;
+  int term = pi.terminate;
+  while (st == 0 && term == CLRSDP_RUNNING && iter < ip.maxiterations) {  // (:742-753)
+    clrsdp_iter_info row;
+    st = iterate(&row);
+    if (rows && n < max_rows) rows[n] = row;
+    n++;
+    term = (row.terminate == CLRSDP_MAXITER) ? CLRSDP_RUNNING : row.terminate;
+  }
+  if (n_rows) *n_rows = n;
+  return st;
+}
+
+// ---- fetch ----------------------------------------------------------------------------------------
+int64_t Solver::fetch(const char* name, int j, int l, clrsdp_mp_out* out) {
+  if (!structure_set) return CLRSDP_ERR_STATE;
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  std::string nm(name);
+  auto put = [&](const MpBuf& t, int64_t off, int64_t n) -> int64_t {
+    if (out) {
+      if (out->n < n) return CLRSDP_ERR_BAD_ARG;
+      ctx.sync();
+      to_host(t, off, n, out, 0);
+    }
+    return n;
+  };
+  std::map<std::string, MpBuf*> vecs = {{"x", &x}, {"dx", &dx}, {"d", &d}, {"c", &c}, {"dx_pred", &dx_pred},
+                                        {"y", &y}, {"dy", &dy}, {"p", &p}, {"b", &b}, {"dy_pred", &dy_pred}};
+  auto vit = vecs.find(nm);
+  if (vit != vecs.end()) return put(*vit->second, 0, (int64_t)vit->second->n);
+  std::map<std::string, MpBuf*> blks = {{"X", &X}, {"Y", &Y}, {"Xinv", &Xinv}, {"R", &R}, {"P", &P}, {"Z", &Z},
+                                        {"dX", &dX}, {"dY", &dY}, {"XY", &XY}, {"dX_pred", &dX_pred},
+                                        {"dY_pred", &dY_pred}, {"Linvx", &Linvx}, {"Linvy", &Linvy}};
+  auto bit = blks.find(nm);
+  if (bit != blks.end() || nm == "Px" || nm == "Py") {
+    if (j < 0 || j >= J || l < 0 || l >= clusters_[j].L) return CLRSDP_ERR_BAD_ARG;
+    const HostBlock& bk = blocks_[clusters_[j].blk0 + l];
+    if (nm == "Px") return put(Px, bk.Poff, (int64_t)(bk.m * bk.Nv) * (bk.m * bk.Nv));
+    if (nm == "Py") return put(Py, bk.Poff, (int64_t)(bk.m * bk.Nv) * (bk.m * bk.Nv));
+    return put(*bit->second, bk.off, (int64_t)bk.nb * bk.nb);
+  }
+  if (nm == "S" || nm == "Sfac" || nm == "Sinvfac") {
+    if (j < 0 || j >= J) return CLRSDP_ERR_BAD_ARG;
+    MpBuf& t = nm == "S" ? S : (nm == "Sfac" ? Us : Linvs);
+    return put(t, clusters_[j].Soff, (int64_t)clusters_[j].dimS * clusters_[j].dimS);
+  }
+  if (nm == "W") return put(Wt, 0, (int64_t)sumS * n_y);
+  if (nm == "Q") return put(Q, 0, (int64_t)n_y * n_y);
+  if (nm == "Qfac") return put(Uq, 0, (int64_t)n_y * n_y);
+  if (nm == "scalar") {
+    const int map_[CLRSDP_S_COUNT] = {SL_MU,      SL_P_OBJ,  SL_D_OBJ, SL_GAP,  SL_PRIMAL_ERR, SL_DUAL_ERR, SL_ALPHA_P,
+                                      SL_ALPHA_D, SL_BETA_C, SL_MU_P,  SL_MU_C, SL_LAM_X,      SL_LAM_Y};
+    if (j < 0 || j >= CLRSDP_S_COUNT) return CLRSDP_ERR_BAD_ARG;
+    return put(scal, map_[j], 1);
+  }
+  return CLRSDP_ERR_BAD_ARG;
+}
+
+// ---- phase-level ops ------------------------------------------------------------------------------
+void Solver::op_gemm(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, clrsdp_mp_out* C) {
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  if (A->n != (int64_t)batch * M * K || B->n != (int64_t)batch * K * N || C->n < (int64_t)batch * M * N)
+    throw SolverError(CLRSDP_ERR_BAD_ARG, "op_gemm: sizes");
+  MpBuf a, b2, c2;
+  a.alloc(A->n, nl), b2.alloc(B->n, nl), c2.alloc((int64_t)batch * M * N, nl);
+  to_device(A, 0, A->n, a, 0);
+  to_device(B, 0, B->n, b2, 0);
+  OperandDesc ad, bd;
+  ad.src = a.t(), ad.batch = batch, ad.rows = M, ad.K = K, ad.rs = K, ad.ks = 1, ad.bstride = (int64_t)M * K;
+  bd.src = b2.t(), bd.batch = batch, bd.rows = N, bd.K = K, bd.rs = 1, bd.ks = N, bd.bstride = (int64_t)K * N;
+  Slice sa, sb;
+  gemm_->slice(ad, sa);
+  gemm_->slice(bd, sb);
+  OutDesc o;
+  o.dst = c2.t(), o.bstride = (int64_t)M * N, o.rs = N, o.cs = 1;
+  gemm_->multiply(sa, sb, plan_of(batch, M, N), o);
+  ctx.sync();
+  to_host(c2, 0, (int64_t)batch * M * N, C, 0);
+}
+void Solver::op_gemm_planes(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, int32_t* planes,
+                            int* n_planes, int32_t* row_exp, int32_t* col_exp) {
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  MpBuf a, b2;
+  a.alloc(A->n, nl), b2.alloc(B->n, nl);
+  to_device(A, 0, A->n, a, 0);
+  to_device(B, 0, B->n, b2, 0);
+  OperandDesc ad, bd;
+  ad.src = a.t(), ad.batch = batch, ad.rows = M, ad.K = K, ad.rs = K, ad.ks = 1, ad.bstride = (int64_t)M * K;
+  bd.src = b2.t(), bd.batch = batch, bd.rows = N, bd.K = K, bd.rs = 1, bd.ks = N, bd.bstride = (int64_t)K * N;
+  Slice sa, sb;
+  gemm_->slice(ad, sa);
+  gemm_->slice(bd, sb);
+  if (*n_planes < gemm_->digits()) throw SolverError(CLRSDP_ERR_BAD_ARG, "op_gemm_planes: plane buffer too small");
+  int T = 0;
+  std::vector<int32_t> tmp((size_t)gemm_->digits() * batch * M * N);
+  gemm_->planes_only(sa, sb, plan_of(batch, M, N), tmp.data(), &T);
+  memcpy(planes, tmp.data(), tmp.size() * sizeof(int32_t));
+  *n_planes = T;
+  CLR_CUDA(cudaMemcpy(row_exp, sa.exps.p, sizeof(int32_t) * batch * M, cudaMemcpyDeviceToHost));
+  CLR_CUDA(cudaMemcpy(col_exp, sb.exps.p, sizeof(int32_t) * batch * N, cudaMemcpyDeviceToHost));
+}
+int Solver::op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, clrsdp_mp_out* Linv) {
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  int64_t tot = (int64_t)batch * n * n;
+  MpBuf a, u, v, li, rd;
+  a.alloc(tot, nl), u.alloc(tot, nl), v.alloc(tot, nl), li.alloc(tot, nl), rd.alloc((int64_t)batch * n, nl);
+  to_device(A, 0, tot, a, 0);
+  std::vector<int64_t> off(batch);
+  for (int i = 0; i < batch; i++) off[i] = (int64_t)i * n * n;
+  DevBuf doff, dst;
+  upload(doff, off, ctx.stream);
+  dst.ensure(sizeof(int) * batch);
+  MatBatch Ab{a.t(), doff.as<int64_t>(), batch, n}, Ub{u.t(), doff.as<int64_t>(), batch, n};
+  MatBatch Vb{v.t(), doff.as<int64_t>(), batch, n}, Lb{li.t(), doff.as<int64_t>(), batch, n};
+  chol_upper(ctx, nl, Ab, Ub, rd.t(), dst.as<int>());
+  tri_inverse(ctx, nl, Ub, rd.t(), Vb, &Lb);
+  std::vector<int> hs(batch);
+  CLR_CUDA(cudaMemcpyAsync(hs.data(), dst.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  for (int s : hs)
+    if (s) return CLRSDP_ERR_NOT_PD_X;
+  if (L) {  // L = U^T: transpose on the host side of the copy
+    std::vector<int8_t> sg(tot);
+    std::vector<int64_t> ex(tot);
+    std::vector<uint32_t> lb((size_t)nl * tot);
+    clrsdp_mp_out tmp{sg.data(), ex.data(), lb.data(), tot};
+    to_host(u, 0, tot, &tmp, 0);
+    for (int bq = 0; bq < batch; bq++)
+      for (int r = 0; r < n; r++)
+        for (int cc = 0; cc < n; cc++) {
+          int64_t s = (int64_t)bq * n * n + (int64_t)cc * n + r, t = (int64_t)bq * n * n + (int64_t)r * n + cc;
+          L->sign[t] = sg[s];
+          L->exp[t] = ex[s];
+          for (int k = 0; k < nl; k++) L->limb[(size_t)k * L->n + t] = lb[(size_t)k * tot + s];
+        }
+  }
+  if (Linv) to_host(li, 0, tot, Linv, 0);
+  return 0;
+}
+void Solver::op_elementwise(int op, const clrsdp_mp* a, const clrsdp_mp* b2, clrsdp_mp_out* cc) {
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  MpBuf A, B, C;
+  A.alloc(a->n, nl), B.alloc(a->n, nl), C.alloc(a->n, nl);
+  to_device(a, 0, a->n, A, 0);
+  if (b2) to_device(b2, 0, a->n, B, 0);
+  ew_binary(ctx, nl, op, C.t(), A.t(), B.t(), a->n);
+  ctx.sync();
+  to_host(C, 0, a->n, cc, 0);
+}
+void Solver::op_lambda_min(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lamo) {
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  int64_t tot = (int64_t)batch * n * n;
+  MpBuf a, out;
+  a.alloc(tot, nl), out.alloc(batch, nl);
+  to_device(A, 0, tot, a, 0);
+  std::vector<int64_t> off(batch);
+  for (int i = 0; i < batch; i++) off[i] = (int64_t)i * n * n;
+  DevBuf doff;
+  upload(doff, off, ctx.stream);
+  lambda_min(ctx, nl, MatBatch{a.t(), doff.as<int64_t>(), batch, n}, out.t(), 0, work.t());
+  ctx.sync();
+  to_host(out, 0, batch, lamo, 0);
+}
+
+}  // namespace clr

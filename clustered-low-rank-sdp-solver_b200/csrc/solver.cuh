@@ -1,0 +1,127 @@
+// solver.cuh — the handle behind the C ABI: problem structure, HBM-resident state, one IPM iteration.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/clrsdp.h"
+#include "gemm_i8.cuh"
+#include "linalg.cuh"
+
+namespace clr {
+
+struct HostBlock {
+  int j, l, m, delta, nb, Nv, np;
+  std::vector<int> ranks, rank_sums;
+  int64_t off, Voff, Hoff, Poff, Toff, VDoff, QPoff;
+  int rs0;
+  int group, idx_in_group;
+};
+struct HostCluster {
+  int m, L, K, dimS, blk0, xoff;
+  int64_t Soff;
+  int group, idx_in_group;
+};
+// blocks of identical shape run as one batch
+struct BlockGroup {
+  int m, delta, nb, Nv, np;
+  std::vector<int> blocks;
+  DevBuf offBlk;                      // [nblk] block arena offsets
+  DevBuf g1_offA, g1_offC, g1_rowB;   // pairing GEMM 1 items (blk, s, r)
+  DevBuf g2_offB, g2_offC, g2_rowA;   // pairing GEMM 2 items (blk, r)
+  DevBuf wa_offA, wa_offC, wa_rowB;   // weighted-A GEMM items (blk, pair)
+  Slice sVt, sVr;                     // static slices of the constraint vectors
+  Slice sX, sY, sXinv, sA, sB, sLinv; // per-iteration slices
+};
+struct ClusterGroup {
+  int dimS;
+  std::vector<int> clusters;
+  DevBuf offS, offBt, offW;
+  Slice sBt;    // static: rows a (n_y) of B_j^T, K = dimS
+  Slice sLinv;  // per iteration: rows of L_j^-1
+};
+
+class Solver {
+ public:
+  Solver(int prec_bits, int device);
+  ~Solver();
+  void set_structure(int J, int n_y, const int* m, const int* L, const int* K, const int* delta, const int* ranks);
+  void upload_cluster(int j, const clrsdp_mp* V, const clrsdp_mp* H, const clrsdp_mp* B, const clrsdp_mp* c);
+  void upload_objective(const clrsdp_mp* b, const clrsdp_mp* b0);
+  void set_params(const clrsdp_mp* rp, const clrsdp_int_params* ip);
+  void init_point();
+  void upload_point(const clrsdp_mp* x, const clrsdp_mp* X, const clrsdp_mp* y, const clrsdp_mp* Y);
+  void download_point(clrsdp_mp_out* x, clrsdp_mp_out* X, clrsdp_mp_out* y, clrsdp_mp_out* Y);
+  int prepare(clrsdp_iter_info* info);
+  int iterate(clrsdp_iter_info* info);
+  int solve(clrsdp_iter_info* rows, int max_rows, int* n_rows);
+  int64_t fetch(const char* name, int j, int l, clrsdp_mp_out* out);
+  // phase-level ops
+  void op_gemm(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, clrsdp_mp_out* C);
+  void op_gemm_planes(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, int32_t* planes,
+                      int* n_planes, int32_t* row_exp, int32_t* col_exp);
+  int op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, clrsdp_mp_out* Linv);
+  void op_lambda_min(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lam);
+  void op_elementwise(int op, const clrsdp_mp* a, const clrsdp_mp* b, clrsdp_mp_out* c);
+
+  Ctx ctx;
+  int nl;
+  int prec;
+  std::string err;
+  clrsdp_int_params ip{500, 0, 0, 0};
+
+ private:
+  // helpers
+  void to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpBuf& dst, int64_t dst_off);
+  void to_host(const MpBuf& src, int64_t src_off, int64_t count, clrsdp_mp_out* dst, int64_t dst_off);
+  void upload_tables();
+  void build_static_slices();
+  MatBatch blkbatch(BlockGroup& g, MpBuf& t) { return MatBatch{t.t(), g.offBlk.as<int64_t>(), (int)g.blocks.size(), g.nb}; }
+  OperandDesc rows_of(BlockGroup& g, MpBuf& t);
+  OperandDesc cols_of(BlockGroup& g, MpBuf& t);
+  OutDesc out_blk(BlockGroup& g, MpBuf& t, bool transposed = false);
+  void block_products_XY();
+  void invert_X();
+  void pairings(MpBuf& M, bool is_xinv, MpBuf& Pout);
+  void first_gemm_Tt(BlockGroup& g, MpBuf& M, Slice* cached);
+  void weighted_A(MpBuf& a, MpBuf& out, MpBuf& E, int sign);
+  void compute_residuals(bool from_pairings);
+  void search_direction();
+  void step_length(MpBuf& Linv, MpBuf& dM, int slot);
+  void decomposition();
+  int check_status();
+  void mark(int bucket_begin);
+
+  std::unique_ptr<GemmEngine> gemm_;
+  // structure
+  int J = 0, n_y = 0, sumS = 0, ntot = 0;
+  std::vector<HostBlock> blocks_;
+  std::vector<HostCluster> clusters_;
+  std::vector<BlockGroup> bgroups_;
+  std::vector<ClusterGroup> cgroups_;
+  int64_t blkN = 0, vtN = 0, hN = 0, pN = 0, tN = 0, vdN = 0, qpN = 0, sN = 0;
+  bool structure_set = false, have_point = false, prepared = false, tables_ready = false;
+  std::vector<int> uploaded_;
+  // device tables
+  DevBuf d_c_m, d_c_K, d_c_L, d_c_blk0, d_c_xoff, d_c_Soff, d_c_dimS, d_b_delta, d_b_Nv, d_b_cluster, d_b_rs0, d_b_Hoff,
+      d_b_Poff, d_b_Voff, d_b_Toff, d_b_VDoff, d_b_QPoff, d_b_off, d_rank_sums, d_samp, d_x_cluster;
+  DevBuf d_row_item, d_linv_off, d_x_off64, d_row0, d_itemK;
+  StructTables st_;
+  // arenas
+  MpBuf X, Y, Xinv, R, P, Z, dX, dY, XY, T1, T2, Ux, Vx, Linvx, Linvy;
+  MpBuf Vt, H, Px, Py, Tt, VD, QP, S, Us, Vs, Linvs, Bmat, Wt, Q, Uq, Vq, Linvq;
+  MpBuf x, dx, d, c, rhs, tvec, tmpx, trx, y, dy, p, b, tmpy, zvec, dyr;
+  MpBuf dX_pred, dY_pred, dx_pred, dy_pred;
+  MpBuf scal, rdiag, lam, work;
+  DevBuf d_status, d_flags, d_scal_out, d_qoff;
+  std::vector<int> h_status;
+  int n_status = 0;
+  // iteration bookkeeping
+  int iter = 1;
+  std::vector<cudaEvent_t> ev_;
+  std::vector<std::pair<int, int>> ev_marks_;  // (bucket, +1 begin / -1 end)
+  double h_scal[SL_COUNT];
+  int h_flags[4];
+};
+
+}  // namespace clr
