@@ -101,20 +101,24 @@ __device__ __forceinline__ void stm(const mp::Tensor& t, int64_t i, const Num<NL
 // =========================================================================================================
 // Cholesky (upper factor), one CTA per matrix, threads (column c, part)
 // =========================================================================================================
+constexpr int TRI_THREADS = 512;
 template <int NL>
-__global__ void chol_kernel(mp::Tensor A, const int64_t* __restrict__ offA, mp::Tensor U,
-                            const int64_t* __restrict__ offU, mp::Tensor rdiag, int n, int* __restrict__ status) {
+__global__ void __launch_bounds__(TRI_THREADS)
+chol_kernel(mp::Tensor A, const int64_t* __restrict__ offA, mp::Tensor U, const int64_t* __restrict__ offU,
+            mp::Tensor rdiag, int n, int* __restrict__ status) {
   extern __shared__ uint32_t sm[];
   __shared__ int bad;
-  const int b = blockIdx.x, c = threadIdx.x, part = threadIdx.y, P = blockDim.y;
+  const int b = blockIdx.x, tx = threadIdx.x, part = threadIdx.y, CX = blockDim.x, P = blockDim.y;
+  const int tid = part * CX + tx, nthr = CX * P;
   const int64_t oa = offA[b], ou = offU[b];
-  if (threadIdx.x == 0 && threadIdx.y == 0) bad = 0;
+  if (tid == 0) bad = 0;
   // U <- upper triangle of A, zeros below
   for (int r = part; r < n; r += P)
-    if (c < n) stm<NL>(U, ou + (int64_t)r * n + c, (r <= c) ? ldm<NL>(A, oa + (int64_t)r * n + c) : mp::zero<NL>());
+    for (int c = tx; c < n; c += CX)
+      stm<NL>(U, ou + (int64_t)r * n + c, (r <= c) ? ldm<NL>(A, oa + (int64_t)r * n + c) : mp::zero<NL>());
   __syncthreads();
   for (int k = 0; k < n; k++) {
-    if (c == 0 && part == 0) {
+    if (tid == 0) {
       Num<NL> a = ldm<NL>(U, ou + (int64_t)k * n + k);
       if (mp::is_zero(a) || a.neg) {
         bad = 1;
@@ -128,12 +132,13 @@ __global__ void chol_kernel(mp::Tensor A, const int64_t* __restrict__ offA, mp::
     }
     __syncthreads();
     if (bad) break;
-    if (part == 0 && c > k && c < n) {
+    {
       Num<NL> rinv = smem_get<NL>(sm, 0);
-      stm<NL>(U, ou + (int64_t)k * n + c, nmul(ldm<NL>(U, ou + (int64_t)k * n + c), rinv));
+      for (int c = k + 1 + tid; c < n; c += nthr)
+        stm<NL>(U, ou + (int64_t)k * n + c, nmul(ldm<NL>(U, ou + (int64_t)k * n + c), rinv));
     }
     __syncthreads();
-    if (c > k && c < n) {
+    for (int c = k + 1 + tx; c < n; c += CX) {
       Num<NL> ukc = ldm<NL>(U, ou + (int64_t)k * n + c);
       for (int r = k + 1 + part; r <= c; r += P) {
         Num<NL> ukr = ldm<NL>(U, ou + (int64_t)k * n + r);
@@ -143,33 +148,36 @@ __global__ void chol_kernel(mp::Tensor A, const int64_t* __restrict__ offA, mp::
     }
     __syncthreads();
   }
-  if (c == 0 && part == 0) status[b] = bad;
+  if (tid == 0) status[b] = bad;
 }
 
 // V = U^-1 (upper) by right-looking back substitution; Linv = V^T written alongside.
 template <int NL>
-__global__ void trinv_kernel(mp::Tensor U, const int64_t* __restrict__ offU, mp::Tensor rdiag, mp::Tensor V,
-                             const int64_t* __restrict__ offV, mp::Tensor Linv, const int64_t* __restrict__ offL,
-                             int n, int want_V) {
-  const int b = blockIdx.x, c = threadIdx.x, part = threadIdx.y, P = blockDim.y;
+__global__ void __launch_bounds__(TRI_THREADS)
+trinv_kernel(mp::Tensor U, const int64_t* __restrict__ offU, mp::Tensor rdiag, mp::Tensor V,
+             const int64_t* __restrict__ offV, mp::Tensor Linv, const int64_t* __restrict__ offL, int n) {
+  const int b = blockIdx.x, tx = threadIdx.x, part = threadIdx.y, CX = blockDim.x, P = blockDim.y;
+  const int tid = part * CX + tx, nthr = CX * P;
   const int64_t ou = offU[b], ov = offV[b], ol = offL ? offL[b] : 0;
   for (int r = part; r < n; r += P)
-    if (c < n) {
+    for (int c = tx; c < n; c += CX) {
       stm<NL>(V, ov + (int64_t)r * n + c, mp::zero<NL>());
       if (offL && c > r) stm<NL>(Linv, ol + (int64_t)r * n + c, mp::zero<NL>());
     }
   __syncthreads();
   for (int k = n - 1; k >= 0; k--) {
-    if (part == 0 && c >= k && c < n) {
-      Num<NL> acc = ldm<NL>(V, ov + (int64_t)k * n + c);
+    {
       Num<NL> rk = ldm<NL>(rdiag, (int64_t)b * n + k);
-      Num<NL> v = (c == k) ? nsub(mp::one<NL>(), acc) : mp::neg(acc);
-      v = nmul(v, rk);
-      stm<NL>(V, ov + (int64_t)k * n + c, v);
-      if (offL) stm<NL>(Linv, ol + (int64_t)c * n + k, v);
+      for (int c = k + tid; c < n; c += nthr) {
+        Num<NL> acc = ldm<NL>(V, ov + (int64_t)k * n + c);
+        Num<NL> v = (c == k) ? nsub(mp::one<NL>(), acc) : mp::neg(acc);
+        v = nmul(v, rk);
+        stm<NL>(V, ov + (int64_t)k * n + c, v);
+        if (offL) stm<NL>(Linv, ol + (int64_t)c * n + k, v);
+      }
     }
     __syncthreads();
-    if (c >= k && c < n) {
+    for (int c = k + tx; c < n; c += CX) {
       Num<NL> vkc = ldm<NL>(V, ov + (int64_t)k * n + c);
       for (int i = part; i < k; i += P) {
         Num<NL> uik = ldm<NL>(U, ou + (int64_t)i * n + k);
@@ -179,18 +187,15 @@ __global__ void trinv_kernel(mp::Tensor U, const int64_t* __restrict__ offU, mp:
     }
     __syncthreads();
   }
-  (void)want_V;
 }
 
 static dim3 tri_block(int n) {
-  int cx = ((n + 31) / 32) * 32;
-  cx = std::min(cx, 1024);
-  int p = std::max(1, 1024 / cx);
+  int cx = std::min(((n + 31) / 32) * 32, 256);
+  int p = std::max(1, TRI_THREADS / cx);
   return dim3(cx, p, 1);
 }
 
 void chol_upper(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& U, mp::Tensor rdiag, int* d_status) {
-  if (A.n > 1024) throw SolverError(-1, "chol_upper: n > 1024 not supported");
   dim3 blk = tri_block(A.n);
   DISPATCH_NL(nl, {
     int tk = ctx.begin("chol");
@@ -204,7 +209,7 @@ void tri_inverse(Ctx& ctx, int nl, const MatBatch& U, mp::Tensor rdiag, const Ma
   DISPATCH_NL(nl, {
     int tk = ctx.begin("trinv");
     trinv_kernel<NL><<<U.batch, blk, 0, ctx.stream>>>(U.t, U.d_off, rdiag, V.t, V.d_off, Linv ? Linv->t : V.t,
-                                                      Linv ? Linv->d_off : nullptr, U.n, 1);
+                                                      Linv ? Linv->d_off : nullptr, U.n);
     ctx.end(tk);
   });
 }
@@ -236,7 +241,8 @@ __device__ bool any_eig_below(const uint32_t* dsm, const uint32_t* e2sm, int n, 
 }
 
 template <int NL>
-__global__ void lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Tensor out, int64_t out_off) {
+__global__ void __launch_bounds__(512)
+lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Tensor out, int64_t out_off) {
   extern __shared__ uint32_t sm[];
   // smem layout (in Num slots of NL+2 words): v[n], q[n], d[n], e2[n], red[33], misc[8], partial[P*CX]
   const int CX = blockDim.x, P = blockDim.y;
