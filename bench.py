@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py — seconds per interior-point iteration of the B200 hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is ONE IPM iteration (one pass of MPMP.jl:754-953) on the synthetic clustered low-rank SDP of
+BASELINE config 3 (64 clusters per GPU, rank-1 constraints, block 64, 128 samples, n_y = 256, 256-bit;
+weak scaling: N GPUs hold 64*N clusters — at N = 8 this is the north star's 512-cluster instance).
+`value` is the device time per iteration with the state resident in HBM; `e2e` is the same iteration
+through the C ABI with the iterate (x, X, y, Y) living in HOST buffers: upload, iterate, download.
+`--impl reference` times the CPU restatement of the reference (oracle/, MPFR) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "clustered-low-rank-sdp-solver_b200"))
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = dict(J_per_gpu=64, delta=64, K=128, n_y=256, prec=256, seed=20261018)
+METRIC = "sec/IPM iteration at 256-bit (Schur build+Cholesky), 1/2/4/8 B200 vs CPU"
+UNIT = "s/iteration"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), bf16_tflops=d.get("bf16_tflops", 1590.0), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.rows, self.stop_flag, self.index = [], False, index
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+def build_problem(J, j_offset, j_total, nl_prec):
+    from clrsdp import instances, solver
+    cons, b, info = instances.synthetic_clustered_sdp(J=J, delta=WORKLOAD["delta"], K=WORKLOAD["K"], n_y=WORKLOAD["n_y"],
+                                                      prec=nl_prec, seed=WORKLOAD["seed"], j_offset=j_offset, j_total=j_total)
+    return cons, b, solver.get_block_info(cons)
+
+
+def algorithmic_int8_macs(bi, prec):
+    """pMACs of the pure-GEMM phases actually executed per iteration x s(s+1)/2, s = p/8."""
+    s = prec // 8
+    per = s * (s + 1) // 2
+    pmac = 0
+    for j in range(bi.J):
+        m, K, dimS = bi.m[j], bi.n_samples[j], bi.dim_S[j]
+        for l in range(bi.L[j]):
+            nb, dl = bi.Y_blocksizes[j][l], bi.delta[j][l]
+            Nv = int(sum(bi.ranks[j][l]))
+            pmac += 2 * (nb * nb * Nv + m * nb * Nv * Nv)          # pairings (X^-1 and Y)
+            pmac += 2 * nb ** 3                                    # XY, dXdY
+            pmac += nb ** 3                                        # X^-1 = V V^T
+            pmac += 2 * (4 * nb ** 3)                              # Z and dY, two directions
+            pmac += 3 * (m * (m + 1) // 2) * dl * dl * Nv          # V D V^T: residual + two directions
+            pmac += 2 * nb * nb * Nv                               # Z V for trace_A, two directions
+            pmac += 2 * (2 * nb ** 3)                              # L^-1 dM L^-T for X and Y
+        pmac += dimS * dimS * bi.n_y                               # W = L^-1 B
+        pmac += bi.n_y * bi.n_y * dimS                             # Q
+    return pmac * per, pmac
+
+
+def cpu_baseline(n_threads, sample_J=None, iters=1):
+    """The oracle (CPU restatement of MPMP.jl, MPFR) timed on a bounded sample: `sample_J` clusters of the
+    same shape instead of 64; per-cluster phases scale linearly with J, the factorisation of Q does not."""
+    from clrsdp import solver
+    from oracle.ref import oracle_handle
+    Jfull = WORKLOAD["J_per_gpu"]
+    sample_J = sample_J or max(1, min(Jfull, n_threads // 2 if n_threads >= 4 else 2))
+    cons, b, bi = build_problem(sample_J, 0, sample_J, WORKLOAD["prec"])
+    h = oracle_handle(WORKLOAD["prec"], n_threads)
+    solver.load_problem(h, cons, b, bi)
+    h.set_params(solver.real_params(h.nlimb))
+    h.init_point()
+    h.prepare()
+    per_iter = []
+    for _ in range(iters):
+        t0 = time.time()
+        r = h.iterate()
+        dt = time.time() - t0
+        tq = r.timings[11]  # chol_Q: independent of J
+        per_iter.append((dt - tq) * (Jfull / sample_J) + tq)
+    h.close()
+    return dict(value=float(np.mean(per_iter)), unit=UNIT, cores=n_threads, kind="port",
+                sample=f"{iters} iteration(s) of the MPFR restatement (oracle/) on {sample_J} of {Jfull} clusters "
+                       f"(same delta/K/n_y), per-cluster phases scaled x{Jfull / sample_J:g}, Q factorisation unscaled; "
+                       "the reference itself (Julia+Arb) cannot run in this image")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_threads = os.cpu_count() or 1
+    vals = []
+    last = None
+    for _ in range(max(1, args.warmup // 3)):
+        cpu_baseline(n_threads, iters=1)
+    for _ in range(args.steps):
+        last = cpu_baseline(n_threads, iters=1)
+        vals.append(last["value"])
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=v * 1e3, higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f256 (MPFR)",
+                data="synthetic", impl="reference",
+                config=dict(workload="synthetic clustered low-rank SDP, BASELINE config 3 per GPU", **WORKLOAD),
+                cpu_baseline=last, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from clrsdp import solver
+    from clrsdp.wire import MpArray
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prec = WORKLOAD["prec"]
+    Jloc = WORKLOAD["J_per_gpu"]
+    cons, b, bi = build_problem(Jloc, rank * Jloc, world * Jloc, prec)
+    h = solver.product_handle(prec, local_rank)
+    if world > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = (ctypes.c_uint8 * 128)()
+            f = h.lib.clrsdp_comm_unique_id
+            f.argtypes = [ctypes.POINTER(ctypes.c_uint8)]
+            st = f(buf)
+            if st != 0:
+                raise RuntimeError("clrsdp_comm_unique_id failed")
+            uid = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        h.comm_init(world, rank, bytes(uid.cpu().tolist()))
+    solver.load_problem(h, cons, b, bi)
+    h.set_params(solver.real_params(h.nlimb))
+    h.init_point()
+    h.prepare()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        r = h.iterate()
+    launches0 = h.launch_count()
+    h.profile_reset(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_s = []
+    for _ in range(args.steps):
+        r = h.iterate()            # blocks until the iteration's log row is back: device work is complete
+        dev_s.append(r.seconds)
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    launches = h.launch_count() - launches0
+    prof = h.profile_dump()
+    h.profile_reset(False)
+    dev_total = float(np.sum(dev_s))
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_total, wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_total, wall = float(t[0]), float(t[1])
+    sec_per_iter = dev_total / args.steps
+
+    # ---- end to end: the iterate lives in host buffers between iterations ----
+    n_x, n_X, n_y = int(sum(bi.dim_S)), int(sum(s * s for row in bi.Y_blocksizes for s in row)), bi.n_y
+    state = h.download_point(n_x, n_X, n_y)
+    bytes_per_num = 4 * h.nlimb + 8 + 1
+    h2d = (n_x + n_y + 2 * n_X) * bytes_per_num
+    d2h = h2d + ctypes.sizeof(type(r))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.upload_point(*state)
+        h.prepare()
+        r = h.iterate()
+        state = h.download_point(n_x, n_X, n_y)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_wall = float(t[0])
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    macs, pmac = algorithmic_int8_macs(bi, prec)
+    mma = prof.get("mma_planes", dict(ms=0.0, launches=0, work=0.0))
+    # int8 dense tensor peak: not in MEASURED_PEAKS.json; nominal 2x the measured bf16 rate (B200_PROFILING.md
+    # gives int8 = fp8 = 2x bf16 nominal), stated as such
+    int8_peak_tops = 2.0 * peaks["bf16_tflops"]
+    mma_tops = (2.0 * mma["work"] / (mma["ms"] * 1e-3) / 1e12) if mma["ms"] > 0 else 0.0
+    top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]
+    roofline = dict(bound="tensor", kernel="mma_planes_kernel", achieved=mma_tops, peak=int8_peak_tops, unit="TOP/s (int8)",
+                    frac=mma_tops / int8_peak_tops if int8_peak_tops else None, traffic=None,
+                    peak_source=f"2 x bf16_tflops ({peaks['source']}); int8 peak itself not measured",
+                    launches=mma["launches"], ms_per_launch=mma["ms"] / max(1, mma["launches"]),
+                    share_of_step=mma["ms"] * 1e-3 / dev_total if dev_total else None,
+                    kernel_ms_per_step={k: round(v["ms"] / args.steps, 4) for k, v in top})
+    line = dict(metric=METRIC, value=sec_per_iter, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=sec_per_iter * 1e3, higher_is_better=False, scaling="weak", vs_baseline=None,
+                dtype=f"u{prec} fixed-limb float (int8 slices, int32 accumulate)", data="synthetic",
+                config=dict(workload="synthetic clustered low-rank SDP, BASELINE config 3 per GPU "
+                                     "(manufactured strictly feasible; iterations from omega*I)",
+                            clusters_total=world * Jloc, l2="working set > L2 (several hundred MB of arenas touched per "
+                            "iteration); no explicit flush", **WORKLOAD),
+                wall_ms_per_step=wall / args.steps * 1e3,
+                e2e=dict(value=e2e_wall / args.steps, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         note="upload_point + prepare + iterate + download_point through the C ABI with host buffers"),
+                gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline,
+                algorithmic=dict(pmac_per_iter=pmac, int8_mac_per_iter=macs))
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)
+        except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
+            line["cpu_baseline"] = dict(error=str(e))
+    if args.profile_out:
+        with open(args.profile_out, "w") as f:
+            json.dump(dict(per_kernel=prof, steps=args.steps, dev_seconds=dev_total), f, indent=1)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -304,6 +304,18 @@ class Handle:
                     "profile_query")
         return ms.value, n.value, work.value
 
+    def profile_dump(self):
+        f = self._fn("profile_dump")
+        f.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        n = f(self._h, None, 0)
+        buf = ctypes.create_string_buffer(max(n, 1))
+        f(self._h, buf, n)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, launches, work = line.split()
+            out[name] = dict(ms=float(ms), launches=int(launches), work=float(work))
+        return out
+
     def comm_init(self, n_ranks: int, rank: int, uid: bytes):
         f = self._fn("comm_init")
         f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]

@@ -1,5 +1,6 @@
 // capi.cu — the extern "C" surface declared in include/clrsdp.h. Exceptions never cross the boundary:
 // every entry point maps them to a status code and keeps the message for clrsdp_last_error.
+#include <algorithm>
 #include <cstring>
 
 #include "solver.cuh"
@@ -193,4 +194,25 @@ CAPI int clrsdp_profile_query(clrsdp_handle h, const char* pattern, double* ms, 
     if (work) *work = w;
     return 0;
   });
+}
+CAPI int clrsdp_profile_dump(clrsdp_handle h, char* buf, int buf_len) {
+  if (!h || !h->s) return CLRSDP_ERR_BAD_ARG;
+  try {
+    h->s->ctx.resolve();
+  } catch (...) {
+    return CLRSDP_ERR_CUDA;
+  }
+  std::string out;
+  char line[256];
+  for (auto& kv : h->s->ctx.prof) {
+    snprintf(line, sizeof(line), "%s %.6f %lld %.6e\n", kv.first.c_str(), kv.second.ms, (long long)kv.second.launches,
+             kv.second.work);
+    out += line;
+  }
+  if (buf && buf_len > 0) {
+    int n = std::min<int>((int)out.size(), buf_len - 1);
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int)out.size() + 1;
 }

@@ -802,6 +802,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   CLR_CUDA(cudaSetDevice(ctx.device));
   double t0 = now_s();
   ev_marks_.clear();
+  mark(CLRSDP_T_COUNT);  // whole iteration (extra bucket, reported as `seconds`)
   clrsdp_iter_info row;
   memset(&row, 0, sizeof(row));
   row.iter = iter;
@@ -874,6 +875,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   reduce_dot(ctx, nl, b.t(), 0, y.t(), 0, n_y, scal.t(), SL_BY, work.t());
   scalar_program(ctx, nl, SP_OBJECTIVES, scal.t(), d_flags.as<int>(), nullptr);
   scalar_program(ctx, nl, SP_ERRORS, scal.t(), d_flags.as<int>(), d_scal_out.as<double>());
+  mark(-1 - CLRSDP_T_COUNT);
   int st = check_status();
   iter += 1;
   row.status = st;
@@ -894,7 +896,8 @@ int Solver::iterate(clrsdp_iter_info* info) {
   if (row.terminate == CLRSDP_RUNNING && iter >= ip.maxiterations) row.terminate = CLRSDP_MAXITER;
   // timing buckets from the CUDA events
   {
-    std::vector<int> open(CLRSDP_T_COUNT, -1);
+    std::vector<int> open(CLRSDP_T_COUNT + 1, -1);
+    double total = 0;
     for (size_t i = 0; i < ev_marks_.size(); i++) {
       int bkt = ev_marks_[i].first;
       if (ev_marks_[i].second > 0) {
@@ -902,12 +905,16 @@ int Solver::iterate(clrsdp_iter_info* info) {
       } else if (open[bkt] >= 0) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_[open[bkt]], ev_[i]);
-        row.timings[bkt] += ms * 1e-3;
+        if (bkt < CLRSDP_T_COUNT)
+          row.timings[bkt] += ms * 1e-3;
+        else
+          total = ms * 1e-3;
         open[bkt] = -1;
       }
     }
+    row.seconds = total;  // device time of the iteration (CUDA events on the launching stream)
   }
-  row.seconds = now_s() - t0;
+  (void)t0;
   if (st) prepared = false;
   if (info) *info = row;
   return st;

@@ -114,7 +114,7 @@ typedef struct {
   int32_t pd_feasible;  /* check_pd_feasibility after this iteration (MPMP.jl:949-953) */
   double  mu, p_obj, d_obj, gap, P_err, p_err, d_err, alpha_p, alpha_d, beta_c;
   double  p_obj_new, d_obj_new, gap_new, primal_err_new, dual_err_new;
-  double  seconds;      /* wall time of this iteration */
+  double  seconds;      /* time of this iteration: CUDA events on the launching stream (oracle: wall clock) */
   double  timings[CLRSDP_T_COUNT];
 } clrsdp_iter_info;
 
@@ -205,6 +205,8 @@ int64_t clrsdp_launch_count(clrsdp_handle h);
 int clrsdp_profile_reset(clrsdp_handle h, int enable);
 int clrsdp_profile_query(clrsdp_handle h, const char* pattern, double* ms, int64_t* launches,
                          double* work);
+/* text table "name ms launches work" of every kernel timed since the last reset; returns bytes needed */
+int clrsdp_profile_dump(clrsdp_handle h, char* buf, int buf_len);
 
 #ifdef __cplusplus
 }
