@@ -236,3 +236,59 @@ def sphere_packing_2point(n=3, d=8, r=None, prec=512, N=2):
     cons = [cons[o - 1] for o in ordering]
     b = MpArray.from_mpf([mp.mpf(-1)] + [mp.mpf(0)] * n_a, nlimb)  # (:89)
     return cons, b, dict(n=n, d=d, prec=prec, n_y=n_y, omega=mp.mpf(100))
+
+
+def random_structured_sdp(spec, n_y=5, prec=256, seed=7, positive_H=True):
+    """Random clustered SDP with arbitrary structure, for parity tests of the general code paths
+    (m > 1, several blocks per cluster, rank > 1, samples of rank 0).
+
+    spec: list over clusters of dict(m=.., K=.., blocks=[dict(delta=.., ranks=[.. K ints ..]), ...]).
+    With positive_H the instance is manufactured strictly feasible (X0 = sum_k (sum_rnk H v v^T) (x) x0_k
+    with each m x m matrix x0_k diagonally dominant), so a full solve converges; otherwise H has mixed
+    signs and only single iterations from omega*I are meaningful.
+    """
+    nlimb = prec // 32
+    rng = np.random.default_rng(seed)
+    constraints, b_int = [], np.zeros(n_y, dtype=object)
+    y0 = _rand_scaled(rng, n_y, -1.0, 1.0).astype(object)
+    for cl in spec:
+        m, K = cl["m"], cl["K"]
+        npairs = m * (m + 1) // 2
+        dimS = npairs * K
+        B = _rand_scaled(rng, (dimS, n_y), -1.0, 1.0)
+        # x0: for every sample a diagonally dominant symmetric m x m matrix, stored by pairs (r,s), s <= r
+        x0 = np.zeros(dimS, dtype=np.int64)
+        for r in range(m):
+            for s in range(r + 1):
+                pr = s + r * (r + 1) // 2
+                x0[pr * K:(pr + 1) * K] = _rand_scaled(rng, K, 1.0, 2.0) if r == s else _rand_scaled(rng, K, -0.2, 0.2)
+        V, H, ranks, Vint, Hint = [], [], [], [], []
+        for bk in cl["blocks"]:
+            dl, rk = bk["delta"], np.asarray(bk["ranks"], dtype=np.int32)
+            Nv = int(rk.sum())
+            v = _rand_scaled(rng, (Nv, dl), -1.0, 1.0)
+            hsign = np.ones(Nv, dtype=np.int64) if positive_H else rng.choice([-1, 1], size=Nv)
+            h = hsign * _rand_scaled(rng, Nv, 0.5, 2.0)
+            V.append(MpArray.from_scaled_int64(v, -FRAC_BITS, nlimb).reshape(Nv, dl))
+            H.append(MpArray.from_scaled_int64(h, -FRAC_BITS, nlimb))
+            ranks.append(rk)
+            Vint.append(v.astype(object))
+            Hint.append(h.astype(object))
+        # dual point Y0 = I (block identity): Tr(A_(r,s,k) Y0) = sum_l sum_rnk H |v|^2 [r == s]
+        c_int = B.astype(object).dot(y0) * (1 << (2 * FRAC_BITS))          # scale 2^-120
+        for r in range(m):
+            pr = r + r * (r + 1) // 2
+            for l, bk in enumerate(cl["blocks"]):
+                rk = ranks[l]
+                pos = 0
+                for k in range(K):
+                    for _ in range(rk[k]):
+                        vv = int((Vint[l][pos] * Vint[l][pos]).sum())       # scale 2^-80
+                        c_int[pr * K + k] += int(Hint[l][pos]) * vv          # scale 2^-120
+                        pos += 1
+        b_int += B.astype(object).T.dot(x0.astype(object))
+        constraints.append(Constraint(V=V, ranks=ranks, H=H,
+                                      B=MpArray.from_scaled_int64(B, -FRAC_BITS, nlimb).reshape(dimS, n_y),
+                                      c=MpArray.from_ints(list(c_int), -3 * FRAC_BITS, nlimb)))
+    b = MpArray.from_ints(list(b_int), -2 * FRAC_BITS, nlimb)
+    return constraints, b

@@ -514,7 +514,8 @@ void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, i
   // algorithmic MACs: M*N*K * s(s+1)/2 with s = p/8, no guard digits, no tile padding
   double s_alg = 4.0 * nl_;
   double alg = (double)nitems * plan.M * plan.N * (double)A.K * (s_alg * (s_alg + 1) / 2.0);
-  int tk = ctx_.begin("mma_planes", alg);
+  std::string nm = "mma_planes_M" + std::to_string(plan.M) + "_N" + std::to_string(plan.N) + "_K" + std::to_string(A.K) + "_b" + std::to_string(nitems);
+  int tk = ctx_.begin(nm.c_str(), alg);
   mma_planes_kernel<<<(unsigned)grid, MMA_THREADS, smem, ctx_.stream>>>(tmA, tmB, p);
   ctx_.end(tk);
 }

@@ -198,7 +198,8 @@ static dim3 tri_block(int n) {
 void chol_upper(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& U, mp::Tensor rdiag, int* d_status) {
   dim3 blk = tri_block(A.n);
   DISPATCH_NL(nl, {
-    int tk = ctx.begin("chol");
+    std::string nm = "chol_n" + std::to_string(A.n);
+    int tk = ctx.begin(nm.c_str());
     chol_kernel<NL><<<A.batch, blk, (NL + 2) * sizeof(uint32_t), ctx.stream>>>(A.t, A.d_off, U.t, U.d_off, rdiag, A.n,
                                                                                d_status);
     ctx.end(tk);
@@ -207,7 +208,8 @@ void chol_upper(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& U, mp::Tens
 void tri_inverse(Ctx& ctx, int nl, const MatBatch& U, mp::Tensor rdiag, const MatBatch& V, const MatBatch* Linv) {
   dim3 blk = tri_block(U.n);
   DISPATCH_NL(nl, {
-    int tk = ctx.begin("trinv");
+    std::string nm = "trinv_n" + std::to_string(U.n);
+    int tk = ctx.begin(nm.c_str());
     trinv_kernel<NL><<<U.batch, blk, 0, ctx.stream>>>(U.t, U.d_off, rdiag, V.t, V.d_off, Linv ? Linv->t : V.t,
                                                       Linv ? Linv->d_off : nullptr, U.n);
     ctx.end(tk);
@@ -449,7 +451,8 @@ void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, int64_t out
       CLR_CUDA(cudaFuncSetAttribute(lambda_min_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr[NL] = true;
     }
-    int tk = ctx.begin("lambda_min");
+    std::string nm = "lambda_min_n" + std::to_string(W.n);
+    int tk = ctx.begin(nm.c_str());
     lambda_min_kernel<NL><<<W.batch, blk, words * sizeof(uint32_t), ctx.stream>>>(W.t, W.d_off, W.n, out, out_off);
     ctx.end(tk);
   });

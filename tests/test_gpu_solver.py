@@ -1,0 +1,188 @@
+"""GPU parity of the interior-point iteration against the oracle, through the C ABI (host-side mirror
+`clrsdp.solver`). Tolerance (north star): relative 2^-(p-16) on single iterations; identical iteration
+counts and objectives to 2^-(p-16) * condition slack on full solves (slack stated per test)."""
+import mpmath
+import numpy as np
+import pytest
+
+from clrsdp import instances, solver
+from clrsdp.capi import ClrsdpError
+from clrsdp.wire import rel_err_bits
+from oracle.ref import oracle_handle
+
+pytestmark = pytest.mark.gpu
+
+GENERAL_SPEC = [dict(m=2, K=5, blocks=[dict(delta=3, ranks=[2, 1, 0, 2, 1]), dict(delta=2, ranks=[1, 1, 1, 1, 1])]),
+                dict(m=1, K=4, blocks=[dict(delta=3, ranks=[1, 2, 1, 1])]),
+                dict(m=3, K=3, blocks=[dict(delta=2, ranks=[2, 2, 1])]),
+                dict(m=2, K=5, blocks=[dict(delta=3, ranks=[1, 1, 2, 0, 2]), dict(delta=2, ranks=[1, 1, 1, 1, 1])])]
+
+BLOCK_FIELDS = ["XY", "R", "Xinv", "Px", "Py", "P", "Z", "dX_pred", "dY_pred", "dX", "dY", "X", "Y"]
+VEC_FIELDS = ["d", "dx_pred", "dy_pred", "dx", "dy", "x", "y"]
+
+
+def pair(cons, b, bi, prec, **params):
+    hs = [solver.product_handle(prec), oracle_handle(prec, 8)]
+    for h in hs:
+        solver.load_problem(h, cons, b, bi)
+        h.set_params(solver.real_params(h.nlimb, **params))
+        h.init_point()
+        h.prepare()
+    return hs
+
+
+def compare_iteration(hg, ho, bi, prec, tol_bits):
+    for name in VEC_FIELDS:
+        assert rel_err_bits(hg.fetch(name), ho.fetch(name)) >= tol_bits, name
+    for j in range(bi.J):
+        assert rel_err_bits(hg.fetch("S", j), ho.fetch("S", j)) >= tol_bits, ("S", j)
+        for l in range(bi.L[j]):
+            for name in BLOCK_FIELDS:
+                a, o = hg.fetch(name, j, l), ho.fetch(name, j, l)
+                if name == "P" and max(abs(v) for v in o.to_double()) < 1e-40:
+                    continue   # residual at rounding level: nothing to compare
+                assert rel_err_bits(a, o) >= tol_bits, (name, j, l)
+    assert rel_err_bits(hg.fetch("Q"), ho.fetch("Q")) >= tol_bits
+    with mpmath.workprec(prec + 32):
+        for s in ("mu", "lambda_x", "lambda_y", "alpha_p", "alpha_d", "beta_c", "p_obj", "d_obj"):
+            a, o = hg.scalar(s), ho.scalar(s)
+            assert abs(a - o) <= abs(o) * mpmath.mpf(2) ** -tol_bits, s
+
+
+@pytest.mark.parametrize("prec", [128, 256, 512])
+def test_iterations_match_oracle_rank1(prec):
+    cons, b, _ = instances.synthetic_clustered_sdp(J=3, delta=8, K=12, n_y=7, prec=prec)
+    bi = solver.get_block_info(cons)
+    hg, ho = pair(cons, b, bi, prec)
+    for it in range(3):
+        rg, ro = hg.iterate(), ho.iterate()
+        assert rg.status == 0 and ro.status == 0
+        compare_iteration(hg, ho, bi, prec, prec - 16)          # relative 2^-(p-16)
+        assert rg.pd_feasible == ro.pd_feasible and rg.terminate == ro.terminate
+
+
+@pytest.mark.parametrize("positive_H", [True, False])
+def test_iterations_match_oracle_general_structure(positive_H):
+    """m > 1, several blocks per cluster, rank > 1, a sample of rank 0, mixed-sign H, ragged shapes."""
+    prec = 256
+    cons, b = instances.random_structured_sdp(GENERAL_SPEC, n_y=4, prec=prec, positive_H=positive_H)
+    bi = solver.get_block_info(cons)
+    hg, ho = pair(cons, b, bi, prec)
+    for it in range(2):
+        rg, ro = hg.iterate(), ho.iterate()
+        assert rg.status == 0 and ro.status == 0
+        compare_iteration(hg, ho, bi, prec, prec - 16)
+
+
+def test_prepare_matches_oracle():
+    prec = 256
+    cons, b = instances.random_structured_sdp(GENERAL_SPEC, n_y=4, prec=prec)
+    bi = solver.get_block_info(cons)
+    hs = [solver.product_handle(prec), oracle_handle(prec, 4)]
+    infos = []
+    for h in hs:
+        solver.load_problem(h, cons, b, bi, b0=3)
+        h.set_params(solver.real_params(h.nlimb, omega_p=100, omega_d=7))
+        h.init_point()
+        infos.append(h.prepare())
+    g, o = infos
+    for k in ("mu", "p_obj", "d_obj", "gap", "P_err", "p_err", "d_err", "primal_err_new", "dual_err_new"):
+        assert getattr(g, k) == pytest.approx(getattr(o, k), rel=1e-13), k
+    assert rel_err_bits(hs[0].fetch("d"), hs[1].fetch("d")) >= prec - 16
+    assert rel_err_bits(hs[0].fetch("p"), hs[1].fetch("p")) >= prec - 16
+
+
+@pytest.mark.parametrize("case", ["rank1", "general"])
+def test_full_solve_same_iteration_count_and_objectives(case):
+    prec = 256
+    if case == "rank1":
+        cons, b, _ = instances.synthetic_clustered_sdp(J=3, delta=6, K=10, n_y=5, prec=prec)
+    else:
+        cons, b = instances.random_structured_sdp(GENERAL_SPEC, n_y=4, prec=prec)
+    bi = solver.get_block_info(cons)
+    og, rg = solver.solverank1sdp(cons, b, bi, verbose=False, return_info=True)
+    oo, ro = solver.solverank1sdp(cons, b, bi, handle=oracle_handle(prec, 8), verbose=False, return_info=True)
+    assert len(rg) == len(ro)                                    # identical iteration count
+    assert rg[-1].terminate == ro[-1].terminate == 3
+    for a, o in zip(rg, ro):
+        assert a.alpha_p == pytest.approx(o.alpha_p, rel=1e-12) and a.alpha_d == pytest.approx(o.alpha_d, rel=1e-12)
+    with mpmath.workprec(prec):
+        # objectives after ~60-80 iterations: rounding differences are amplified by the conditioning of X, S
+        # (up to ~2^60 near the optimum); tolerance 2^-(p-16-64)
+        tol = mpmath.mpf(2) ** -(prec - 16 - 64)
+        assert abs(og[8] - oo[8]) <= abs(oo[8]) * tol
+        assert abs(og[9] - oo[9]) <= abs(oo[9]) * tol
+        assert og[7] < mpmath.mpf(10) ** -15 and oo[7] < mpmath.mpf(10) ** -15
+
+
+def test_warm_start_roundtrip():
+    """download_point -> upload_point reproduces the same next iteration (initial_solutions, MPMP.jl:613,689)."""
+    prec = 256
+    cons, b, _ = instances.synthetic_clustered_sdp(J=2, delta=4, K=6, n_y=3, prec=prec)
+    bi = solver.get_block_info(cons)
+    h1 = solver.product_handle(prec)
+    solver.load_problem(h1, cons, b, bi)
+    h1.set_params(solver.real_params(h1.nlimb))
+    h1.init_point()
+    h1.prepare()
+    h1.iterate()
+    n_x, n_X = sum(bi.dim_S), sum(s * s for row in bi.Y_blocksizes for s in row)
+    st = h1.download_point(n_x, n_X, bi.n_y)
+    r1 = h1.iterate()
+    h2 = solver.product_handle(prec)
+    solver.load_problem(h2, cons, b, bi)
+    h2.set_params(solver.real_params(h2.nlimb))
+    h2.upload_point(*st)
+    h2.prepare()
+    r2 = h2.iterate()
+    assert r1.alpha_p == r2.alpha_p and r1.alpha_d == r2.alpha_d and r1.mu == r2.mu
+    a, o = h1.fetch("x"), h2.fetch("x")
+    assert np.array_equal(a.limb, o.limb) and np.array_equal(a.exp, o.exp)     # bit-identical
+
+
+def test_call_order_and_argument_errors():
+    h = solver.product_handle(256)
+    with pytest.raises(ClrsdpError) as e:
+        h.iterate()
+    assert e.value.code == -15
+    with pytest.raises(ClrsdpError):
+        h.set_structure(3, [1], [1], [0], [2], [1])            # n_samples = 0
+    cons, b, _ = instances.synthetic_clustered_sdp(J=2, delta=3, K=4, n_y=2, prec=256)
+    bi = solver.get_block_info(cons)
+    solver.load_problem(h, cons, b, bi)
+    with pytest.raises(ClrsdpError):
+        h.upload_cluster(0, cons[0].V[0], cons[0].H[0], cons[0].B, cons[1].c.take(range(3)))   # wrong size
+    with pytest.raises(ClrsdpError):
+        h.fetch("nonsense")
+
+
+def test_not_positive_definite_point_is_reported():
+    prec = 256
+    cons, b, _ = instances.synthetic_clustered_sdp(J=2, delta=3, K=4, n_y=2, prec=prec)
+    bi = solver.get_block_info(cons)
+    h = solver.product_handle(prec)
+    solver.load_problem(h, cons, b, bi)
+    h.set_params(solver.real_params(h.nlimb, omega_p=-1))       # X = -I is not PD
+    h.init_point()
+    h.prepare()
+    with pytest.raises(ClrsdpError) as e:
+        h.iterate()
+    assert e.value.code == -10 and "higher precision" in str(e.value)
+
+
+def test_launch_counter_and_profile():
+    prec = 256
+    cons, b, _ = instances.synthetic_clustered_sdp(J=2, delta=4, K=6, n_y=3, prec=prec)
+    bi = solver.get_block_info(cons)
+    h = solver.product_handle(prec)
+    solver.load_problem(h, cons, b, bi)
+    h.set_params(solver.real_params(h.nlimb))
+    h.init_point()
+    h.prepare()
+    n0 = h.launch_count()
+    h.profile_reset(True)
+    r = h.iterate()
+    prof = h.profile_dump()
+    assert h.launch_count() - n0 == sum(v["launches"] for v in prof.values()) > 100
+    assert any(k.startswith("mma_planes") for k in prof)
+    assert r.seconds > 0 and sum(r.timings) > 0
