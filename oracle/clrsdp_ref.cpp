@@ -1404,6 +1404,11 @@ REF_API int64_t clrsdp_ref_fetch(clrsdp_handle h, const char* name, int j, int l
   if (nm == "p") return put_vec(out, h->p, h->nlimb);
   if (nm == "d") return put_vec(out, h->d, h->nlimb);
   if (nm == "b") return put_vec(out, h->b, h->nlimb);
+  if (nm == "c") {
+    std::vector<Real> cc;
+    for (auto& c : h->cl) cc.insert(cc.end(), c.c.begin(), c.c.end());
+    return put_vec(out, cc, h->nlimb);
+  }
   if (nm == "X") return blockmat(h->X);
   if (nm == "Y") return blockmat(h->Y);
   if (nm == "Xinv") return blockmat(h->Xinv);
