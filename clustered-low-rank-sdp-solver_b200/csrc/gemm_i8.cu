@@ -25,7 +25,7 @@ struct GatherArgs {
 };
 
 __device__ __forceinline__ int64_t item_off(const GatherArgs& g, int b) {
-  return g.d_off ? g.d_off[b] : g.off0 + (int64_t)b * g.bstride;
+  return g.off0 + (g.d_off ? g.d_off[b] : (int64_t)b * g.bstride);
 }
 
 // one warp per row: max exponent over the non-zero entries (EXP_ZERO for an all-zero row)
@@ -393,8 +393,10 @@ __global__ void carry_kernel(CarryArgs c) {
       // value = N_int * 2^(ea + eb - 4 - 8T), N_int = (W / 2^(32 NW)) * 2^(32 NW - sh)
       mp::round_guard<NL>(r, X, 32 * NW - sh + ea + eb - 4 - 8 * T, negf ? 1u : 0u);
     }
-    int64_t at = (c.d_off ? c.d_off[gb] : c.off0 + (int64_t)gb * c.bstride) + (int64_t)i * c.rs + (int64_t)j * c.cs;
-    if (c.epi != EPI_STORE) {
+    int64_t at = c.off0 + (c.d_off ? c.d_off[gb] : (int64_t)gb * c.bstride) + (int64_t)i * c.rs + (int64_t)j * c.cs;
+    if (c.epi == EPI_NEG) {
+      r = mp::neg(r);
+    } else if (c.epi != EPI_STORE) {
       mp::Num<NL> e = mp::load<NL>(c.ew, c.en, (size_t)at);
       if (c.epi == EPI_SUB_FROM)
         r = mp::sub(e, r);

@@ -17,7 +17,7 @@ constexpr int GUARD_DIGITS = 2;  // digits beyond p/8 kept per operand and per p
 inline int num_digits(int nl) { return 4 * nl + GUARD_DIGITS; }
 
 // gather description of a logical operand [batch][rows][K] inside an mp tensor:
-//   element (b, r, k) lives at  off(b) + r*rs + k*ks,   off(b) = d_off ? d_off[b] : off0 + b*bstride
+//   element (b, r, k) lives at  off(b) + r*rs + k*ks,   off(b) = off0 + (d_off ? d_off[b] : b*bstride)
 struct OperandDesc {
   mp::Tensor src;
   const int64_t* d_off = nullptr;
@@ -25,7 +25,7 @@ struct OperandDesc {
   int64_t rs = 0, ks = 1;
   int batch = 1, rows = 0, K = 0;
 };
-// destination of a product: element (b, i, j) at off(b) + i*rs + j*cs
+// destination of a product: element (b, i, j) at off(b) + i*rs + j*cs, off(b) as above
 struct OutDesc {
   mp::Tensor dst;
   const int64_t* d_off = nullptr;
@@ -37,7 +37,8 @@ enum : int {
   EPI_STORE = 0,      // C = A*B
   EPI_SUB_FROM = 1,   // C = E - A*B     (E = extra operand, same addressing as C)
   EPI_MINUS_SUB = 2,  // C = A*B - E
-  EPI_ADD = 3         // C = A*B + E
+  EPI_ADD = 3,        // C = A*B + E
+  EPI_NEG = 4         // C = -A*B
 };
 
 struct Slice {

@@ -104,28 +104,28 @@ __device__ __forceinline__ void stm(const mp::Tensor& t, int64_t i, const Num<NL
 constexpr int TRI_THREADS = 512;
 template <int NL>
 __global__ void __launch_bounds__(TRI_THREADS)
-chol_kernel(mp::Tensor A, const int64_t* __restrict__ offA, mp::Tensor U, const int64_t* __restrict__ offU,
-            mp::Tensor rdiag, int n, int* __restrict__ status) {
+chol_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shiftA, int ldA, mp::Tensor U,
+            const int64_t* __restrict__ offU, int64_t shiftU, int ld, mp::Tensor rdiag, int n, int* __restrict__ status) {
   extern __shared__ uint32_t sm[];
   __shared__ int bad;
   const int b = blockIdx.x, tx = threadIdx.x, part = threadIdx.y, CX = blockDim.x, P = blockDim.y;
   const int tid = part * CX + tx, nthr = CX * P;
-  const int64_t oa = offA[b], ou = offU[b];
-  if (tid == 0) bad = 0;
+  const int64_t oa = offA[b] + shiftA, ou = offU[b] + shiftU;
+  if (tid == 0) bad = status[b];  // sticky across the panels of a blocked factorisation
   // U <- upper triangle of A, zeros below
   for (int r = part; r < n; r += P)
     for (int c = tx; c < n; c += CX)
-      stm<NL>(U, ou + (int64_t)r * n + c, (r <= c) ? ldm<NL>(A, oa + (int64_t)r * n + c) : mp::zero<NL>());
+      stm<NL>(U, ou + (int64_t)r * ld + c, (r <= c) ? ldm<NL>(A, oa + (int64_t)r * ldA + c) : mp::zero<NL>());
   __syncthreads();
   for (int k = 0; k < n; k++) {
     if (tid == 0) {
-      Num<NL> a = ldm<NL>(U, ou + (int64_t)k * n + k);
+      Num<NL> a = ldm<NL>(U, ou + (int64_t)k * ld + k);
       if (mp::is_zero(a) || a.neg) {
         bad = 1;
       } else {
         Num<NL> rinv;
         Num<NL> d = nsqrt_rsqrt(a, rinv);
-        stm<NL>(U, ou + (int64_t)k * n + k, d);
+        stm<NL>(U, ou + (int64_t)k * ld + k, d);
         stm<NL>(rdiag, (int64_t)b * n + k, rinv);
         smem_put<NL>(sm, 0, rinv);
       }
@@ -135,14 +135,14 @@ chol_kernel(mp::Tensor A, const int64_t* __restrict__ offA, mp::Tensor U, const 
     {
       Num<NL> rinv = smem_get<NL>(sm, 0);
       for (int c = k + 1 + tid; c < n; c += nthr)
-        stm<NL>(U, ou + (int64_t)k * n + c, nmul(ldm<NL>(U, ou + (int64_t)k * n + c), rinv));
+        stm<NL>(U, ou + (int64_t)k * ld + c, nmul(ldm<NL>(U, ou + (int64_t)k * ld + c), rinv));
     }
     __syncthreads();
     for (int c = k + 1 + tx; c < n; c += CX) {
-      Num<NL> ukc = ldm<NL>(U, ou + (int64_t)k * n + c);
+      Num<NL> ukc = ldm<NL>(U, ou + (int64_t)k * ld + c);
       for (int r = k + 1 + part; r <= c; r += P) {
-        Num<NL> ukr = ldm<NL>(U, ou + (int64_t)k * n + r);
-        int64_t at = ou + (int64_t)r * n + c;
+        Num<NL> ukr = ldm<NL>(U, ou + (int64_t)k * ld + r);
+        int64_t at = ou + (int64_t)r * ld + c;
         stm<NL>(U, at, nsub(ldm<NL>(U, at), nmul(ukr, ukc)));
       }
     }
@@ -154,34 +154,35 @@ chol_kernel(mp::Tensor A, const int64_t* __restrict__ offA, mp::Tensor U, const 
 // V = U^-1 (upper) by right-looking back substitution; Linv = V^T written alongside.
 template <int NL>
 __global__ void __launch_bounds__(TRI_THREADS)
-trinv_kernel(mp::Tensor U, const int64_t* __restrict__ offU, mp::Tensor rdiag, mp::Tensor V,
-             const int64_t* __restrict__ offV, mp::Tensor Linv, const int64_t* __restrict__ offL, int n) {
+trinv_kernel(mp::Tensor U, const int64_t* __restrict__ offU, int64_t shiftU, mp::Tensor rdiag, mp::Tensor V,
+             const int64_t* __restrict__ offV, int64_t shiftV, mp::Tensor Linv, const int64_t* __restrict__ offL,
+             int64_t shiftL, int ld, int n) {
   const int b = blockIdx.x, tx = threadIdx.x, part = threadIdx.y, CX = blockDim.x, P = blockDim.y;
   const int tid = part * CX + tx, nthr = CX * P;
-  const int64_t ou = offU[b], ov = offV[b], ol = offL ? offL[b] : 0;
+  const int64_t ou = offU[b] + shiftU, ov = offV[b] + shiftV, ol = offL ? offL[b] + shiftL : 0;
   for (int r = part; r < n; r += P)
     for (int c = tx; c < n; c += CX) {
-      stm<NL>(V, ov + (int64_t)r * n + c, mp::zero<NL>());
-      if (offL && c > r) stm<NL>(Linv, ol + (int64_t)r * n + c, mp::zero<NL>());
+      stm<NL>(V, ov + (int64_t)r * ld + c, mp::zero<NL>());
+      if (offL && c > r) stm<NL>(Linv, ol + (int64_t)r * ld + c, mp::zero<NL>());
     }
   __syncthreads();
   for (int k = n - 1; k >= 0; k--) {
     {
       Num<NL> rk = ldm<NL>(rdiag, (int64_t)b * n + k);
       for (int c = k + tid; c < n; c += nthr) {
-        Num<NL> acc = ldm<NL>(V, ov + (int64_t)k * n + c);
+        Num<NL> acc = ldm<NL>(V, ov + (int64_t)k * ld + c);
         Num<NL> v = (c == k) ? nsub(mp::one<NL>(), acc) : mp::neg(acc);
         v = nmul(v, rk);
-        stm<NL>(V, ov + (int64_t)k * n + c, v);
-        if (offL) stm<NL>(Linv, ol + (int64_t)c * n + k, v);
+        stm<NL>(V, ov + (int64_t)k * ld + c, v);
+        if (offL) stm<NL>(Linv, ol + (int64_t)c * ld + k, v);
       }
     }
     __syncthreads();
     for (int c = k + tx; c < n; c += CX) {
-      Num<NL> vkc = ldm<NL>(V, ov + (int64_t)k * n + c);
+      Num<NL> vkc = ldm<NL>(V, ov + (int64_t)k * ld + c);
       for (int i = part; i < k; i += P) {
-        Num<NL> uik = ldm<NL>(U, ou + (int64_t)i * n + k);
-        int64_t at = ov + (int64_t)i * n + c;
+        Num<NL> uik = ldm<NL>(U, ou + (int64_t)i * ld + k);
+        int64_t at = ov + (int64_t)i * ld + c;
         stm<NL>(V, at, nadd(ldm<NL>(V, at), nmul(uik, vkc)));
       }
     }
@@ -200,8 +201,9 @@ void chol_upper(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& U, mp::Tens
   DISPATCH_NL(nl, {
     std::string nm = "chol_n" + std::to_string(A.n);
     int tk = ctx.begin(nm.c_str());
-    chol_kernel<NL><<<A.batch, blk, (NL + 2) * sizeof(uint32_t), ctx.stream>>>(A.t, A.d_off, U.t, U.d_off, rdiag, A.n,
-                                                                               d_status);
+    if (U.stride() != U.n && A.t.w != U.t.w) throw SolverError(-1, "chol_upper: sub-blocks must be factored in place");
+    chol_kernel<NL><<<A.batch, blk, (NL + 2) * sizeof(uint32_t), ctx.stream>>>(
+        A.t, A.d_off, A.shift, A.stride(), U.t, U.d_off, U.shift, U.stride(), rdiag, A.n, d_status);
     ctx.end(tk);
   });
 }
@@ -210,8 +212,11 @@ void tri_inverse(Ctx& ctx, int nl, const MatBatch& U, mp::Tensor rdiag, const Ma
   DISPATCH_NL(nl, {
     std::string nm = "trinv_n" + std::to_string(U.n);
     int tk = ctx.begin(nm.c_str());
-    trinv_kernel<NL><<<U.batch, blk, 0, ctx.stream>>>(U.t, U.d_off, rdiag, V.t, V.d_off, Linv ? Linv->t : V.t,
-                                                      Linv ? Linv->d_off : nullptr, U.n);
+    if (V.stride() != U.stride() || (Linv && Linv->stride() != U.stride()))
+      throw SolverError(-1, "tri_inverse: operands must share the leading dimension");
+    trinv_kernel<NL><<<U.batch, blk, 0, ctx.stream>>>(U.t, U.d_off, U.shift, rdiag, V.t, V.d_off, V.shift,
+                                                      Linv ? Linv->t : V.t, Linv ? Linv->d_off : nullptr,
+                                                      Linv ? Linv->shift : 0, U.stride(), U.n);
     ctx.end(tk);
   });
 }
@@ -558,6 +563,40 @@ void ew_binary(Ctx& ctx, int nl, int op, mp::Tensor c, mp::Tensor a, mp::Tensor 
   DISPATCH_NL(nl, {
     int tk = ctx.begin("ew_binary");
     binary_kernel<NL><<<ew_grid(ctx, n), 128, 0, ctx.stream>>>(op, c, a, b, n);
+    ctx.end(tk);
+  });
+}
+template <int NL>
+__global__ void mat_copy_kernel(mp::Tensor D, const int64_t* __restrict__ offD, int64_t shD, int ldD, mp::Tensor S,
+                                const int64_t* __restrict__ offS, int64_t shS, int ldS, int batch, int n, int mode) {
+  int64_t total = (int64_t)batch * n * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / ((int64_t)n * n));
+    int rem = (int)(idx % ((int64_t)n * n));
+    int r = rem / n, c = rem % n;
+    Num<NL> v = mp::zero<NL>();
+    if (mode == 0 || (mode == 1 && r <= c)) v = ldm<NL>(S, offS[b] + shS + (int64_t)r * ldS + c);
+    stm<NL>(D, offD[b] + shD + (int64_t)r * ldD + c, v);
+  }
+}
+void mat_copy(Ctx& ctx, int nl, const MatBatch& dst, const MatBatch& src, bool upper_only) {
+  int64_t total = (int64_t)dst.batch * dst.n * dst.n;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("mat_copy", (double)total * 4.0 * (NL + 1) * 2);
+    mat_copy_kernel<NL><<<ew_grid(ctx, total), 128, 0, ctx.stream>>>(dst.t, dst.d_off, dst.shift, dst.stride(), src.t,
+                                                                     src.d_off, src.shift, src.stride(), dst.batch,
+                                                                     dst.n, upper_only ? 1 : 0);
+    ctx.end(tk);
+  });
+}
+void mat_zero(Ctx& ctx, int nl, const MatBatch& dst) {
+  int64_t total = (int64_t)dst.batch * dst.n * dst.n;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("mat_zero", (double)total * 4.0 * (NL + 1));
+    mat_copy_kernel<NL><<<ew_grid(ctx, total), 128, 0, ctx.stream>>>(dst.t, dst.d_off, dst.shift, dst.stride(), dst.t,
+                                                                     dst.d_off, dst.shift, dst.stride(), dst.batch,
+                                                                     dst.n, 2);
     ctx.end(tk);
   });
 }

@@ -7,11 +7,22 @@
 
 namespace clr {
 
-// batch of n x n matrices inside an mp tensor: matrix b starts at d_off[b]; row-major, leading dim n
+// batch of n x n matrices inside an mp tensor: element (r,c) of matrix b at d_off[b] + shift + r*ld + c
+// (ld = 0 means ld = n). Sub-blocks of larger matrices are expressed through shift/ld.
 struct MatBatch {
   mp::Tensor t;
   const int64_t* d_off = nullptr;
   int batch = 0, n = 0;
+  int ld = 0;
+  int64_t shift = 0;
+  int stride() const { return ld ? ld : n; }
+  MatBatch sub(int r0, int c0, int nn) const {
+    MatBatch m = *this;
+    m.shift = shift + (int64_t)r0 * stride() + c0;
+    m.ld = stride();
+    m.n = nn;
+    return m;
+  }
 };
 
 // ---- factorisations ----------------------------------------------------------------------------------
@@ -41,6 +52,9 @@ void ew_symmetrize(Ctx& ctx, int nl, const MatBatch& out, mp::Tensor in);
 // M = s*I per block (MPMP.jl:660-686)
 void ew_set_identity(Ctx& ctx, int nl, const MatBatch& M, mp::Tensor scal, int slot);
 void ew_zero(Ctx& ctx, int nl, mp::Tensor t, int64_t off, int64_t n);
+// dst = src for a batch of (sub)matrices; with upper_only the strictly lower part of dst is zeroed instead
+void mat_copy(Ctx& ctx, int nl, const MatBatch& dst, const MatBatch& src, bool upper_only);
+void mat_zero(Ctx& ctx, int nl, const MatBatch& dst);
 // c[i] = a[i] (op) b[i], op in '+','-','*','/','s' (sqrt of a): the scalar arithmetic of mpf.cuh on the device
 void ew_binary(Ctx& ctx, int nl, int op, mp::Tensor c, mp::Tensor a, mp::Tensor b, int64_t n);
 

@@ -452,6 +452,73 @@ static GemmPlan plan_of(int batch, int M, int N, const int* rowA = nullptr, cons
   return p;
 }
 
+
+// ---- blocked Cholesky + triangular inverse (north star (3)) ------------------------------------------
+static OperandDesc op_rows(const MatBatch& m, int r0, int c0, int rows, int K) {
+  OperandDesc a;
+  a.src = m.t, a.d_off = m.d_off, a.batch = m.batch;
+  a.off0 = m.shift + (int64_t)r0 * m.stride() + c0;
+  a.rs = m.stride(), a.ks = 1, a.rows = rows, a.K = K;
+  return a;
+}
+static OperandDesc op_cols(const MatBatch& m, int r0, int c0, int rows, int K) {  // row operand i = column c0+i
+  OperandDesc a = op_rows(m, r0, c0, rows, K);
+  a.rs = 1, a.ks = m.stride();
+  return a;
+}
+static OutDesc out_sub(const MatBatch& m, int r0, int c0) {
+  OutDesc o;
+  o.dst = m.t, o.d_off = m.d_off;
+  o.off0 = m.shift + (int64_t)r0 * m.stride() + c0;
+  o.rs = m.stride(), o.cs = 1;
+  return o;
+}
+constexpr int PANEL = 64;
+
+void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv,
+                          int* d_stat) {
+  const int n = A.n, batch = A.batch;
+  if (n <= PANEL) {
+    chol_upper(ctx, nl, A, Uw, rdiag.t(), d_stat);
+    tri_inverse(ctx, nl, Uw, rdiag.t(), Vw, &Linv);
+    return;
+  }
+  mat_copy(ctx, nl, Uw, A, true);  // work on the upper triangle
+  mat_zero(ctx, nl, Linv);
+  for (int k0 = 0; k0 < n; k0 += PANEL) {
+    const int wk = std::min(PANEL, n - k0), n2 = n - k0 - wk;
+    MatBatch U11 = Uw.sub(k0, k0, wk), V11 = Vw.sub(k0, k0, wk), L11 = Linv.sub(k0, k0, wk);
+    chol_upper(ctx, nl, U11, U11, rdiag.t(), d_stat);
+    tri_inverse(ctx, nl, U11, rdiag.t(), V11, &L11);
+    if (n2 > 0) {
+      // U12 = L11^-1 A12
+      gemm_->slice(op_rows(Linv, k0, k0, wk, wk), fs1_);
+      gemm_->slice(op_cols(Uw, k0, k0 + wk, n2, wk), fs2_);
+      gemm_->multiply(fs1_, fs2_, plan_of(batch, wk, n2), out_sub(Uw, k0, k0 + wk));
+      // A22 -= U12^T U12
+      gemm_->slice(op_cols(Uw, k0, k0 + wk, n2, wk), fs2_);
+      mp::Tensor ut = Uw.t;
+      gemm_->multiply(fs2_, fs2_, plan_of(batch, n2, n2), out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
+    }
+  }
+  // off-diagonal panels of L^-1:  Linv[p, 0:k0] = -Linv_pp * ( L[p, 0:k0] * Linv[0:k0, 0:k0] )
+  tscr.alloc(std::max<size_t>(tscr.n, (size_t)batch * PANEL * n), nl);
+  for (int k0 = PANEL; k0 < n; k0 += PANEL) {
+    const int wk = std::min(PANEL, n - k0);
+    // T[i][c] = sum_r U[r][k0+i] * Linv[r][c], stored transposed: Tt[c][i]
+    gemm_->slice(op_cols(Uw, 0, k0, wk, k0), fs1_);
+    gemm_->slice(op_cols(Linv, 0, 0, k0, k0), fs2_);
+    OutDesc ot;
+    ot.dst = tscr.t(), ot.bstride = (int64_t)PANEL * n, ot.rs = 1, ot.cs = wk;
+    gemm_->multiply(fs1_, fs2_, plan_of(batch, wk, k0), ot);
+    gemm_->slice(op_rows(Linv, k0, k0, wk, wk), fs1_);
+    OperandDesc tb;
+    tb.src = tscr.t(), tb.batch = batch, tb.bstride = (int64_t)PANEL * n, tb.rs = wk, tb.ks = 1, tb.rows = k0, tb.K = wk;
+    gemm_->slice(tb, fs2_);
+    gemm_->multiply(fs1_, fs2_, plan_of(batch, wk, k0), out_sub(Linv, k0, 0), EPI_NEG);
+  }
+}
+
 // XY = X*Y per block (kept: both residual_R calls use it, MPMP.jl:1195,1209)
 void Solver::block_products_XY() {
   for (auto& g : bgroups_) {
@@ -466,9 +533,8 @@ void Solver::invert_X() {
   int sbase = 0;
   for (auto& g : bgroups_) {
     MatBatch A = blkbatch(g, X), U = blkbatch(g, Ux), V = blkbatch(g, Vx), Li = blkbatch(g, Linvx);
-    chol_upper(ctx, nl, A, U, rdiag.t(), d_status.as<int>() + sbase);
-    tri_inverse(ctx, nl, U, rdiag.t(), V, &Li);
-    gemm_->slice(rows_of(g, Vx), g.sA);
+    chol_inverse(A, U, V, Li, d_status.as<int>() + sbase);
+    gemm_->slice(cols_of(g, Linvx), g.sA);  // X^-1 = L^-T L^-1: row operand i = column i of L^-1
     gemm_->multiply(g.sA, g.sA, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, Xinv));
     sbase += (int)g.blocks.size();
   }
@@ -584,8 +650,7 @@ void Solver::decomposition() {
     MatBatch U{Us.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
     MatBatch V{Vs.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
     MatBatch Li{Linvs.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
-    chol_upper(ctx, nl, A, U, rdiag.t(), d_status.as<int>() + sbase);
-    tri_inverse(ctx, nl, U, rdiag.t(), V, &Li);
+    chol_inverse(A, U, V, Li, d_status.as<int>() + sbase);
     sbase += (int)g.clusters.size();
   }
   mark(-1 - CLRSDP_T_CHOL_S);
@@ -622,8 +687,7 @@ void Solver::decomposition() {
   {
     MatBatch A{Q.t(), d_qoff.as<int64_t>(), 1, n_y}, U{Uq.t(), d_qoff.as<int64_t>(), 1, n_y};
     MatBatch V{Vq.t(), d_qoff.as<int64_t>(), 1, n_y}, Li{Linvq.t(), d_qoff.as<int64_t>(), 1, n_y};
-    chol_upper(ctx, nl, A, U, rdiag.t(), d_status.as<int>() + 2 * (int)blocks_.size() + J);
-    tri_inverse(ctx, nl, U, rdiag.t(), V, &Li);
+    chol_inverse(A, U, V, Li, d_status.as<int>() + 2 * (int)blocks_.size() + J);
   }
   mark(-1 - CLRSDP_T_CHOL_Q);
 }
@@ -802,6 +866,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   CLR_CUDA(cudaSetDevice(ctx.device));
   double t0 = now_s();
   ev_marks_.clear();
+  CLR_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int) * n_status, ctx.stream));
   mark(CLRSDP_T_COUNT);  // whole iteration (extra bucket, reported as `seconds`)
   clrsdp_iter_info row;
   memset(&row, 0, sizeof(row));
@@ -857,8 +922,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
     int sbase = (int)blocks_.size();  // status slots of the Y blocks follow those of the X blocks
     for (auto& g : bgroups_) {
       MatBatch A = blkbatch(g, Y), U = blkbatch(g, Ux), V = blkbatch(g, Vx), Li = blkbatch(g, Linvy);
-      chol_upper(ctx, nl, A, U, rdiag.t(), d_status.as<int>() + sbase);
-      tri_inverse(ctx, nl, U, rdiag.t(), V, &Li);
+      chol_inverse(A, U, V, Li, d_status.as<int>() + sbase);
       sbase += (int)g.blocks.size();
     }
   }
@@ -1037,14 +1101,15 @@ int Solver::op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, 
   dst.ensure(sizeof(int) * batch);
   MatBatch Ab{a.t(), doff.as<int64_t>(), batch, n}, Ub{u.t(), doff.as<int64_t>(), batch, n};
   MatBatch Vb{v.t(), doff.as<int64_t>(), batch, n}, Lb{li.t(), doff.as<int64_t>(), batch, n};
-  chol_upper(ctx, nl, Ab, Ub, rd.t(), dst.as<int>());
-  tri_inverse(ctx, nl, Ub, rd.t(), Vb, &Lb);
+  CLR_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(int) * batch, ctx.stream));
+  rdiag.alloc(std::max<size_t>(rdiag.n, (size_t)batch * n), nl);
+  chol_inverse(Ab, Ub, Vb, Lb, dst.as<int>());
   std::vector<int> hs(batch);
   CLR_CUDA(cudaMemcpyAsync(hs.data(), dst.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, ctx.stream));
   ctx.sync();
   for (int s : hs)
     if (s) return CLRSDP_ERR_NOT_PD_X;
-  if (L) {  // L = U^T: transpose on the host side of the copy
+  if (L) {  // L = U^T: transpose on the host side of the copy (entries below the diagonal of U are ignored)
     std::vector<int8_t> sg(tot);
     std::vector<int64_t> ex(tot);
     std::vector<uint32_t> lb((size_t)nl * tot);
@@ -1054,9 +1119,10 @@ int Solver::op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, 
       for (int r = 0; r < n; r++)
         for (int cc = 0; cc < n; cc++) {
           int64_t s = (int64_t)bq * n * n + (int64_t)cc * n + r, t = (int64_t)bq * n * n + (int64_t)r * n + cc;
-          L->sign[t] = sg[s];
-          L->exp[t] = ex[s];
-          for (int k = 0; k < nl; k++) L->limb[(size_t)k * L->n + t] = lb[(size_t)k * tot + s];
+          bool upper = cc > r;  // U is only meaningful on and above its diagonal
+          L->sign[t] = upper ? 0 : sg[s];
+          L->exp[t] = upper ? 0 : ex[s];
+          for (int k = 0; k < nl; k++) L->limb[(size_t)k * L->n + t] = upper ? 0u : lb[(size_t)k * tot + s];
         }
   }
   if (Linv) to_host(li, 0, tot, Linv, 0);

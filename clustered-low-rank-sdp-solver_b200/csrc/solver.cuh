@@ -89,6 +89,9 @@ class Solver {
   void search_direction();
   void step_length(MpBuf& Linv, MpBuf& dM, int slot);
   void decomposition();
+  // Linv = (chol A)^-1 for a batch of SPD matrices: blocked right-looking Cholesky, panels on the CUDA cores,
+  // trailing updates and the off-diagonal inverse panels through the sliced tensor-core GEMM
+  void chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv, int* d_status);
   int check_status();
   void mark(int bucket_begin);
 
@@ -112,7 +115,8 @@ class Solver {
   MpBuf Vt, H, Px, Py, Tt, VD, QP, S, Us, Vs, Linvs, Bmat, Wt, Q, Uq, Vq, Linvq;
   MpBuf x, dx, d, c, rhs, tvec, tmpx, trx, y, dy, p, b, tmpy, zvec, dyr;
   MpBuf dX_pred, dY_pred, dx_pred, dy_pred;
-  MpBuf scal, rdiag, lam, work;
+  MpBuf scal, rdiag, lam, work, tscr;
+  Slice fs1_, fs2_;
   DevBuf d_status, d_flags, d_scal_out, d_qoff;
   std::vector<int> h_status;
   int n_status = 0;
