@@ -131,15 +131,26 @@ struct DevBuf {
 // a multiprecision tensor in HBM (planar layout of mpf.cuh)
 struct MpBuf {
   DevBuf buf;
-  size_t n = 0;
+  size_t n = 0;      // plane stride in words
+  size_t count = 0;  // numbers addressable through this buffer / view
   int nl = 0;
+  uint32_t* base = nullptr;  // non-null for a view into another MpBuf
   void alloc(size_t n_, int nl_) {
     n = n_ ? n_ : 1;
+    count = n;
     nl = nl_;
+    base = nullptr;
     buf.ensure((size_t)(nl + 1) * n * sizeof(uint32_t));
   }
-  mp::Tensor t() const { return mp::Tensor{buf.as<uint32_t>(), n}; }
-  uint32_t* w() const { return buf.as<uint32_t>(); }
+  // view of `cnt` numbers starting at element `off` of parent (shares the parent's planes)
+  void alias(const MpBuf& parent, size_t off, size_t cnt) {
+    n = parent.n;
+    count = cnt;
+    nl = parent.nl;
+    base = parent.w() + off;
+  }
+  mp::Tensor t() const { return mp::Tensor{w(), n}; }
+  uint32_t* w() const { return base ? base : buf.as<uint32_t>(); }
 };
 
 template <class T>

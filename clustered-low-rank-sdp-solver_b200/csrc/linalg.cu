@@ -190,6 +190,134 @@ trinv_kernel(mp::Tensor U, const int64_t* __restrict__ offU, int64_t shiftU, mp:
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused panel factorisation: U (upper Cholesky factor) and G = L^-1 = U^-T of one w x w SPD block, w <= 64,
+// entirely in shared memory (packed triangles). Gaussian elimination on the augmented matrix [A | I]:
+// the row operations that turn A into U turn I into L^-1, so the inverse costs no extra dependency
+// chain. Warp 0 runs the critical path one step ahead (update of row k+1, pivot sqrt/rsqrt, row
+// scaling) while the other warps apply update k to the rows below: ONE __syncthreads per step.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PANEL_THREADS = 512;
+__host__ __device__ inline int pk_u(int w, int r, int c) { return r * w - (r * (r - 1)) / 2 + (c - r); }  // r <= c
+__host__ __device__ inline int pk_g(int r, int j) { return (r * (r + 1)) / 2 + j; }                      // j <= r
+template <int NL>
+__global__ void __launch_bounds__(PANEL_THREADS)
+panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shiftA, int ldA, mp::Tensor Lm,
+                    const int64_t* __restrict__ offL, int64_t shiftL, int ldL, int w, int write_u,
+                    int* __restrict__ status) {
+  extern __shared__ uint32_t sm[];
+  const int ntri = w * (w + 1) / 2;
+  uint32_t* Us = sm;                                  // packed upper triangle of the work matrix / U
+  uint32_t* Gs = sm + (size_t)ntri * (NL + 2);        // packed lower triangle of G
+  __shared__ int bad;
+  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t oa = offA[b] + shiftA, ol = offL[b] + shiftL;
+  if (tid == 0) bad = status[b];
+  for (int idx = tid; idx < w * w; idx += nthr) {
+    int r = idx / w, c = idx % w;
+    if (r <= c) smem_put<NL>(Us, pk_u(w, r, c), ldm<NL>(A, oa + (int64_t)r * ldA + c));
+    if (c <= r) smem_put<NL>(Gs, pk_g(r, c), r == c ? mp::one<NL>() : mp::zero<NL>());
+  }
+  __syncthreads();
+  // step 0 of the critical path: pivot 0 and scaling of row 0
+  if (warp == 0) {
+    if (lane == 0) {
+      Num<NL> a = smem_get<NL>(Us, pk_u(w, 0, 0));
+      if (mp::is_zero(a) || a.neg) {
+        bad = 1;
+      } else {
+        Num<NL> rinv, d = nsqrt_rsqrt(a, rinv);
+        smem_put<NL>(Us, pk_u(w, 0, 0), d);
+        smem_put<NL>(Gs, pk_g(0, 0), rinv);
+      }
+    }
+    __syncwarp();
+    if (!bad) {
+      Num<NL> rinv = smem_get<NL>(Gs, pk_g(0, 0));
+      for (int c = 1 + lane; c < w; c += 32) smem_put<NL>(Us, pk_u(w, 0, c), nmul(smem_get<NL>(Us, pk_u(w, 0, c)), rinv));
+    }
+  }
+  __syncthreads();
+  for (int k = 0; k + 1 < w && !bad; k++) {
+    // row k of U and of G are final. Apply elimination step k to the rows below.
+    if (warp == 0) {
+      const int r = k + 1;
+      Num<NL> mult = smem_get<NL>(Us, pk_u(w, k, r));
+      for (int q = lane; q < w; q += 32) {
+        if (q >= r) {
+          int at = pk_u(w, r, q);
+          smem_put<NL>(Us, at, nsub(smem_get<NL>(Us, at), nmul(mult, smem_get<NL>(Us, pk_u(w, k, q)))));
+        } else if (q <= k) {
+          int at = pk_g(r, q);
+          smem_put<NL>(Gs, at, nsub(smem_get<NL>(Gs, at), nmul(mult, smem_get<NL>(Gs, pk_g(k, q)))));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        Num<NL> a = smem_get<NL>(Us, pk_u(w, r, r));
+        if (mp::is_zero(a) || a.neg) {
+          bad = 1;
+        } else {
+          Num<NL> rinv, d = nsqrt_rsqrt(a, rinv);
+          smem_put<NL>(Us, pk_u(w, r, r), d);
+          smem_put<NL>(sm + (size_t)2 * ntri * (NL + 2), 0, rinv);
+        }
+      }
+      __syncwarp();
+      if (!bad) {
+        Num<NL> rinv = smem_get<NL>(sm + (size_t)2 * ntri * (NL + 2), 0);
+        for (int q = lane; q < w; q += 32) {
+          if (q > r) {
+            int at = pk_u(w, r, q);
+            smem_put<NL>(Us, at, nmul(smem_get<NL>(Us, at), rinv));
+          } else {
+            int at = pk_g(r, q);  // q <= r, includes the unit diagonal
+            smem_put<NL>(Gs, at, nmul(smem_get<NL>(Gs, at), rinv));
+          }
+        }
+      }
+    } else {
+      const int rows = w - (k + 2);
+      for (int idx = tid - 32; idx < rows * w; idx += nthr - 32) {
+        int r = k + 2 + idx / w, q = idx % w;
+        if (q >= r) {
+          int at = pk_u(w, r, q);
+          smem_put<NL>(Us, at, nsub(smem_get<NL>(Us, at), nmul(smem_get<NL>(Us, pk_u(w, k, r)), smem_get<NL>(Us, pk_u(w, k, q)))));
+        } else if (q <= k) {
+          int at = pk_g(r, q);
+          smem_put<NL>(Gs, at, nsub(smem_get<NL>(Gs, at), nmul(smem_get<NL>(Us, pk_u(w, k, r)), smem_get<NL>(Gs, pk_g(k, q)))));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int idx = tid; idx < w * w; idx += nthr) {
+    int r = idx / w, c = idx % w;
+    if (write_u) stm<NL>(A, oa + (int64_t)r * ldA + c, r <= c ? smem_get<NL>(Us, pk_u(w, r, c)) : mp::zero<NL>());
+    stm<NL>(Lm, ol + (int64_t)r * ldL + c, c <= r ? smem_get<NL>(Gs, pk_g(r, c)) : mp::zero<NL>());
+  }
+  if (tid == 0) status[b] = bad;
+}
+int panel_width(int nl) { return nl <= 8 ? 64 : 32; }
+void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status) {
+  if (A.n > panel_width(nl)) throw SolverError(-1, "panel_factor: block larger than the panel width");
+  DISPATCH_NL(nl, {
+    size_t words = ((size_t)A.n * (A.n + 1) + 1) * (NL + 2);
+    static bool attr[17] = {false};
+    if (!attr[NL]) {
+      CLR_CUDA(cudaFuncSetAttribute(panel_factor_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr[NL] = true;
+    }
+    std::string nm = "panel_factor_n" + std::to_string(A.n);
+    int tk = ctx.begin(nm.c_str());
+    panel_factor_kernel<NL><<<A.batch, PANEL_THREADS, words * sizeof(uint32_t), ctx.stream>>>(
+        A.t, A.d_off, A.shift, A.stride(), Linv.t, Linv.d_off, Linv.shift, Linv.stride(), A.n, write_u ? 1 : 0,
+        d_status);
+    ctx.end(tk);
+  });
+}
+
 static dim3 tri_block(int n) {
   int cx = std::min(((n + 31) / 32) * 32, 256);
   int p = std::max(1, TRI_THREADS / cx);
@@ -249,25 +377,27 @@ __device__ bool any_eig_below(const uint32_t* dsm, const uint32_t* e2sm, int n, 
 
 template <int NL>
 __global__ void __launch_bounds__(512)
-lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Tensor out, int64_t out_off) {
+lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Tensor out, const int* __restrict__ out_index) {
   extern __shared__ uint32_t sm[];
-  // smem layout (in Num slots of NL+2 words): v[n], q[n], d[n], e2[n], red[33], misc[8], partial[P*CX]
+  // smem layout (in Num slots of NL+2 words): v[n], q[n], d[n], e2[n], eabs[n], red[33], misc[8], partial[P*CX]
   const int CX = blockDim.x, P = blockDim.y;
   uint32_t* vsm = sm;
   uint32_t* qsm = vsm + (size_t)n * (NL + 2);
   uint32_t* dsm = qsm + (size_t)n * (NL + 2);
   uint32_t* e2sm = dsm + (size_t)n * (NL + 2);
-  uint32_t* red = e2sm + (size_t)n * (NL + 2);
+  uint32_t* easm = e2sm + (size_t)n * (NL + 2);
+  uint32_t* red = easm + (size_t)n * (NL + 2);
   uint32_t* misc = red + 33 * (NL + 2);
   uint32_t* part_sm = misc + 8 * (NL + 2);
   __shared__ int flag, first_t;
   const int b = blockIdx.x, c = threadIdx.x, part = threadIdx.y;
   const int tid = part * CX + c, nthr = CX * P;
   const int64_t ow = offW[b];
+  const int64_t out_at = out_index ? out_index[b] : b;
   auto Wat = [&](int r, int cc) { return ow + (int64_t)r * n + cc; };
 
   if (n == 1) {
-    if (tid == 0) stm<NL>(out, out_off + b, ldm<NL>(W, ow));
+    if (tid == 0) stm<NL>(out, out_at, ldm<NL>(W, ow));
     return;
   }
   // ---- Householder tridiagonalisation (symmetric full storage, both triangles kept up to date) ----
@@ -281,6 +411,7 @@ lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Ten
       if (mp::is_zero(tail)) {
         flag = 1;  // column already tridiagonal
         smem_put<NL>(e2sm, k, nmul(x1, x1));
+        smem_put<NL>(easm, k, mp::fabs(x1));
       } else {
         flag = 0;
         Num<NL> sigma = nadd(tail, nmul(x1, x1));
@@ -291,6 +422,7 @@ lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Ten
         smem_put<NL>(misc, 0, alpha);
         smem_put<NL>(misc, 1, binv);
         smem_put<NL>(e2sm, k, sigma);  // alpha^2
+        smem_put<NL>(easm, k, mp::fabs(alpha));
       }
     }
     __syncthreads();
@@ -335,6 +467,7 @@ lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Ten
   if (tid == 0) {
     Num<NL> x1 = ldm<NL>(W, Wat(n - 2, n - 1));
     smem_put<NL>(e2sm, n - 2, nmul(x1, x1));
+    smem_put<NL>(easm, n - 2, mp::fabs(x1));
   }
   __syncthreads();
   // ---- Gershgorin interval (thread 0) ----
@@ -342,8 +475,8 @@ lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Ten
     Num<NL> lo = mp::zero<NL>(), hi = mp::zero<NL>(), nrm = mp::zero<NL>();
     for (int i = 0; i < n; i++) {
       Num<NL> rad = mp::zero<NL>();
-      if (i > 0) rad = nadd(rad, nsqrt(smem_get<NL>(e2sm, i - 1)));
-      if (i + 1 < n) rad = nadd(rad, nsqrt(smem_get<NL>(e2sm, i)));
+      if (i > 0) rad = nadd(rad, smem_get<NL>(easm, i - 1));
+      if (i + 1 < n) rad = nadd(rad, smem_get<NL>(easm, i));
       Num<NL> di = smem_get<NL>(dsm, i);
       Num<NL> a1 = nsub(di, rad), a2 = nadd(di, rad);
       if (i == 0 || ncmp(a1, lo) < 0) lo = a1;
@@ -439,18 +572,17 @@ lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Ten
   }
   if (tid == 0) {
     Num<NL> lo = smem_get<NL>(misc, 2), hi = smem_get<NL>(misc, 3);
-    stm<NL>(out, out_off + b, mp::mul_2exp(nadd(lo, hi), -1));
+    stm<NL>(out, out_at, mp::mul_2exp(nadd(lo, hi), -1));
   }
 }
 
-size_t lambda_min_work_elems(int, int) { return 1; }
-void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, int64_t out_off, mp::Tensor) {
+void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, const int* d_out_index) {
   if (W.n > 512) throw SolverError(-1, "lambda_min: n > 512 not supported");
   int cx = std::min(1024, ((W.n + 31) / 32) * 32);
   int P = std::max(1, 512 / cx);
   dim3 blk(cx, P, 1);
   DISPATCH_NL(nl, {
-    size_t words = (size_t)(4 * W.n + 33 + 8 + P * cx) * (NL + 2);
+    size_t words = (size_t)(5 * W.n + 33 + 8 + P * cx) * (NL + 2);
     static bool attr[17] = {false};
     if (!attr[NL]) {
       CLR_CUDA(cudaFuncSetAttribute(lambda_min_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -458,7 +590,7 @@ void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, int64_t out
     }
     std::string nm = "lambda_min_n" + std::to_string(W.n);
     int tk = ctx.begin(nm.c_str());
-    lambda_min_kernel<NL><<<W.batch, blk, words * sizeof(uint32_t), ctx.stream>>>(W.t, W.d_off, W.n, out, out_off);
+    lambda_min_kernel<NL><<<W.batch, blk, words * sizeof(uint32_t), ctx.stream>>>(W.t, W.d_off, W.n, out, d_out_index);
     ctx.end(tk);
   });
 }

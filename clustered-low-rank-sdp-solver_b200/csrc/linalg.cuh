@@ -32,11 +32,15 @@ struct MatBatch {
 void chol_upper(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& U, mp::Tensor rdiag, int* d_status);
 // V = U^-1 (upper triangular, row-major) and optionally Linv = V^T = L^-1 (lower triangular, row-major).
 void tri_inverse(Ctx& ctx, int nl, const MatBatch& U, mp::Tensor rdiag, const MatBatch& V, const MatBatch* Linv);
+// Fused panel factorisation of w x w SPD blocks (w <= panel_width(nl)): A is overwritten by its upper Cholesky
+// factor U (if write_u) and Linv receives L^-1 = U^-T (lower); both may be sub-blocks of larger matrices.
+int panel_width(int nl);
+void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status);
 // smallest eigenvalue of each symmetric matrix (destroys W): out[out_off + b].
 // Replaces approx_eig_qr! + min over real parts (MPMP.jl:1857-1870) by Householder tridiagonalisation
 // + multisection with Sturm counts.
-void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, int64_t out_off, mp::Tensor work);
-size_t lambda_min_work_elems(int batch, int n);
+// out[d_out_index ? d_out_index[b] : b] receives the result of matrix b.
+void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, const int* d_out_index);
 
 // ---- elementwise ---------------------------------------------------------------------------------------
 // out[i] = sa*a[i] + sb*b[i], sa,sb in {-1,0,+1}; i in [0,n) at offsets (oo, ao, bo)

@@ -181,8 +181,13 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
     clusters_.push_back(c);
   }
   // arenas
-  for (MpBuf* t : {&X, &Y, &Xinv, &R, &P, &Z, &dX, &dY, &XY, &T1, &T2, &Ux, &Vx, &Linvx, &Linvy, &dX_pred, &dY_pred})
-    t->alloc(blkN, nl);
+  for (MpBuf* t : {&XY2, &dXY2, &Linv2, &U2, &W2, &T1d, &T2d}) t->alloc(2 * blkN, nl);
+  X.alias(XY2, 0, blkN), Y.alias(XY2, blkN, blkN);
+  dX.alias(dXY2, 0, blkN), dY.alias(dXY2, blkN, blkN);
+  Linvx.alias(Linv2, 0, blkN), Linvy.alias(Linv2, blkN, blkN);
+  Ux.alias(U2, 0, blkN), Vx.alias(U2, blkN, blkN);
+  T1.alias(T1d, 0, blkN), T2.alias(T2d, 0, blkN);
+  for (MpBuf* t : {&Xinv, &R, &P, &Z, &XY, &dX_pred, &dY_pred}) t->alloc(blkN, nl);
   Vt.alloc(vtN, nl);
   H.alloc(hN, nl);
   Px.alloc(pN, nl);
@@ -200,7 +205,7 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
   for (auto& g : bgroups_) maxrd = std::max<int64_t>(maxrd, (int64_t)g.blocks.size() * g.nb);
   for (auto& g : cgroups_) maxrd = std::max<int64_t>(maxrd, (int64_t)g.clusters.size() * g.dimS);
   rdiag.alloc(maxrd, nl);
-  lam.alloc(blocks_.size(), nl);
+  lam.alloc(2 * blocks_.size(), nl);
   work.alloc(std::max<size_t>({(size_t)4096, reduce_work_elems(), gemv_work_elems(n_y, sumS), gemv_work_elems(sumS, n_y)}), nl);
   n_status = 2 * (int)blocks_.size() + J + 1;  // X blocks, Y blocks, S_j, Q
   d_status.ensure(sizeof(int) * n_status);
@@ -263,8 +268,8 @@ void Solver::upload_tables() {
   // per-group batch tables
   for (auto& g : bgroups_) {
     int nblk = (int)g.blocks.size(), m = g.m;
-    std::vector<int64_t> offBlk, g1A, g1C, g2B, g2C, waA, waC;
-    std::vector<int> g1rB, g2rA, warB;
+    std::vector<int64_t> offBlk, offBlk2, g1A, g1C, g2B, g2C, waA, waC;
+    std::vector<int> g1rB, g2rA, warB, lamIdx2;
     for (int q = 0; q < nblk; q++) {
       const HostBlock& bk = blocks_[g.blocks[q]];
       offBlk.push_back(bk.off);
@@ -285,6 +290,11 @@ void Solver::upload_tables() {
         warB.push_back(q * g.delta);
       }
     }
+    offBlk2 = offBlk;
+    for (int q = 0; q < nblk; q++) offBlk2.push_back(offBlk[q] + blkN);
+    for (int q = 0; q < nblk; q++) lamIdx2.push_back(g.blocks[q]);
+    for (int q = 0; q < nblk; q++) lamIdx2.push_back((int)blocks_.size() + g.blocks[q]);
+    up(g.offBlk2, offBlk2, s), up(g.lamIdx2, lamIdx2, s);
     up(g.offBlk, offBlk, s), up(g.g1_offA, g1A, s), up(g.g1_offC, g1C, s), up(g.g1_rowB, g1rB, s);
     up(g.g2_offB, g2B, s), up(g.g2_offC, g2C, s), up(g.g2_rowA, g2rA, s);
     up(g.wa_offA, waA, s), up(g.wa_offC, waC, s), up(g.wa_rowB, warB, s);
@@ -473,23 +483,25 @@ static OutDesc out_sub(const MatBatch& m, int r0, int c0) {
   o.rs = m.stride(), o.cs = 1;
   return o;
 }
-constexpr int PANEL = 64;
 
 void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv,
-                          int* d_stat) {
+                          int* d_stat, bool want_u) {
   const int n = A.n, batch = A.batch;
-  if (n <= PANEL) {
-    chol_upper(ctx, nl, A, Uw, rdiag.t(), d_stat);
-    tri_inverse(ctx, nl, Uw, rdiag.t(), Vw, &Linv);
+  const int PANEL = panel_width(nl);
+  (void)Vw;
+  if (n <= PANEL && !want_u) {
+    panel_factor(ctx, nl, A, Linv, false, d_stat);  // A is only read
     return;
   }
   mat_copy(ctx, nl, Uw, A, true);  // work on the upper triangle
+  if (n <= PANEL) {
+    panel_factor(ctx, nl, Uw, Linv, true, d_stat);
+    return;
+  }
   mat_zero(ctx, nl, Linv);
   for (int k0 = 0; k0 < n; k0 += PANEL) {
     const int wk = std::min(PANEL, n - k0), n2 = n - k0 - wk;
-    MatBatch U11 = Uw.sub(k0, k0, wk), V11 = Vw.sub(k0, k0, wk), L11 = Linv.sub(k0, k0, wk);
-    chol_upper(ctx, nl, U11, U11, rdiag.t(), d_stat);
-    tri_inverse(ctx, nl, U11, rdiag.t(), V11, &L11);
+    panel_factor(ctx, nl, Uw.sub(k0, k0, wk), Linv.sub(k0, k0, wk), want_u, d_stat);
     if (n2 > 0) {
       // U12 = L11^-1 A12
       gemm_->slice(op_rows(Linv, k0, k0, wk, wk), fs1_);
@@ -528,15 +540,21 @@ void Solver::block_products_XY() {
   }
 }
 
-// X^-1 per block through the Cholesky factor (spd_inv!, MPMP.jl:764-801): X = U^T U, V = U^-1, X^-1 = V V^T
-void Solver::invert_X() {
+// Cholesky factors of X and Y for all blocks in one batch (spd_inv! :764-801 and cho! :1846): X = Lx Lx^T,
+// Y = Ly Ly^T; only the inverse factors are kept. X and Y do not change until the update at the end of
+// the iteration, so both factorisations run together and share the latency of the pivot chain.
+void Solver::factor_XY() {
   int sbase = 0;
   for (auto& g : bgroups_) {
-    MatBatch A = blkbatch(g, X), U = blkbatch(g, Ux), V = blkbatch(g, Vx), Li = blkbatch(g, Linvx);
-    chol_inverse(A, U, V, Li, d_status.as<int>() + sbase);
-    gemm_->slice(cols_of(g, Linvx), g.sA);  // X^-1 = L^-T L^-1: row operand i = column i of L^-1
+    chol_inverse(blkbatch2(g, XY2), blkbatch2(g, U2), blkbatch2(g, U2), blkbatch2(g, Linv2), d_status.as<int>() + sbase);
+    sbase += 2 * (int)g.blocks.size();
+  }
+}
+// X^-1 = Lx^-T Lx^-1 (spd_inv!, MPMP.jl:766)
+void Solver::invert_X() {
+  for (auto& g : bgroups_) {
+    gemm_->slice(cols_of(g, Linvx), g.sA);  // row operand i = column i of L^-1
     gemm_->multiply(g.sA, g.sA, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, Xinv));
-    sbase += (int)g.blocks.size();
   }
 }
 
@@ -763,26 +781,28 @@ void Solver::search_direction() {
   mark(-1 - CLRSDP_T_DY);
 }
 
-// compute_step_length (MPMP.jl:1829-1898): lambda_min( L^-1 dM L^-T ) over all blocks -> scal[slot]
-void Solver::step_length(MpBuf& Linv, MpBuf& dM, int slot) {
+// compute_step_length (MPMP.jl:1829-1898) for X and Y together: lambda_min( L^-1 dM L^-T ) per block
+void Solver::step_lengths() {
   for (auto& g : bgroups_) {
-    int nblk = (int)g.blocks.size();
-    gemm_->slice(rows_of(g, dM), g.sA);
-    gemm_->slice(rows_of(g, Linv), g.sLinv);
+    int nb2 = 2 * (int)g.blocks.size();
+    OperandDesc a;
+    a.src = dXY2.t(), a.d_off = g.offBlk2.as<int64_t>(), a.batch = nb2, a.rows = g.nb, a.K = g.nb, a.rs = g.nb, a.ks = 1;
+    gemm_->slice(a, g.sA);
+    a.src = Linv2.t();
+    gemm_->slice(a, g.sLinv);
     // T[i][j] = sum_k dM[i][k] Linv[j][k], stored transposed
-    gemm_->multiply(g.sA, g.sLinv, plan_of(nblk, g.nb, g.nb), out_blk(g, T1, true));
-    gemm_->slice(rows_of(g, T1), g.sB);
-    gemm_->multiply(g.sLinv, g.sB, plan_of(nblk, g.nb, g.nb), out_blk(g, T2));
-    ew_symmetrize(ctx, nl, blkbatch(g, T1), T2.t());
-    // lam[] is indexed by position in group order
-    int64_t base = 0;
-    for (auto& g2 : bgroups_) {
-      if (&g2 == &g) break;
-      base += (int64_t)g2.blocks.size();
-    }
-    lambda_min(ctx, nl, blkbatch(g, T1), lam.t(), base, work.t());
+    OutDesc o;
+    o.dst = T1d.t(), o.d_off = g.offBlk2.as<int64_t>(), o.rs = 1, o.cs = g.nb;
+    gemm_->multiply(g.sA, g.sLinv, plan_of(nb2, g.nb, g.nb), o);
+    a.src = T1d.t();
+    gemm_->slice(a, g.sB);
+    o.dst = T2d.t(), o.rs = g.nb, o.cs = 1;
+    gemm_->multiply(g.sLinv, g.sB, plan_of(nb2, g.nb, g.nb), o);
+    ew_symmetrize(ctx, nl, blkbatch2(g, W2), T2d.t());
+    lambda_min(ctx, nl, blkbatch2(g, W2), lam.t(), g.lamIdx2.as<int>());
   }
-  reduce_min(ctx, nl, lam.t(), 0, (int64_t)blocks_.size(), scal.t(), slot, work.t());
+  reduce_min(ctx, nl, lam.t(), 0, (int64_t)blocks_.size(), scal.t(), SL_LAM_X, work.t());
+  reduce_min(ctx, nl, lam.t(), (int64_t)blocks_.size(), (int64_t)blocks_.size(), scal.t(), SL_LAM_Y, work.t());
 }
 
 // ---- timing marks: bucket >= 0 begins a bucket, -1-bucket ends it -----------------------------------
@@ -807,10 +827,18 @@ int Solver::check_status() {
   CLR_CUDA(cudaMemcpyAsync(h_flags, d_flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx.stream));
   ctx.sync();
   int nb = (int)blocks_.size();
-  for (int i = 0; i < nb; i++)
-    if (h_status[i]) return CLRSDP_ERR_NOT_PD_X;
-  for (int i = nb; i < 2 * nb; i++)
-    if (h_status[i]) return CLRSDP_ERR_NOT_PD_Y;
+  {  // slots [0, 2 nb): per group, first the X blocks then the Y blocks
+    int base = 0, bad_y = 0;
+    for (auto& g : bgroups_) {
+      int n1 = (int)g.blocks.size();
+      for (int i = 0; i < n1; i++)
+        if (h_status[base + i]) return CLRSDP_ERR_NOT_PD_X;
+      for (int i = n1; i < 2 * n1; i++)
+        if (h_status[base + i]) bad_y = 1;
+      base += 2 * n1;
+    }
+    if (bad_y) return CLRSDP_ERR_NOT_PD_Y;
+  }
   for (int i = 2 * nb; i < 2 * nb + J; i++)
     if (h_status[i]) return CLRSDP_ERR_SINGULAR_S;
   if (h_status[2 * nb + J]) return CLRSDP_ERR_SINGULAR_Q;
@@ -884,6 +912,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   for (auto& g : bgroups_) ew_residual_R(ctx, nl, blkbatch(g, R), scal.t(), SL_MU_P, XY.t(), nullptr);
   mark(-1 - CLRSDP_T_R);
   mark(CLRSDP_T_XINV);
+  factor_XY();
   invert_X();
   mark(-1 - CLRSDP_T_XINV);
   mark(CLRSDP_T_DECOMP);
@@ -917,16 +946,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   mark(-1 - CLRSDP_T_CORRECTOR);
   // step 7
   mark(CLRSDP_T_ALPHA);
-  step_length(Linvx, dX, SL_LAM_X);
-  {
-    int sbase = (int)blocks_.size();  // status slots of the Y blocks follow those of the X blocks
-    for (auto& g : bgroups_) {
-      MatBatch A = blkbatch(g, Y), U = blkbatch(g, Ux), V = blkbatch(g, Vx), Li = blkbatch(g, Linvy);
-      chol_inverse(A, U, V, Li, d_status.as<int>() + sbase);
-      sbase += (int)g.blocks.size();
-    }
-  }
-  step_length(Linvy, dY, SL_LAM_Y);
+  step_lengths();
   scalar_program(ctx, nl, SP_ALPHA, scal.t(), d_flags.as<int>(), nullptr);
   mark(-1 - CLRSDP_T_ALPHA);
   // step 8
@@ -1016,7 +1036,7 @@ int64_t Solver::fetch(const char* name, int j, int l, clrsdp_mp_out* out) {
   std::map<std::string, MpBuf*> vecs = {{"x", &x}, {"dx", &dx}, {"d", &d}, {"c", &c}, {"dx_pred", &dx_pred},
                                         {"y", &y}, {"dy", &dy}, {"p", &p}, {"b", &b}, {"dy_pred", &dy_pred}};
   auto vit = vecs.find(nm);
-  if (vit != vecs.end()) return put(*vit->second, 0, (int64_t)vit->second->n);
+  if (vit != vecs.end()) return put(*vit->second, 0, (int64_t)vit->second->count);
   std::map<std::string, MpBuf*> blks = {{"X", &X}, {"Y", &Y}, {"Xinv", &Xinv}, {"R", &R}, {"P", &P}, {"Z", &Z},
                                         {"dX", &dX}, {"dY", &dY}, {"XY", &XY}, {"dX_pred", &dX_pred},
                                         {"dY_pred", &dY_pred}, {"Linvx", &Linvx}, {"Linvy", &Linvy}};
@@ -1103,7 +1123,7 @@ int Solver::op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, 
   MatBatch Vb{v.t(), doff.as<int64_t>(), batch, n}, Lb{li.t(), doff.as<int64_t>(), batch, n};
   CLR_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(int) * batch, ctx.stream));
   rdiag.alloc(std::max<size_t>(rdiag.n, (size_t)batch * n), nl);
-  chol_inverse(Ab, Ub, Vb, Lb, dst.as<int>());
+  chol_inverse(Ab, Ub, Vb, Lb, dst.as<int>(), true);
   std::vector<int> hs(batch);
   CLR_CUDA(cudaMemcpyAsync(hs.data(), dst.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, ctx.stream));
   ctx.sync();
@@ -1148,7 +1168,7 @@ void Solver::op_lambda_min(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* 
   for (int i = 0; i < batch; i++) off[i] = (int64_t)i * n * n;
   DevBuf doff;
   upload(doff, off, ctx.stream);
-  lambda_min(ctx, nl, MatBatch{a.t(), doff.as<int64_t>(), batch, n}, out.t(), 0, work.t());
+  lambda_min(ctx, nl, MatBatch{a.t(), doff.as<int64_t>(), batch, n}, out.t(), nullptr);
   ctx.sync();
   to_host(out, 0, batch, lamo, 0);
 }

@@ -27,6 +27,7 @@ struct BlockGroup {
   int m, delta, nb, Nv, np;
   std::vector<int> blocks;
   DevBuf offBlk;                      // [nblk] block arena offsets
+  DevBuf offBlk2, lamIdx2;            // [2 nblk] offsets into the paired (X|Y) arenas; output slots of lambda_min
   DevBuf g1_offA, g1_offC, g1_rowB;   // pairing GEMM 1 items (blk, s, r)
   DevBuf g2_offB, g2_offC, g2_rowA;   // pairing GEMM 2 items (blk, r)
   DevBuf wa_offA, wa_offC, wa_rowB;   // weighted-A GEMM items (blk, pair)
@@ -77,6 +78,7 @@ class Solver {
   void upload_tables();
   void build_static_slices();
   MatBatch blkbatch(BlockGroup& g, MpBuf& t) { return MatBatch{t.t(), g.offBlk.as<int64_t>(), (int)g.blocks.size(), g.nb}; }
+  MatBatch blkbatch2(BlockGroup& g, MpBuf& t) { return MatBatch{t.t(), g.offBlk2.as<int64_t>(), 2 * (int)g.blocks.size(), g.nb}; }
   OperandDesc rows_of(BlockGroup& g, MpBuf& t);
   OperandDesc cols_of(BlockGroup& g, MpBuf& t);
   OutDesc out_blk(BlockGroup& g, MpBuf& t, bool transposed = false);
@@ -87,11 +89,13 @@ class Solver {
   void weighted_A(MpBuf& a, MpBuf& out, MpBuf& E, int sign);
   void compute_residuals(bool from_pairings);
   void search_direction();
-  void step_length(MpBuf& Linv, MpBuf& dM, int slot);
+  void factor_XY();
+  void step_lengths();
   void decomposition();
   // Linv = (chol A)^-1 for a batch of SPD matrices: blocked right-looking Cholesky, panels on the CUDA cores,
   // trailing updates and the off-diagonal inverse panels through the sliced tensor-core GEMM
-  void chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv, int* d_status);
+  void chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv, int* d_status,
+                    bool want_u = false);
   int check_status();
   void mark(int bucket_begin);
 
@@ -111,7 +115,8 @@ class Solver {
   DevBuf d_row_item, d_linv_off, d_x_off64, d_row0, d_itemK;
   StructTables st_;
   // arenas
-  MpBuf X, Y, Xinv, R, P, Z, dX, dY, XY, T1, T2, Ux, Vx, Linvx, Linvy;
+  MpBuf XY2, dXY2, Linv2, U2, W2, T1d, T2d;  // paired arenas: X|Y, dX|dY, Lx^-1|Ly^-1, work
+  MpBuf X, Y, Xinv, R, P, Z, dX, dY, XY, T1, T2, Ux, Vx, Linvx, Linvy;  // X,Y,dX,dY,Linv*,T1,T2,Ux are views
   MpBuf Vt, H, Px, Py, Tt, VD, QP, S, Us, Vs, Linvs, Bmat, Wt, Q, Uq, Vq, Linvq;
   MpBuf x, dx, d, c, rhs, tvec, tmpx, trx, y, dy, p, b, tmpy, zvec, dyr;
   MpBuf dX_pred, dY_pred, dx_pred, dy_pred;
