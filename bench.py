@@ -251,12 +251,22 @@ def main():
         return
     peaks = measured_peaks()
     macs, pmac = algorithmic_int8_macs(bi, prec)
-    mma = prof.get("mma_planes", dict(ms=0.0, launches=0, work=0.0))
+    mma = dict(ms=0.0, launches=0, work=0.0)
+    for k, v in prof.items():          # kernel names carry the GEMM shape: mma_planes_M.._N.._K.._b..
+        if k.startswith("mma_planes"):
+            for f in mma:
+                mma[f] += v[f]
     # int8 dense tensor peak: not in MEASURED_PEAKS.json; nominal 2x the measured bf16 rate (B200_PROFILING.md
     # gives int8 = fp8 = 2x bf16 nominal), stated as such
     int8_peak_tops = 2.0 * peaks["bf16_tflops"]
     mma_tops = (2.0 * mma["work"] / (mma["ms"] * 1e-3) / 1e12) if mma["ms"] > 0 else 0.0
-    top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]
+    agg = {}
+    for k, v in prof.items():
+        base = k.split("_M")[0] if k.startswith("mma_planes") else k
+        a = agg.setdefault(base, dict(ms=0.0, launches=0))
+        a["ms"] += v["ms"]
+        a["launches"] += v["launches"]
+    top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]
     roofline = dict(bound="tensor", kernel="mma_planes_kernel", achieved=mma_tops, peak=int8_peak_tops, unit="TOP/s (int8)",
                     frac=mma_tops / int8_peak_tops if int8_peak_tops else None, traffic=None,
                     peak_source=f"2 x bf16_tflops ({peaks['source']}); int8 peak itself not measured",

@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["gemm_i8.cu", "linalg.cu", "solver.cu", "capi.cu"]
-HEADERS = ["mpf.cuh", "common.cuh", "gemm_i8.cuh", "linalg.cuh", "solver.cuh", os.path.join("..", "..", "include", "clrsdp.h")]
+HEADERS = ["mpf.cuh", "common.cuh", "gemm_i8.cuh", "linalg.cuh", "solver.cuh", "comm.cuh", os.path.join("..", "..", "include", "clrsdp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 LIB = os.path.join(CSRC, "libclrsdp.so")
@@ -43,7 +43,7 @@ def build(verbose=True):
         list(ex.map(run, jobs))
     objs = [os.path.join(CSRC, s.replace(".cu", ".o")) for s in SOURCES]
     if jobs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd, cwd=CSRC)

@@ -166,12 +166,22 @@ CAPI int clrsdp_op_elementwise(clrsdp_handle h, int op, const clrsdp_mp* a, cons
   });
 }
 CAPI int clrsdp_comm_unique_id(uint8_t id[128]) {
-  (void)id;
-  return CLRSDP_ERR_NCCL;  // multi-GPU sharding arrives with SURVEY §8e; see DESIGN.md
+  if (!id) return CLRSDP_ERR_BAD_ARG;
+  try {
+    ncclUniqueId uid;
+    if (clr::NcclApi::get().GetUniqueId(&uid) != ncclSuccess) return CLRSDP_ERR_NCCL;
+    memcpy(id, uid.internal, 128);
+    return CLRSDP_OK;
+  } catch (...) {
+    return CLRSDP_ERR_NCCL;
+  }
 }
 CAPI int clrsdp_comm_init(clrsdp_handle h, int n_ranks, int rank, const uint8_t id[128]) {
-  (void)h, (void)n_ranks, (void)rank, (void)id;
-  return CLRSDP_ERR_NCCL;
+  return guard(h, [&](clr::Solver& s) {
+    if (!id) return (int)CLRSDP_ERR_BAD_ARG;
+    s.comm_init(n_ranks, rank, id);
+    return 0;
+  });
 }
 CAPI int64_t clrsdp_launch_count(clrsdp_handle h) { return (h && h->s) ? h->s->ctx.launches : 0; }
 CAPI int clrsdp_profile_reset(clrsdp_handle h, int enable) {

@@ -1,6 +1,8 @@
 // linalg.cu — CUDA-core multiprecision kernels (see linalg.cuh). One thread owns one number in registers;
 // tensors are planar in HBM so that a warp's 32 numbers are one coalesced line per limb plane.
 #include "linalg.cuh"
+#include "../../include/clrsdp.h"
+#include "comm.cuh"
 
 #include <algorithm>
 
@@ -1098,6 +1100,34 @@ void assemble_weighted(Ctx& ctx, int nl, const StructTables& st, mp::Tensor QP, 
   DISPATCH_NL(nl, {
     int tk = ctx.begin("assemble_weighted", (double)blk_total * 4.0 * (NL + 1) * 3.0);
     assemble_kernel<NL><<<ew_grid(ctx, blk_total), 128, 0, ctx.stream>>>(st, QP, out, E, sign, blk_total);
+    ctx.end(tk);
+  });
+}
+
+// =========================================================================================================
+// combination of the per-rank partial tensors after ncclAllGather (rank order => identical on all ranks)
+// =========================================================================================================
+template <int NL>
+__global__ void combine_ranks_kernel(const uint32_t* __restrict__ g, int nranks, int64_t n, mp::Tensor out, int64_t off,
+                                     int op) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    Num<NL> acc = mp::load<NL>(g, (size_t)n, (size_t)i);
+    for (int r = 1; r < nranks; r++) {
+      Num<NL> v = mp::load<NL>(g + (size_t)r * (NL + 1) * n, (size_t)n, (size_t)i);
+      if (op == COMB_SUM)
+        acc = mp::add(acc, v);
+      else if (op == COMB_MAX)
+        acc = mp::cmp(acc, v) >= 0 ? acc : v;
+      else
+        acc = mp::cmp(acc, v) <= 0 ? acc : v;
+    }
+    stm<NL>(out, off + i, acc);
+  }
+}
+void combine_ranks(Ctx& ctx, int nl, const uint32_t* gathered, int nranks, int64_t n, mp::Tensor out, int64_t off, int op) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("combine_ranks", (double)n * 4.0 * (NL + 1) * (nranks + 1));
+    combine_ranks_kernel<NL><<<ew_grid(ctx, n), 128, 0, ctx.stream>>>(gathered, nranks, n, out, off, op);
     ctx.end(tk);
   });
 }

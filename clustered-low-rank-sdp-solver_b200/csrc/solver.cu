@@ -49,9 +49,34 @@ Solver::Solver(int prec_bits, int device) : nl(prec_bits / 32), prec(prec_bits) 
 
 Solver::~Solver() {
   cudaSetDevice(ctx.device);
+  if (comm_.comm) NcclApi::get().CommDestroy(comm_.comm);
   for (auto e : ev_) cudaEventDestroy(e);
   for (auto e : ctx.pool) cudaEventDestroy(e);
   if (ctx.stream) cudaStreamDestroy(ctx.stream);
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------
+void Solver::comm_init(int n_ranks, int rank, const uint8_t* id) {
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw SolverError(CLRSDP_ERR_BAD_ARG, "comm_init: bad rank");
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  if (n_ranks == 1) return;
+  ncclUniqueId uid;
+  memcpy(uid.internal, id, NCCL_UNIQUE_ID_BYTES);
+  CLR_NCCL(NcclApi::get().CommInitRank(&comm_.comm, n_ranks, uid, rank));
+  comm_.nranks = n_ranks;
+  comm_.rank = rank;
+  prepared = false;
+}
+void Solver::allreduce(MpBuf& t, int64_t off, int64_t n, int op) {
+  if (!comm_.active() || n <= 0) return;
+  size_t words = (size_t)(nl + 1) * n;
+  comm_.stage.ensure(words * sizeof(uint32_t));
+  comm_.gathered.ensure(words * sizeof(uint32_t) * comm_.nranks);
+  // pack the planes of the region contiguously: [(nl+1)][n]
+  CLR_CUDA(cudaMemcpy2DAsync(comm_.stage.p, (size_t)n * 4, t.w() + off, t.n * 4, (size_t)n * 4, nl + 1,
+                             cudaMemcpyDeviceToDevice, ctx.stream));
+  CLR_NCCL(NcclApi::get().AllGather(comm_.stage.p, comm_.gathered.p, words, ncclUint32, comm_.comm, ctx.stream));
+  combine_ranks(ctx, nl, comm_.gathered.as<uint32_t>(), comm_.nranks, n, t.t(), off, op);
 }
 
 // ---- wire <-> device -------------------------------------------------------------------------------
@@ -309,21 +334,25 @@ void Solver::upload_tables() {
     up(g.offS, offS, s), up(g.offBt, offBt, s), up(g.offW, offW, s);
   }
   CLR_CUDA(cudaStreamSynchronize(s));
-  // n = size(X,1) as an mp scalar
-  {
-    int8_t sg = 1;
-    int64_t ex = 0;
-    std::vector<uint32_t> limbs(nl, 0);
-    int v = ntot, bl = 0;
-    while ((1ll << bl) <= v) bl++;
-    uint64_t top = (uint64_t)v << (64 - bl);
-    limbs[nl - 1] = (uint32_t)(top >> 32);
-    limbs[nl - 2] = (uint32_t)top;
-    ex = bl;
-    clrsdp_mp one{&sg, &ex, limbs.data(), 1};
-    to_device(&one, 0, 1, scal, SL_NTOT);
-  }
+  ntot_local = ntot;
+  upload_ntot();
   tables_ready = true;
+}
+
+// n = size(X,1) (MPMP.jl:755) as an mp scalar; with sharded clusters the local sizes are summed over the ranks
+void Solver::upload_ntot() {
+  int8_t sg = 1;
+  int64_t ex = 0;
+  std::vector<uint32_t> limbs(nl, 0);
+  int v = ntot_local, bl = 0;
+  while ((1ll << bl) <= v) bl++;
+  uint64_t top = (uint64_t)v << (64 - bl);
+  limbs[nl - 1] = (uint32_t)(top >> 32);
+  limbs[nl - 2] = (uint32_t)top;
+  ex = bl;
+  clrsdp_mp one{&sg, &ex, limbs.data(), 1};
+  to_device(&one, 0, 1, scal, SL_NTOT);
+  allreduce(scal, SL_NTOT, 1, COMB_SUM);
 }
 
 void Solver::upload_cluster(int j, const clrsdp_mp* V, const clrsdp_mp* Hh, const clrsdp_mp* B, const clrsdp_mp* cc) {
@@ -647,11 +676,14 @@ void Solver::compute_residuals(bool from_pairings) {
   g2.A = Bmat.t(), g2.x = x.t(), g2.out = tmpy.t();
   g2.rs = 1, g2.ks = n_y, g2.rows = n_y, g2.K = sumS;
   gemv(ctx, nl, g2, work.t());
+  allreduce(tmpy, 0, n_y, COMB_SUM);  // sum over the clusters of all ranks (:1137-1139)
   ew_lincomb(ctx, nl, p.t(), 0, b.t(), 0, 1, tmpy.t(), 0, -1, n_y);
   // errors (max-abs) of this P, p, d: used by the log row now and, stale, by terminate() after the update
   reduce_maxabs(ctx, nl, P.t(), 0, blkN, scal.t(), SL_PERR_P, work.t());
   reduce_maxabs(ctx, nl, p.t(), 0, n_y, scal.t(), SL_PERR_p, work.t());
   reduce_maxabs(ctx, nl, d.t(), 0, sumS, scal.t(), SL_DERR, work.t());
+  allreduce(scal, SL_PERR_P, 1, COMB_MAX);
+  allreduce(scal, SL_DERR, 1, COMB_MAX);
 }
 
 // compute_T_decomposition (MPMP.jl:1417-1514) with Cholesky instead of LU (S and Q are SPD, :1430-1432)
@@ -699,6 +731,7 @@ void Solver::decomposition() {
     o.dst = Q.t();
     o.rs = n_y, o.cs = 1;
     gemm_->multiply(sW, sW, plan_of(1, n_y, n_y), o);
+    allreduce(Q, 0, (int64_t)n_y * n_y, COMB_SUM);  // the cross-cluster reduction (sum(Q), :1494)
   }
   mark(-1 - CLRSDP_T_Q);
   mark(CLRSDP_T_CHOL_Q);
@@ -743,6 +776,7 @@ void Solver::search_direction() {
     w.A = Wt.t(), w.x = tvec.t(), w.out = tmpy.t();
     w.rs = sumS, w.ks = 1, w.rows = n_y, w.K = sumS;
     gemv(ctx, nl, w, work.t());
+    allreduce(tmpy, 0, n_y, COMB_SUM);  // sum(temp_y), :1761
     ew_lincomb(ctx, nl, dyr.t(), 0, p.t(), 0, 1, tmpy.t(), 0, -1, n_y);  // p - sum_j B^T U^-1 t_j (:1761)
     // dy = Q^-1 dyr = Lq^-T (Lq^-1 dyr)
     GemvArgs q1;
@@ -803,6 +837,7 @@ void Solver::step_lengths() {
   }
   reduce_min(ctx, nl, lam.t(), 0, (int64_t)blocks_.size(), scal.t(), SL_LAM_X, work.t());
   reduce_min(ctx, nl, lam.t(), (int64_t)blocks_.size(), (int64_t)blocks_.size(), scal.t(), SL_LAM_Y, work.t());
+  allreduce(scal, SL_LAM_X, 2, COMB_MIN);  // global minimum over all ranks (:1890-1891); LAM_X, LAM_Y adjacent
 }
 
 // ---- timing marks: bucket >= 0 begins a bucket, -1-bucket ends it -----------------------------------
@@ -821,7 +856,7 @@ void Solver::mark(int code) {
     ev_marks_.emplace_back(-1 - code, -1);
 }
 
-int Solver::check_status() {
+int Solver::check_status_local() {
   CLR_CUDA(cudaMemcpyAsync(h_status.data(), d_status.p, sizeof(int) * n_status, cudaMemcpyDeviceToHost, ctx.stream));
   CLR_CUDA(cudaMemcpyAsync(h_scal, d_scal_out.p, sizeof(h_scal), cudaMemcpyDeviceToHost, ctx.stream));
   CLR_CUDA(cudaMemcpyAsync(h_flags, d_flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx.stream));
@@ -845,6 +880,19 @@ int Solver::check_status() {
   return 0;
 }
 
+// every rank must see a failure of any rank, otherwise the next collective would dead-lock
+int Solver::check_status() {
+  int st = check_status_local();
+  if (!comm_.active()) return st;
+  int code = -st;  // 0 or 10..13
+  d_status_any.ensure(sizeof(int));
+  CLR_CUDA(cudaMemcpyAsync(d_status_any.p, &code, sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+  CLR_NCCL(NcclApi::get().AllReduce(d_status_any.p, d_status_any.p, 1, ncclInt32, ncclMax, comm_.comm, ctx.stream));
+  CLR_CUDA(cudaMemcpyAsync(&code, d_status_any.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  return -code;
+}
+
 // loop initialisation (MPMP.jl:716-736)
 int Solver::prepare(clrsdp_iter_info* info) {
   if (!have_point) return CLRSDP_ERR_STATE;
@@ -856,11 +904,14 @@ int Solver::prepare(clrsdp_iter_info* info) {
   int zero2[2] = {0, 0};
   CLR_CUDA(cudaMemcpyAsync(d_flags.p, zero2, 2 * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
   iter = 1;
+  upload_ntot();
   ew_zero(ctx, nl, scal.t(), SL_ALPHA_P, 1);
   ew_zero(ctx, nl, scal.t(), SL_ALPHA_D, 1);
   reduce_dot(ctx, nl, X.t(), 0, Y.t(), 0, blkN, scal.t(), SL_DOT_XY, work.t());
+  allreduce(scal, SL_DOT_XY, 1, COMB_SUM);
   scalar_program(ctx, nl, SP_MU, scal.t(), d_flags.as<int>(), nullptr);
   reduce_dot(ctx, nl, c.t(), 0, x.t(), 0, sumS, scal.t(), SL_CX, work.t());
+  allreduce(scal, SL_CX, 1, COMB_SUM);
   reduce_dot(ctx, nl, b.t(), 0, y.t(), 0, n_y, scal.t(), SL_BY, work.t());
   compute_residuals(false);
   // the initial duality gap is computed WITHOUT b0 (MPMP.jl:725 -> :1067-1074)
@@ -905,6 +956,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   row.gap = h_scal[SL_GAP];
   // step 3
   reduce_dot(ctx, nl, X.t(), 0, Y.t(), 0, blkN, scal.t(), SL_DOT_XY, work.t());
+  allreduce(scal, SL_DOT_XY, 1, COMB_SUM);
   scalar_program(ctx, nl, SP_MU, scal.t(), d_flags.as<int>(), nullptr);
   // step 4: R = mu_p I - X Y
   mark(CLRSDP_T_R);
@@ -930,6 +982,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   ew_lincomb(ctx, nl, dy_pred.t(), 0, dy.t(), 0, 1, dy.t(), 0, 0, n_y);
   // step 5
   reduce_dot_sum(ctx, nl, X.t(), dX.t(), Y.t(), dY.t(), blkN, scal.t(), SL_DOT_SUM, work.t());
+  allreduce(scal, SL_DOT_SUM, 1, COMB_SUM);
   scalar_program(ctx, nl, SP_BETA, scal.t(), d_flags.as<int>(), nullptr);
   // step 6: R = mu_c I - X Y - dX dY
   mark(CLRSDP_T_R);
@@ -956,6 +1009,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   ew_axpy(ctx, nl, Y.t(), 0, dY.t(), 0, scal.t(), SL_ALPHA_D, blkN);
   // new objectives; errors are the ones computed from P,p,d BEFORE the update (:940-944)
   reduce_dot(ctx, nl, c.t(), 0, x.t(), 0, sumS, scal.t(), SL_CX, work.t());
+  allreduce(scal, SL_CX, 1, COMB_SUM);
   reduce_dot(ctx, nl, b.t(), 0, y.t(), 0, n_y, scal.t(), SL_BY, work.t());
   scalar_program(ctx, nl, SP_OBJECTIVES, scal.t(), d_flags.as<int>(), nullptr);
   scalar_program(ctx, nl, SP_ERRORS, scal.t(), d_flags.as<int>(), d_scal_out.as<double>());

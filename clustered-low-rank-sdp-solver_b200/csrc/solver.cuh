@@ -7,6 +7,7 @@
 #include "../../include/clrsdp.h"
 #include "gemm_i8.cuh"
 #include "linalg.cuh"
+#include "comm.cuh"
 
 namespace clr {
 
@@ -57,6 +58,7 @@ class Solver {
   int iterate(clrsdp_iter_info* info);
   int solve(clrsdp_iter_info* rows, int max_rows, int* n_rows);
   int64_t fetch(const char* name, int j, int l, clrsdp_mp_out* out);
+  void comm_init(int n_ranks, int rank, const uint8_t* id);
   // phase-level ops
   void op_gemm(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, clrsdp_mp_out* C);
   void op_gemm_planes(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, int32_t* planes,
@@ -97,9 +99,15 @@ class Solver {
   void chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv, int* d_status,
                     bool want_u = false);
   int check_status();
+  int check_status_local();
+  void upload_ntot();
+  // all-reduce of t[off, off+n) over the ranks (no-op on one rank)
+  void allreduce(MpBuf& t, int64_t off, int64_t n, int op);
   void mark(int bucket_begin);
 
   std::unique_ptr<GemmEngine> gemm_;
+  Comm comm_;
+  int ntot_local = 0;
   // structure
   int J = 0, n_y = 0, sumS = 0, ntot = 0;
   std::vector<HostBlock> blocks_;
@@ -122,7 +130,7 @@ class Solver {
   MpBuf dX_pred, dY_pred, dx_pred, dy_pred;
   MpBuf scal, rdiag, lam, work, tscr;
   Slice fs1_, fs2_;
-  DevBuf d_status, d_flags, d_scal_out, d_qoff;
+  DevBuf d_status, d_flags, d_scal_out, d_qoff, d_status_any;
   std::vector<int> h_status;
   int n_status = 0;
   // iteration bookkeeping
