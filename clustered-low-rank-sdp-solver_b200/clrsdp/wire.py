@@ -67,6 +67,15 @@ class MpArray:
         out.limb[:, :] = self.limb[:, idx]
         return out
 
+    def widen(self, nlimb: int) -> "MpArray":
+        """the same values at a higher precision (zero limbs appended at the low end; exact)."""
+        assert nlimb >= self.nlimb
+        out = MpArray(self.shape, nlimb)
+        out.sign[:] = self.sign
+        out.exp[:] = self.exp
+        out.limb[nlimb - self.nlimb:, :] = self.limb
+        return out
+
     def transpose2d(self) -> "MpArray":
         r, c = self.shape
         idx = np.arange(r * c).reshape(r, c).T.reshape(-1)

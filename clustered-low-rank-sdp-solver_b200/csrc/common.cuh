@@ -96,6 +96,13 @@ struct Ctx {
   void sync() { CLR_CUDA(cudaStreamSynchronize(stream)); }
 };
 
+// Bumped by every device (re)allocation or release: a captured CUDA graph bakes device addresses (and TMA
+// descriptors) into its nodes, so the solver drops its graph whenever the epoch moved since the capture.
+inline uint64_t& alloc_epoch() {
+  static uint64_t e = 0;
+  return e;
+}
+
 // simple owning device buffer
 struct DevBuf {
   void* p = nullptr;
@@ -114,7 +121,10 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaFree(p);
+      alloc_epoch()++;
+    }
     p = nullptr;
     bytes = 0;
   }
@@ -122,6 +132,7 @@ struct DevBuf {
     if (b <= bytes) return;
     release();
     CLR_CUDA(cudaMalloc(&p, b));
+    alloc_epoch()++;
     bytes = b;
   }
   template <class T>

@@ -28,70 +28,87 @@ __device__ __forceinline__ int64_t item_off(const GatherArgs& g, int b) {
   return g.off0 + (g.d_off ? g.d_off[b] : (int64_t)b * g.bstride);
 }
 
-// one warp per row: max exponent over the non-zero entries (EXP_ZERO for an all-zero row)
-template <int NL>
-__global__ void rowexp_kernel(GatherArgs g, int32_t* __restrict__ exps) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= g.rows_total) return;
-  int b = warp / g.rows, r = warp % g.rows;
-  const uint32_t* hdr = g.w + (size_t)NL * g.n;
-  int64_t base = item_off(g, b) + (int64_t)r * g.rs;
-  int32_t mx = mp::EXP_ZERO;
-  for (int k = lane; k < g.K; k += 32) {
-    int32_t e = ((int32_t)hdr[base + (int64_t)k * g.ks]) >> 1;
-    mx = max(mx, e);
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) exps[warp] = mx;
-}
-
-// thread per (row, k): fixed-point conversion relative to the row exponent, balanced digits.
+// Fixed-point conversion of one entry relative to its row exponent and balanced radix-256 digits:
 //   F = trunc( x * 2^(8S-2-rexp) ),  |F| < 2^(8S-2);   F = sum_a d_a 256^(S-1-a),  d_a in [-128,127]
 template <int NL, int S>
-__global__ void slice_kernel(GatherArgs g, const int32_t* __restrict__ exps, int8_t* __restrict__ digits) {
+__device__ __forceinline__ void slice_entry(const GatherArgs& g, int row, int k, int32_t rexp, int8_t* __restrict__ digits) {
   constexpr int NLW = NL + 2;
   static_assert(8 * S + 2 <= 32 * NLW, "digit window too small");
-  int64_t total = (int64_t)g.rows_total * g.Kp;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int row = (int)(idx / g.Kp), k = (int)(idx % g.Kp);
-    uint32_t W[NLW];
+  uint32_t W[NLW];
 #pragma unroll
-    for (int i = 0; i < NLW; i++) W[i] = 0;
-    bool negf = false;
-    if (k < g.K) {
+  for (int i = 0; i < NLW; i++) W[i] = 0;
+  bool negf = false;
+  if (k < g.K) {
+    int b = row / g.rows, r = row % g.rows;
+    int64_t at = item_off(g, b) + (int64_t)r * g.rs + (int64_t)k * g.ks;
+    mp::Num<NL> x = mp::load<NL>(g.w, g.n, (size_t)at);
+    if (!mp::is_zero(x)) {
+      uint32_t d = (uint32_t)(rexp - x.e);
+      uint32_t sr = 32u * NLW - 8u * S + 2u + d;
+      if (sr < 32u * NLW) {
+#pragma unroll
+        for (int i = 0; i < NL; i++) W[i + 2] = x.m[i];
+        mp::shr_limbs<NLW>(W, sr >> 5);
+        mp::shr_bits<NLW>(W, sr & 31u);
+        negf = x.neg != 0;
+      }
+    }
+  }
+  if (negf) {  // two's complement
+    uint32_t c = 1;
+#pragma unroll
+    for (int i = 0; i < NLW; i++) {
+      uint64_t s = (uint64_t)(~W[i]) + c;
+      W[i] = (uint32_t)s;
+      c = (uint32_t)(s >> 32);
+    }
+  }
+  int carry = 0;
+  int8_t* out = digits + ((size_t)(S - 1) * g.rows_total + row) * g.Kp + k;
+  const size_t pstride = (size_t)g.rows_total * g.Kp;
+#pragma unroll
+  for (int i = 0; i < S; i++) {
+    int v = (int)((W[i >> 2] >> (8 * (i & 3))) & 0xFFu) + carry;
+    carry = v >= 128 ? 1 : 0;
+    v -= carry << 8;
+    *out = (int8_t)v;
+    out -= pstride;
+  }
+}
+
+// Row exponent + slicing in one launch. A block of 8 warps owns 8/WPR rows (WPR warps per row): pass 1 takes the
+// maximum exponent over the row's non-zero entries (EXP_ZERO for an all-zero row), pass 2 converts the row.
+// The second read of the row hits L1/L2.
+constexpr int SLICE_THREADS = 256;
+template <int NL, int S>
+__global__ void __launch_bounds__(SLICE_THREADS, 3) slice_rows_kernel(GatherArgs g, int wpr, int32_t* __restrict__ exps,
+                                                                    int8_t* __restrict__ digits) {
+  __shared__ int32_t smx[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rpb = 8 / wpr, sub = warp % wpr;
+  const uint32_t* hdr = g.w + (size_t)NL * g.n;
+  const int ngroups = (g.rows_total + rpb - 1) / rpb;
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int row = grp * rpb + warp / wpr;
+    const bool live = row < g.rows_total;
+    int32_t mx = mp::EXP_ZERO;
+    int64_t base = 0;
+    if (live) {
       int b = row / g.rows, r = row % g.rows;
-      int64_t at = item_off(g, b) + (int64_t)r * g.rs + (int64_t)k * g.ks;
-      mp::Num<NL> x = mp::load<NL>(g.w, g.n, (size_t)at);
-      if (!mp::is_zero(x)) {
-        uint32_t d = (uint32_t)(exps[row] - x.e);
-        uint32_t sr = 32u * NLW - 8u * S + 2u + d;
-        if (sr < 32u * NLW) {
-#pragma unroll
-          for (int i = 0; i < NL; i++) W[i + 2] = x.m[i];
-          mp::shr_limbs<NLW>(W, sr >> 5);
-          mp::shr_bits<NLW>(W, sr & 31u);
-          negf = x.neg != 0;
-        }
-      }
+      base = item_off(g, b) + (int64_t)r * g.rs;
+      for (int k = sub * 32 + lane; k < g.K; k += 32 * wpr) mx = max(mx, ((int32_t)hdr[base + (int64_t)k * g.ks]) >> 1);
     }
-    if (negf) {  // two's complement
-      uint32_t c = 1;
 #pragma unroll
-      for (int i = 0; i < NLW; i++) {
-        uint64_t s = (uint64_t)(~W[i]) + c;
-        W[i] = (uint32_t)s;
-        c = (uint32_t)(s >> 32);
-      }
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (wpr > 1) {
+      __syncthreads();
+      if (lane == 0) smx[warp] = mx;
+      __syncthreads();
+      for (int q = 0; q < wpr; q++) mx = max(mx, smx[(warp / wpr) * wpr + q]);
     }
-    int carry = 0;
-#pragma unroll
-    for (int i = 0; i < S; i++) {
-      int v = (int)((W[i >> 2] >> (8 * (i & 3))) & 0xFFu) + carry;
-      carry = v >= 128 ? 1 : 0;
-      v -= carry << 8;
-      digits[((size_t)(S - 1 - i) * g.rows_total + row) * g.Kp + k] = (int8_t)v;
+    if (live) {
+      if (sub == 0 && lane == 0) exps[row] = mx;
+      for (int k = sub * 32 + lane; k < g.Kp; k += 32 * wpr) slice_entry<NL, S>(g, row, k, mx, digits);
     }
   }
 }
@@ -347,13 +364,32 @@ __global__ void carry_kernel(CarryArgs c) {
 #pragma unroll
     for (int q = 0; q < NW; q++) W[q] = 0;
     int64_t carry = 0;
+    // planes from the least significant (t = T-1) upwards, CH at a time: the CH (x nsplit) loads of a chunk are
+    // independent and all in flight before the carry chain consumes them
+    constexpr int CH = 17;
 #pragma unroll
-    for (int t = T - 1; t >= 0; t--) {
-      int64_t v = carry;
-      for (int s = 0; s < c.nsplit; s++) v += c.planes[(size_t)t * pstride + (size_t)s * total + idx];
-      int pos = T - 1 - t;  // byte position from the least significant end
-      W[pos >> 2] |= (uint32_t)(v & 0xFF) << (8 * (pos & 3));
-      carry = v >> 8;
+    for (int c0 = T - 1; c0 >= 0; c0 -= CH) {
+      int64_t acc[CH];
+#pragma unroll
+      for (int u = 0; u < CH; u++) acc[u] = 0;
+      for (int s = 0; s < c.nsplit; s++) {
+        const int32_t* ps = c.planes + (size_t)s * total + idx;
+        int32_t v32[CH];
+#pragma unroll
+        for (int u = 0; u < CH; u++) v32[u] = (c0 - u >= 0) ? ps[(size_t)(c0 - u >= 0 ? c0 - u : 0) * pstride] : 0;
+#pragma unroll
+        for (int u = 0; u < CH; u++) acc[u] += v32[u];
+      }
+#pragma unroll
+      for (int u = 0; u < CH; u++) {
+        const int t = c0 - u;
+        if (t >= 0) {
+          int64_t v = carry + acc[u];
+          const int pos = T - 1 - t;  // byte position from the least significant end
+          W[pos >> 2] |= (uint32_t)(v & 0xFF) << (8 * (pos & 3));
+          carry = v >> 8;
+        }
+      }
     }
     // remaining carry (signed) goes above byte T-1
     {
@@ -460,14 +496,15 @@ static void slice_impl(Ctx& ctx, const OperandDesc& op, Slice& out) {
   out.digits.ensure(bytes);
   out.exps.ensure(sizeof(int32_t) * (size_t)std::max(out.rows_total, 1));
   GatherArgs g{op.src.w, op.src.n, op.d_off, op.off0, op.bstride, op.rs, op.ks, op.batch, op.rows, K, Kp, out.rows_total};
-  int tk = ctx.begin("rowexp");
-  rowexp_kernel<NL><<<ceil_div((int64_t)out.rows_total * 32, 256), 256, 0, ctx.stream>>>(g, out.exps.as<int32_t>());
-  ctx.end(tk);
   int64_t total = (int64_t)out.rows_total * Kp;
-  int grid = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)ctx.sm_count * 16);
+  // long rows (or few of them) get a whole block per row, short rows one warp
+  int wpr = (Kp > 256 || (int64_t)out.rows_total * 32 < (int64_t)ctx.sm_count * 256) ? 8 : 1;
+  if (Kp <= 32) wpr = 1;
+  int rpb = 8 / wpr;
+  int grid = (int)std::min<int64_t>(ceil_div(out.rows_total, rpb), (int64_t)ctx.sm_count * 8);
   // algorithmic bytes: read (p/8+4) per entry, write S digit bytes
-  tk = ctx.begin("slice", (double)total * (4.0 * (NL + 1) + S));
-  slice_kernel<NL, S><<<grid, 256, 0, ctx.stream>>>(g, out.exps.as<int32_t>(), out.digits.as<int8_t>());
+  int tk = ctx.begin("slice", (double)total * (4.0 * (NL + 1) + S));
+  slice_rows_kernel<NL, S><<<grid, SLICE_THREADS, 0, ctx.stream>>>(g, wpr, out.exps.as<int32_t>(), out.digits.as<int8_t>());
   ctx.end(tk);
 }
 

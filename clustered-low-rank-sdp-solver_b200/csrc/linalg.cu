@@ -28,6 +28,7 @@ template <int NL> __device__ __noinline__ Num<NL> ndiv(const Num<NL>& a, const N
 template <int NL> __device__ __noinline__ Num<NL> nrecip(const Num<NL>& a) { return mp::recip(a); }
 template <int NL> __device__ __noinline__ Num<NL> nsqrt(const Num<NL>& a) { return mp::sqrt(a); }
 template <int NL> __device__ __noinline__ Num<NL> nsqrt_rsqrt(const Num<NL>& a, Num<NL>& r) { return mp::sqrt_rsqrt(a, r); }
+template <int NL> __device__ __noinline__ Num<NL> nmsm(const Num<NL>& a, const Num<NL>& b, const Num<NL>& c, const Num<NL>& d) { return mp::mul_sub_mul(a, b, c, d); }
 template <int NL> __device__ __noinline__ int ncmp(const Num<NL>& a, const Num<NL>& b) { return mp::cmp(a, b); }
 
 // =========================================================================================================
@@ -193,15 +194,36 @@ trinv_kernel(mp::Tensor U, const int64_t* __restrict__ offU, int64_t shiftU, mp:
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fused panel factorisation: U (upper Cholesky factor) and G = L^-1 = U^-T of one w x w SPD block, w <= 64,
+// Fused panel factorisation: U (upper Cholesky factor) and G = L^-1 = U^-T of one w x w SPD block, w <= 32,
 // entirely in shared memory (packed triangles). Gaussian elimination on the augmented matrix [A | I]:
-// the row operations that turn A into U turn I into L^-1, so the inverse costs no extra dependency
-// chain. Warp 0 runs the critical path one step ahead (update of row k+1, pivot sqrt/rsqrt, row
-// scaling) while the other warps apply update k to the rows below: ONE __syncthreads per step.
+// the row operations that turn A into U turn I into L^-1, so the inverse costs no extra dependency chain.
+//
+// The pivot chain is the latency floor of the whole solver (n dependent steps per n x n matrix), so the
+// loop is DIVISION- AND SQUARE-ROOT-FREE: step k replaces every later row by
+//        row_r <- mu_k * row_r - (R_k[r] * 2^-e_k) * row_k ,   mu_k = d'_k * 2^-e_k in [1/2, 1),
+// (d'_k = current pivot), i.e. all unpivoted rows carry the common scale tau_k = prod_{i<k} mu_i. The
+// true factors are recovered at the end, for all rows in parallel, by one rsqrt per row:
+//        U_k = R'_k * f_k ,  G_k = G'_k * f_k ,  f_k = (tau_k * d'_k)^-1/2 .
+// Warp 0 runs the chain one step ahead (row k+1, one element per lane: two multiplications and one
+// subtraction per step) while the other warps apply step k to the rows below: ONE __syncthreads per step.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int PANEL_THREADS = 512;
+constexpr int PANEL_W = 32;
 __host__ __device__ inline int pk_u(int w, int r, int c) { return r * w - (r * (r - 1)) / 2 + (c - r); }  // r <= c
 __host__ __device__ inline int pk_g(int r, int j) { return (r * (r + 1)) / 2 + j; }                      // j <= r
+template <int NL>
+__device__ __forceinline__ void panel_elim(uint32_t* Us, uint32_t* Gs, int w, int k, int r, int qp, const Num<NL>& mu,
+                                           int ek) {
+  // qp enumerates the active columns of row r: G part q = qp <= k, U part q = qp + (r - k - 1) >= r
+  Num<NL> gam = mp::mul_2exp(smem_get<NL>(Us, pk_u(w, k, r)), -ek);
+  if (qp <= k) {
+    int at = pk_g(r, qp);
+    smem_put<NL>(Gs, at, nmsm(mu, smem_get<NL>(Gs, at), gam, smem_get<NL>(Gs, pk_g(k, qp))));
+  } else {
+    int q = qp + (r - k - 1), at = pk_u(w, r, q);
+    smem_put<NL>(Us, at, nmsm(mu, smem_get<NL>(Us, at), gam, smem_get<NL>(Us, pk_u(w, k, q))));
+  }
+}
 template <int NL>
 __global__ void __launch_bounds__(PANEL_THREADS)
 panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shiftA, int ldA, mp::Tensor Lm,
@@ -209,8 +231,9 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
                     int* __restrict__ status) {
   extern __shared__ uint32_t sm[];
   const int ntri = w * (w + 1) / 2;
-  uint32_t* Us = sm;                                  // packed upper triangle of the work matrix / U
-  uint32_t* Gs = sm + (size_t)ntri * (NL + 2);        // packed lower triangle of G
+  uint32_t* Us = sm;                                  // packed upper triangle of the scaled work matrix R'
+  uint32_t* Gs = sm + (size_t)ntri * (NL + 2);        // packed lower triangle of G' (diagonal slots: tau)
+  uint32_t* Fs = sm + (size_t)2 * ntri * (NL + 2);    // f_k per row
   __shared__ int bad;
   const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int64_t oa = offA[b] + shiftA, ol = offL[b] + shiftL;
@@ -218,94 +241,71 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
   for (int idx = tid; idx < w * w; idx += nthr) {
     int r = idx / w, c = idx % w;
     if (r <= c) smem_put<NL>(Us, pk_u(w, r, c), ldm<NL>(A, oa + (int64_t)r * ldA + c));
-    if (c <= r) smem_put<NL>(Gs, pk_g(r, c), r == c ? mp::one<NL>() : mp::zero<NL>());
+    if (c <= r) smem_put<NL>(Gs, pk_g(r, c), (r == 0 && c == 0) ? mp::one<NL>() : mp::zero<NL>());
   }
   __syncthreads();
-  // step 0 of the critical path: pivot 0 and scaling of row 0
-  if (warp == 0) {
-    if (lane == 0) {
-      Num<NL> a = smem_get<NL>(Us, pk_u(w, 0, 0));
-      if (mp::is_zero(a) || a.neg) {
-        bad = 1;
-      } else {
-        Num<NL> rinv, d = nsqrt_rsqrt(a, rinv);
-        smem_put<NL>(Us, pk_u(w, 0, 0), d);
-        smem_put<NL>(Gs, pk_g(0, 0), rinv);
-      }
-    }
-    __syncwarp();
-    if (!bad) {
-      Num<NL> rinv = smem_get<NL>(Gs, pk_g(0, 0));
-      for (int c = 1 + lane; c < w; c += 32) smem_put<NL>(Us, pk_u(w, 0, c), nmul(smem_get<NL>(Us, pk_u(w, 0, c)), rinv));
-    }
+  if (tid == 0) {
+    Num<NL> a = smem_get<NL>(Us, pk_u(w, 0, 0));
+    if (mp::is_zero(a) || a.neg) bad = 1;
   }
   __syncthreads();
   for (int k = 0; k + 1 < w && !bad; k++) {
-    // row k of U and of G are final. Apply elimination step k to the rows below.
+    // rows 0..k are final (scaled); apply elimination step k to the rows below
+    Num<NL> mu = smem_get<NL>(Us, pk_u(w, k, k));
+    const int ek = mu.e;
+    mu.e = 0;
     if (warp == 0) {
       const int r = k + 1;
-      Num<NL> mult = smem_get<NL>(Us, pk_u(w, k, r));
-      for (int q = lane; q < w; q += 32) {
-        if (q >= r) {
-          int at = pk_u(w, r, q);
-          smem_put<NL>(Us, at, nsub(smem_get<NL>(Us, at), nmul(mult, smem_get<NL>(Us, pk_u(w, k, q)))));
-        } else if (q <= k) {
-          int at = pk_g(r, q);
-          smem_put<NL>(Gs, at, nsub(smem_get<NL>(Gs, at), nmul(mult, smem_get<NL>(Gs, pk_g(k, q)))));
-        }
-      }
+      if (lane < w) panel_elim<NL>(Us, Gs, w, k, r, lane, mu, ek);  // exactly w active columns: one per lane
       __syncwarp();
       if (lane == 0) {
         Num<NL> a = smem_get<NL>(Us, pk_u(w, r, r));
-        if (mp::is_zero(a) || a.neg) {
-          bad = 1;
-        } else {
-          Num<NL> rinv, d = nsqrt_rsqrt(a, rinv);
-          smem_put<NL>(Us, pk_u(w, r, r), d);
-          smem_put<NL>(sm + (size_t)2 * ntri * (NL + 2), 0, rinv);
-        }
-      }
-      __syncwarp();
-      if (!bad) {
-        Num<NL> rinv = smem_get<NL>(sm + (size_t)2 * ntri * (NL + 2), 0);
-        for (int q = lane; q < w; q += 32) {
-          if (q > r) {
-            int at = pk_u(w, r, q);
-            smem_put<NL>(Us, at, nmul(smem_get<NL>(Us, at), rinv));
-          } else {
-            int at = pk_g(r, q);  // q <= r, includes the unit diagonal
-            smem_put<NL>(Gs, at, nmul(smem_get<NL>(Gs, at), rinv));
-          }
-        }
+        if (mp::is_zero(a) || a.neg) bad = 1;
       }
     } else {
-      const int rows = w - (k + 2);
-      for (int idx = tid - 32; idx < rows * w; idx += nthr - 32) {
-        int r = k + 2 + idx / w, q = idx % w;
-        if (q >= r) {
-          int at = pk_u(w, r, q);
-          smem_put<NL>(Us, at, nsub(smem_get<NL>(Us, at), nmul(smem_get<NL>(Us, pk_u(w, k, r)), smem_get<NL>(Us, pk_u(w, k, q)))));
-        } else if (q <= k) {
-          int at = pk_g(r, q);
-          smem_put<NL>(Gs, at, nsub(smem_get<NL>(Gs, at), nmul(smem_get<NL>(Us, pk_u(w, k, r)), smem_get<NL>(Gs, pk_g(k, q)))));
+      // the common diagonal of the unpivoted rows of G': tau_{k+1} = mu_k tau_k (only row k+1's slot is kept)
+      if (tid == 32) smem_put<NL>(Gs, pk_g(k + 1, k + 1), nmul(mu, smem_get<NL>(Gs, pk_g(k, k))));
+      // rows r = k+2+i, i in [0,R): row i has cnt_i = w-1-i active columns; rows i and R-1-i are paired so that
+      // every pair has the same number of elements
+      const int R = w - (k + 2);
+      const int C = 2 * (w - 1) - (R - 1);  // cnt_i + cnt_{R-1-i}
+      const int npair = R >> 1;
+      const int total = npair * C + ((R & 1) ? (w - 1 - (R >> 1)) : 0);
+      for (int idx = tid - 32; idx < total; idx += nthr - 32) {
+        int i, qp;
+        if (idx < npair * C) {
+          int pr = idx / C, j = idx % C, c0 = w - 1 - pr;
+          if (j < c0) i = pr, qp = j; else i = R - 1 - pr, qp = j - c0;
+        } else {
+          i = R >> 1, qp = idx - npair * C;
         }
+        panel_elim<NL>(Us, Gs, w, k, k + 2 + i, qp, mu, ek);
       }
     }
     __syncthreads();
   }
+  // f_k = rsqrt(tau_k d'_k), one row per lane
+  if (warp == 0 && !bad && lane < w) {
+    Num<NL> f, root = nsqrt_rsqrt(nmul(smem_get<NL>(Gs, pk_g(lane, lane)), smem_get<NL>(Us, pk_u(w, lane, lane))), f);
+    (void)root;
+    smem_put<NL>(Fs, lane, f);
+  }
   __syncthreads();
-  for (int idx = tid; idx < w * w; idx += nthr) {
-    int r = idx / w, c = idx % w;
-    if (write_u) stm<NL>(A, oa + (int64_t)r * ldA + c, r <= c ? smem_get<NL>(Us, pk_u(w, r, c)) : mp::zero<NL>());
-    stm<NL>(Lm, ol + (int64_t)r * ldL + c, c <= r ? smem_get<NL>(Gs, pk_g(r, c)) : mp::zero<NL>());
+  if (!bad) {
+    for (int idx = tid; idx < w * w; idx += nthr) {
+      int r = idx / w, c = idx % w;
+      Num<NL> f = smem_get<NL>(Fs, r);
+      if (write_u) stm<NL>(A, oa + (int64_t)r * ldA + c, r <= c ? nmul(smem_get<NL>(Us, pk_u(w, r, c)), f) : mp::zero<NL>());
+      stm<NL>(Lm, ol + (int64_t)r * ldL + c, c <= r ? nmul(smem_get<NL>(Gs, pk_g(r, c)), f) : mp::zero<NL>());
+    }
   }
   if (tid == 0) status[b] = bad;
 }
-int panel_width(int nl) { return nl <= 8 ? 64 : 32; }
+int panel_width(int nl) { (void)nl; return PANEL_W; }
 void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status) {
   if (A.n > panel_width(nl)) throw SolverError(-1, "panel_factor: block larger than the panel width");
   DISPATCH_NL(nl, {
-    size_t words = ((size_t)A.n * (A.n + 1) + 1) * (NL + 2);
+    size_t words = ((size_t)A.n * (A.n + 1) + A.n) * (NL + 2);
     static bool attr[17] = {false};
     if (!attr[NL]) {
       CLR_CUDA(cudaFuncSetAttribute(panel_factor_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

@@ -260,12 +260,11 @@ MP_HD Num<NL> add(const Num<NL>& a, const Num<NL>& b) {
 template <int NL>
 MP_HD Num<NL> sub(const Num<NL>& a, const Num<NL>& b) { return add(a, neg(b)); }
 
+// top NL+2 limbs of the 2NL-limb product of the mantissas (truncated: columns NL-2 .. 2NL-1, error < NL units of
+// the lowest kept limb). Not normalised: the value P / 2^(32(NL+2)) lies in [1/4, 1).
 template <int NL>
-MP_HD Num<NL> mul(const Num<NL>& a, const Num<NL>& b) {
-  if (is_zero(a) || is_zero(b)) return zero<NL>();
-  // truncated product: columns NL-2 .. 2NL-1 of the 2NL-limb product (error < NL * 2^-32 ulp)
+MP_HD void mul_raw(const Num<NL>& a, const Num<NL>& b, uint32_t (&P)[NL + 2]) {
   constexpr int C0 = (NL >= 2) ? NL - 2 : 0;
-  uint32_t P[NL + 2];  // P[k] = column C0+k ... ; for NL==1 P has 3 entries, P[0] unused
   uint64_t lo = 0;
   uint32_t hi = 0;
 #pragma unroll
@@ -285,6 +284,12 @@ MP_HD Num<NL> mul(const Num<NL>& a, const Num<NL>& b) {
   }
   P[NL + 1] = (uint32_t)lo;
   if (NL < 2) P[0] = 0;
+}
+template <int NL>
+MP_HD Num<NL> mul(const Num<NL>& a, const Num<NL>& b) {
+  if (is_zero(a) || is_zero(b)) return zero<NL>();
+  uint32_t P[NL + 2];
+  mul_raw<NL>(a, b, P);
   // P[2..NL+1] = top NL limbs, P[1] = guard, P[0] = extra
   uint32_t X[NL + 1];
 #pragma unroll
@@ -298,6 +303,62 @@ MP_HD Num<NL> mul(const Num<NL>& a, const Num<NL>& b) {
   }
   Num<NL> out;
   round_guard<NL>(out, X, e, a.neg ^ b.neg);
+  return out;
+}
+// a*b - c*d with ONE rounding: both products are kept to NL+1 accurate limbs (error < NL * 2^-32 ulp of the larger
+// product), aligned, combined, normalised and rounded.
+// The building block of the elimination steps and three-term recurrences on the latency-bound paths.
+template <int NL>
+MP_HD Num<NL> mul_sub_mul(const Num<NL>& a, const Num<NL>& b, const Num<NL>& c, const Num<NL>& d) {
+  const bool z1 = is_zero(a) || is_zero(b), z2 = is_zero(c) || is_zero(d);
+  if (z2) return z1 ? zero<NL>() : mul(a, b);
+  if (z1) return neg(mul(c, d));
+  uint32_t X[NL + 2], Y[NL + 2];
+  int32_t ex = a.e + b.e, ey = c.e + d.e;
+  uint32_t nx = a.neg ^ b.neg, ny = (c.neg ^ d.neg) ^ 1u;
+  mul_raw<NL>(a, b, X);
+  mul_raw<NL>(c, d, Y);
+  if (ey > ex) {  // X takes the product with the larger exponent
+#pragma unroll
+    for (int i = 0; i < NL + 2; i++) {
+      uint32_t t = X[i];
+      X[i] = Y[i];
+      Y[i] = t;
+    }
+    int32_t te = ex; ex = ey; ey = te;
+    uint32_t tn = nx; nx = ny; ny = tn;
+  }
+  uint32_t dd = (uint32_t)(ex - ey);
+  if (dd < 32u * (NL + 2)) {
+    shr_limbs<NL + 2>(Y, dd >> 5);
+    shr_bits<NL + 2>(Y, dd & 31u);
+    if (nx == ny) {
+      uint32_t cy = add_n<NL + 2>(X, Y);
+      if (cy) {
+        shr_bits<NL + 2>(X, 1);
+        X[NL + 1] |= 0x80000000u;
+        ex += 1;
+      }
+    } else {
+      if (cmp_n<NL + 2>(X, Y) < 0) {
+#pragma unroll
+        for (int i = 0; i < NL + 2; i++) {
+          uint32_t t = X[i];
+          X[i] = Y[i];
+          Y[i] = t;
+        }
+        nx = ny;
+      }
+      sub_n<NL + 2>(X, Y);
+    }
+  }
+  int sh = normalize_n<NL + 2>(X);
+  if (sh < 0) return zero<NL>();
+  uint32_t G[NL + 1];
+#pragma unroll
+  for (int i = 0; i <= NL; i++) G[i] = X[i + 1];
+  Num<NL> out;
+  round_guard<NL>(out, G, ex - sh, nx);
   return out;
 }
 

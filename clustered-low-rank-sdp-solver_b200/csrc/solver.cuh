@@ -104,6 +104,8 @@ class Solver {
   // all-reduce of t[off, off+n) over the ranks (no-op on one rank)
   void allreduce(MpBuf& t, int64_t off, int64_t n, int op);
   void mark(int bucket_begin);
+  void iteration_body();
+  void drop_graph();
 
   std::unique_ptr<GemmEngine> gemm_;
   Comm comm_;
@@ -129,7 +131,13 @@ class Solver {
   MpBuf x, dx, d, c, rhs, tvec, tmpx, trx, y, dy, p, b, tmpy, zvec, dyr;
   MpBuf dX_pred, dY_pred, dx_pred, dy_pred;
   MpBuf scal, rdiag, lam, work, tscr;
-  Slice fs1_, fs2_;
+  Slice fs1_, fs2_, sW_;
+  // CUDA-graph replay of the iteration body (one launch instead of ~1000)
+  bool use_graph_ = true, capturing_ = false;
+  cudaGraphExec_t gexec_ = nullptr;
+  uint64_t graph_epoch_ = 0;
+  int direct_iters_ = 0;
+  int64_t graph_launches_ = 0;
   DevBuf d_status, d_flags, d_scal_out, d_qoff, d_status_any;
   std::vector<int> h_status;
   int n_status = 0;

@@ -33,6 +33,7 @@ static int run(int op, const clrsdp_mp* a, const clrsdp_mp* b, clrsdp_mp_out* c)
       case '/': z = mp::div(x, y); break;
       case 's': z = mp::sqrt(x); break;
       case 'r': { mp::Num<NL> r; mp::sqrt_rsqrt(x, r); z = r; } break;
+      case 'm': { int64_t j = (i + 1) % a->n; z = mp::mul_sub_mul(x, y, rd<NL>(a, j), rd<NL>(b, j)); } break;
       case 'd': z = mp::from_double<NL>(mp::to_double(x)); break;
       case 'c': z = mp::from_int<NL>(mp::cmp(x, y)); break;
       case 'i': z = mp::from_int<NL>((int64_t)a->exp[i] * (a->sign[i] < 0 ? -1 : 1)); break;

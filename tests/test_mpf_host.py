@@ -96,6 +96,38 @@ def test_binary_ops(shim, nlimb, op):
 
 
 @pytest.mark.parametrize("nlimb", [4, 8, 12, 16])
+def test_fused_mul_sub_mul(shim, nlimb):
+    """a*b - c*d with a single rounding (the elimination step of the panel factorisation), including
+    near-total cancellation: c*d = a*b*(1 + tiny)."""
+    rng = random.Random(77 + nlimb)
+    n = 400
+    a = rand_nums(rng, n, nlimb, erange=20)
+    b = rand_nums(rng, n, nlimb, erange=20)
+    for i in range(0, n - 1, 5):                     # entries i, i+1 multiply to nearly the same product
+        ma, ea = a.get_int(i)
+        mb, eb = b.get_int(i)
+        if ma == 0 or mb == 0:
+            continue
+        a.set_int(i + 1, mb + rng.randint(-2, 2), eb + rng.randint(-1, 1))
+        b.set_int(i + 1, ma, ea)
+    fa, fb = a.to_fractions(), b.to_fractions()
+    exact = [fa[i] * fb[i] - fa[(i + 1) % n] * fb[(i + 1) % n] for i in range(n)]
+    got = run(shim, "m", a, b)
+    p = 32 * nlimb
+    # error: half an ulp of the result plus the truncation of the two products (NL units of limb NL+1)
+    worst = Fraction(0)
+    for i, ex in enumerate(exact):
+        g = got.to_fraction(i)
+        mag = max(abs(fa[i] * fb[i]), abs(fa[(i + 1) % n] * fb[(i + 1) % n]))
+        bound = Fraction(2) ** -(p + 27) * mag
+        if ex != 0:
+            e = abs(ex).numerator.bit_length() - abs(ex).denominator.bit_length()
+            k = e if abs(ex) < Fraction(2) ** e else e + 1
+            bound += Fraction(2) ** (k - p) * Fraction(5001, 10000)
+        assert abs(g - ex) <= bound, (i, float(abs(g - ex) / bound))
+
+
+@pytest.mark.parametrize("nlimb", [4, 8, 12, 16])
 def test_sqrt_and_rsqrt(shim, nlimb):
     import mpmath
     rng = random.Random(99 + nlimb)
