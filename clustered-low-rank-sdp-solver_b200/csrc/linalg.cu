@@ -379,7 +379,8 @@ __device__ bool any_eig_below(const uint32_t* dsm, const uint32_t* e2sm, int n, 
 
 template <int NL>
 __global__ void __launch_bounds__(512)
-lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Tensor out, const int* __restrict__ out_index) {
+lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Tensor out, const int* __restrict__ out_index,
+                  const int* __restrict__ only_if) {
   extern __shared__ uint32_t sm[];
   // smem layout (in Num slots of NL+2 words): v[n], q[n], d[n], e2[n], eabs[n], red[33], misc[8], partial[P*CX]
   const int CX = blockDim.x, P = blockDim.y;
@@ -394,6 +395,7 @@ lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Ten
   __shared__ int flag, first_t;
   const int b = blockIdx.x, c = threadIdx.x, part = threadIdx.y;
   const int tid = part * CX + c, nthr = CX * P;
+  if (only_if && !only_if[b]) return;  // already solved by the mixed-precision kernel
   const int64_t ow = offW[b];
   const int64_t out_at = out_index ? out_index[b] : b;
   auto Wat = [&](int r, int cc) { return ow + (int64_t)r * n + cc; };
@@ -578,21 +580,497 @@ lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Ten
   }
 }
 
-void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, const int* d_out_index) {
+// ---------------------------------------------------------------------------------------------------------
+// Mixed-precision smallest eigenvalue (the production path of compute_step_length, MPMP.jl:1857-1870).
+//
+// The tridiagonalisation above costs 4/3 n^3 multiprecision operations on a dependency chain. Here the n^3
+// work is done in FP64 and only O(n^2) work per refinement step in multiprecision:
+//   1. Wd = fp64(W * 2^-emax); Householder tridiagonalisation of Wd in shared memory, Sturm multisection
+//      for a lower bound lo of lambda_min(Wd) (absolute accuracy ~2^-45 |W|);
+//   2. Cholesky (FP64) of Wd - sigma I, sigma = lo - 2^-36 |W|  (positive definite by construction), three
+//      inverse iterations for an FP64 eigenvector v;
+//   3. multiprecision refinement: r = W v - rho v with rho = v'Wv / v'v at full precision; the correction
+//      (W - sigma)^-1 r is computed in FP64 with the Cholesky factor (r scaled by its exponent), projected
+//      against v and subtracted. The error contracts by ~2^-36 |W| / gap per step; iterate until the
+//      residual is at the rounding level of the working precision, so rho is an eigenvalue to 2^-(p-12) |W|
+//      (and quadratically better in the residual while the gap is resolved).
+// A matrix whose refinement does not contract (clustered smallest eigenvalues closer than ~2^-30 |W|), or whose
+// FP64 factorisation breaks down, is flagged and handled by lambda_min_kernel (flags[b] = 1).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LMX_THREADS = 256;
+constexpr int LMX_NT = 5;  // vector slots per lane of warp 0: n <= 160
+constexpr int LMX_MAX_ITERS = 64;
+
+// x <- (Wd - sigma)^-1 x for a vector distributed over the lanes of one warp (element i = lane + 32 t).
+// A holds the Cholesky factor L in both triangles (A[k][i] = A[i][k] = L[max][min]); rd[k] = 1/L[k][k].
+__device__ __forceinline__ void lmx_solve(const double* __restrict__ A, const double* __restrict__ rd, int n, int LD,
+                                          int lane, double (&x)[LMX_NT]) {
+#pragma unroll
+  for (int t0 = 0; t0 < LMX_NT; t0++) {  // L y = x
+    if (32 * t0 >= n) break;
+    for (int kl = 0; kl < 32; kl++) {
+      const int k = 32 * t0 + kl;
+      if (k >= n) break;
+      const double yk = __shfl_sync(0xffffffffu, x[t0], kl) * rd[k];
+      if (lane == kl) x[t0] = yk;
+      const double* row = A + (size_t)k * LD;
+#pragma unroll
+      for (int t = t0; t < LMX_NT; t++) {
+        const int i = lane + 32 * t;
+        if (i > k && i < n) x[t] -= row[i] * yk;
+      }
+    }
+  }
+#pragma unroll
+  for (int t0 = LMX_NT - 1; t0 >= 0; t0--) {  // L^T z = y
+    if (32 * t0 >= n) continue;
+    for (int kl = 31; kl >= 0; kl--) {
+      const int k = 32 * t0 + kl;
+      if (k >= n) continue;
+      const double zk = __shfl_sync(0xffffffffu, x[t0], kl) * rd[k];
+      if (lane == kl) x[t0] = zk;
+      const double* row = A + (size_t)k * LD;
+#pragma unroll
+      for (int t = 0; t <= t0; t++) {
+        const int i = lane + 32 * t;
+        if (i < k) x[t] -= row[i] * zk;
+      }
+    }
+  }
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <int NL>
+__global__ void __launch_bounds__(LMX_THREADS)
+lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Tensor out,
+                        const int* __restrict__ out_index, int* __restrict__ flags) {
+  extern __shared__ double smd[];
+  const int LD = n | 1;
+  double* A = smd;
+  double* dT = A + (size_t)n * LD;
+  double* eT = dT + n;
+  double* vv = eT + n;
+  double* ww = vv + n;
+  double* part = ww + n;
+  double* sc = part + LMX_THREADS;  // 16 scalars
+  uint32_t* vsm = reinterpret_cast<uint32_t*>(sc + 16);        // mp vector v
+  uint32_t* psm = vsm + (size_t)n * (NL + 2);                  // mp partial sums [LMX_THREADS]
+  uint32_t* red = psm + (size_t)LMX_THREADS * (NL + 2);        // block_reduce scratch [33]
+  __shared__ int s_int[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t ow = offW[b];
+  const int64_t out_at = out_index ? out_index[b] : b;
+  const uint32_t* hdr = W.w + (size_t)NL * W.n;
+
+  if (n == 1) {
+    if (tid == 0) {
+      stm<NL>(out, out_at, ldm<NL>(W, ow));
+      flags[b] = 0;
+    }
+    return;
+  }
+  // ---- common exponent ----
+  int emax = mp::EXP_ZERO;
+  for (int idx = tid; idx < n * n; idx += LMX_THREADS) emax = max(emax, ((int32_t)hdr[ow + idx]) >> 1);
+  emax = __reduce_max_sync(0xffffffffu, emax);
+  if (lane == 0) s_int[warp] = emax;
+  __syncthreads();
+  emax = s_int[0];
+#pragma unroll
+  for (int q = 1; q < LMX_THREADS / 32; q++) emax = max(emax, s_int[q]);
+  __syncthreads();
+  if (emax == mp::EXP_ZERO) {  // the zero matrix
+    if (tid == 0) {
+      stm<NL>(out, out_at, mp::zero<NL>());
+      flags[b] = 0;
+    }
+    return;
+  }
+  auto load_fp64 = [&]() {
+    for (int idx = tid; idx < n * n; idx += LMX_THREADS) {
+      const int r = idx / n, c = idx - r * n;
+      Num<NL> x = ldm<NL>(W, ow + idx);
+      double v = 0.0;
+      if (!mp::is_zero(x) && x.e - emax > -1000) {
+        v = ldexp(mp::mant_to_double(x), x.e - emax);
+        if (x.neg) v = -v;
+      }
+      A[(size_t)r * LD + c] = v;
+    }
+  };
+  load_fp64();
+  __syncthreads();
+  // symmetrise the FP64 copy (the callers pass symmetric matrices; this makes the copy exactly symmetric)
+  for (int idx = tid; idx < n * n; idx += LMX_THREADS) {
+    const int r = idx / n, c = idx - r * n;
+    if (r < c) {
+      double s = 0.5 * (A[(size_t)r * LD + c] + A[(size_t)c * LD + r]);
+      A[(size_t)r * LD + c] = s;
+      A[(size_t)c * LD + r] = s;
+    }
+  }
+  __syncthreads();
+
+  // ---- 1. Householder tridiagonalisation in FP64 (full symmetric storage) ----
+  const int R = ((n + 31) / 32) * 32;
+  const int parts = LMX_THREADS / R > 0 ? LMX_THREADS / R : 1;
+  const int row = tid % R, prt = tid / R;
+  for (int k = 0; k + 2 < n; k++) {
+    if (warp == 0) {
+      const double* rk = A + (size_t)k * LD;
+      double sg = 0.0;
+      for (int i = k + 2 + lane; i < n; i += 32) sg += rk[i] * rk[i];
+      sg = warp_sum(sg);
+      const double x1 = rk[k + 1];
+      if (sg == 0.0) {
+        if (lane == 0) {
+          eT[k] = x1;
+          dT[k] = rk[k];
+          sc[2 + (k & 1)] = 1.0;  // skip flag
+        }
+      } else {
+        const double alpha = -copysign(sqrt(x1 * x1 + sg), x1);
+        const double v1 = x1 - alpha;
+        const double binv = 2.0 / (sg + v1 * v1);
+        for (int i = k + 2 + lane; i < n; i += 32) vv[i] = rk[i];
+        if (lane == 0) {
+          vv[k + 1] = v1;
+          eT[k] = alpha;
+          dT[k] = rk[k];
+          sc[0] = binv;
+          sc[2 + (k & 1)] = 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    if (sc[2 + (k & 1)] != 0.0) continue;
+    {
+      double acc = 0.0;
+      if (row > k && row < n && prt < parts)
+        for (int j = k + 1 + prt; j < n; j += parts) acc += A[(size_t)j * LD + row] * vv[j];
+      part[tid] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const double binv = sc[0];
+      double pl[LMX_NT], vp = 0.0;
+#pragma unroll
+      for (int t = 0; t < LMX_NT; t++) {
+        const int i = lane + 32 * t;
+        pl[t] = 0.0;
+        if (i > k && i < n) {
+          double s = 0.0;
+          for (int q = 0; q < parts; q++) s += part[q * R + i];
+          pl[t] = s * binv;
+          vp += pl[t] * vv[i];
+        }
+      }
+      vp = warp_sum(vp);
+      const double Kc = 0.5 * vp * binv;
+#pragma unroll
+      for (int t = 0; t < LMX_NT; t++) {
+        const int i = lane + 32 * t;
+        if (i > k && i < n) ww[i] = pl[t] - Kc * vv[i];
+      }
+    }
+    __syncthreads();
+    {
+      const int m = n - k - 1;
+      for (int idx = tid; idx < m * m; idx += LMX_THREADS) {
+        const int i = k + 1 + idx / m, j = k + 1 + idx % m;
+        A[(size_t)i * LD + j] -= vv[i] * ww[j] + ww[i] * vv[j];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    dT[n - 2] = A[(size_t)(n - 2) * LD + (n - 2)];
+    dT[n - 1] = A[(size_t)(n - 1) * LD + (n - 1)];
+    eT[n - 2] = A[(size_t)(n - 2) * LD + (n - 1)];
+    eT[n - 1] = 0.0;
+  }
+  __syncthreads();
+  // ---- Gershgorin bounds of T ----
+  if (warp == 0) {
+    double lo = 1e300, hi = -1e300;
+    for (int i = lane; i < n; i += 32) {
+      double rad = (i > 0 ? fabs(eT[i - 1]) : 0.0) + (i + 1 < n ? fabs(eT[i]) : 0.0);
+      lo = fmin(lo, dT[i] - rad);
+      hi = fmax(hi, dT[i] + rad);
+    }
+    lo = -warp_max(-lo);
+    hi = warp_max(hi);
+    if (lane == 0) {
+      double nrm = fmax(fabs(lo), fabs(hi));
+      sc[4] = lo - 1e-9 * nrm - 1e-300;
+      sc[5] = hi + 1e-9 * nrm + 1e-300;
+      sc[6] = nrm;
+    }
+  }
+  __syncthreads();
+  const double nrm = sc[6];
+  // ---- multisection with Sturm counts: invariant: no eigenvalue below lo, at least one below hi ----
+  for (int round = 0; round < 9; round++) {
+    const double lo = sc[4], hi = sc[5];
+    if (!(hi - lo > nrm * 0x1p-50)) break;
+    if (tid == 0) s_int[0] = LMX_THREADS - 1;
+    __syncthreads();
+    const double wdt = (hi - lo) * (1.0 / LMX_THREADS);
+    double xt = hi;
+    if (tid < LMX_THREADS - 1) {
+      xt = lo + wdt * (double)(tid + 1);
+      const double pivmin = 1e-290;
+      double q = dT[0] - xt;
+      bool below = q < 0.0;
+      for (int i = 1; i < n && !below; i++) {
+        if (fabs(q) < pivmin) q = pivmin;  // q >= 0 here
+        q = dT[i] - xt - eT[i - 1] * eT[i - 1] / q;
+        below = q < 0.0;
+      }
+      if (below) atomicMin(&s_int[0], tid);
+    }
+    __syncthreads();
+    const int ft = s_int[0];
+    __syncthreads();
+    if (tid == ft) sc[5] = xt;
+    if (ft > 0 && tid == ft - 1) sc[4] = xt;
+    __syncthreads();
+  }
+  const double lam0 = sc[4];
+  const double sigma = lam0 - nrm * 0x1p-36;
+  __syncthreads();
+  // ---- 2. Cholesky of Wd - sigma I (factor kept in both triangles) ----
+  load_fp64();
+  __syncthreads();
+  for (int i = tid; i < n; i += LMX_THREADS) A[(size_t)i * LD + i] -= sigma;
+  if (tid == 0) s_int[1] = 0;
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += LMX_THREADS) {  // exact symmetry (see above)
+    const int r = idx / n, c = idx - r * n;
+    if (r < c) {
+      double s = 0.5 * (A[(size_t)r * LD + c] + A[(size_t)c * LD + r]);
+      A[(size_t)r * LD + c] = s;
+      A[(size_t)c * LD + r] = s;
+    }
+  }
+  __syncthreads();
+  for (int k = 0; k < n; k++) {
+    const double piv = A[(size_t)k * LD + k];
+    if (!(piv > 0.0)) {  // uniform: every thread reads the same value
+      if (tid == 0) s_int[1] = 1;
+      break;
+    }
+    const double rs = rsqrt(piv);
+    __syncthreads();  // everyone has read the pivot
+    for (int i = k + tid; i < n; i += LMX_THREADS) {
+      if (i == k) {
+        A[(size_t)k * LD + k] = piv * rs;
+        dT[k] = rs;
+      } else {
+        const double l = A[(size_t)k * LD + i] * rs;
+        A[(size_t)k * LD + i] = l;
+        A[(size_t)i * LD + k] = l;
+      }
+    }
+    __syncthreads();
+    const int m = n - k - 1;
+    const double* rk = A + (size_t)k * LD;
+    for (int idx = tid; idx < m * m; idx += LMX_THREADS) {
+      const int i = k + 1 + idx / m, j = k + 1 + idx % m;
+      A[(size_t)i * LD + j] -= rk[i] * rk[j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_int[1]) {
+    if (tid == 0) flags[b] = 1;
+    return;
+  }
+  // ---- FP64 inverse iteration (warp 0) ----
+  if (warp == 0) {
+    double x[LMX_NT];
+#pragma unroll
+    for (int t = 0; t < LMX_NT; t++) {
+      const uint32_t i = (uint32_t)(lane + 32 * t);
+      x[t] = (int)i < n ? (double)((i * 2654435761u >> 8) & 0xFFFFu) * (1.0 / 65536.0) - 0.5 : 0.0;
+    }
+    for (int it = 0; it < 4; it++) {
+      lmx_solve(A, dT, n, LD, lane, x);
+      double mx = 0.0;
+#pragma unroll
+      for (int t = 0; t < LMX_NT; t++) mx = fmax(mx, fabs(x[t]));
+      mx = warp_max(mx);
+      double s2 = 0.0;
+#pragma unroll
+      for (int t = 0; t < LMX_NT; t++) {
+        x[t] = mx > 0.0 ? x[t] / mx : 0.0;
+        s2 += x[t] * x[t];
+      }
+      s2 = warp_sum(s2);
+      const double rn = s2 > 0.0 ? rsqrt(s2) : 0.0;
+#pragma unroll
+      for (int t = 0; t < LMX_NT; t++) x[t] *= rn;
+    }
+#pragma unroll
+    for (int t = 0; t < LMX_NT; t++) {
+      const int i = lane + 32 * t;
+      if (i < n) smem_put<NL>(vsm, i, mp::from_double<NL>(x[t]));
+    }
+  }
+  __syncthreads();
+  // ---- 3. multiprecision refinement ----
+  // exponent of |W| as an mp quantity: nrm * 2^emax
+  int nrm_e;
+  (void)frexp(nrm, &nrm_e);
+  nrm_e += emax;
+  const int target = nrm_e - (32 * NL - 12);
+  int prev_rexp = 1 << 30, stalls = 0;
+  bool done = false, failed = false;
+  Num<NL> rho = mp::zero<NL>();
+  for (int iter = 0; iter < LMX_MAX_ITERS; iter++) {
+    // w = W v (W symmetric: column `row` is read as row-major W[j][row], coalesced over the threads)
+    {
+      Num<NL> acc = mp::zero<NL>();
+      if (row < n && prt < parts)
+        for (int j = prt; j < n; j += parts)
+          acc = nadd(acc, nmul(ldm<NL>(W, ow + (int64_t)j * n + row), smem_get<NL>(vsm, j)));
+      smem_put<NL>(psm, tid, acc);
+    }
+    __syncthreads();
+    Num<NL> wi = mp::zero<NL>(), vi = mp::zero<NL>();
+    if (tid < n) {
+      for (int q = 0; q < parts; q++) wi = nadd(wi, smem_get<NL>(psm, q * R + tid));
+      vi = smem_get<NL>(vsm, tid);
+    }
+    Num<NL> svv = block_reduce<NL, RED_ADD>(tid < n ? nmul(vi, vi) : mp::zero<NL>(), red);
+    Num<NL> svw = block_reduce<NL, RED_ADD>(tid < n ? nmul(vi, wi) : mp::zero<NL>(), red);
+    if (mp::is_zero(svv)) {
+      failed = true;
+      break;
+    }
+    rho = ndiv(svw, svv);
+    Num<NL> ri = mp::zero<NL>();
+    if (tid < n) ri = nsub(wi, nmul(rho, vi));
+    int rexp = __reduce_max_sync(0xffffffffu, ri.e);
+    __syncthreads();
+    if (lane == 0) s_int[warp] = rexp;
+    __syncthreads();
+    rexp = s_int[0];
+#pragma unroll
+    for (int q = 1; q < LMX_THREADS / 32; q++) rexp = max(rexp, s_int[q]);
+    if (rexp <= target) {
+      done = true;
+      break;
+    }
+    if (rexp > prev_rexp - 8) {
+      if (++stalls >= 3) {
+        failed = true;
+        break;
+      }
+    }
+    prev_rexp = rexp;
+    // FP64 correction of the scaled residual
+    if (tid < n) {
+      double rd = 0.0;
+      if (!mp::is_zero(ri) && ri.e - rexp > -1000) {
+        rd = ldexp(mp::mant_to_double(ri), ri.e - rexp);
+        if (ri.neg) rd = -rd;
+      }
+      ww[tid] = rd;
+      vv[tid] = mp::to_double(vi);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double x[LMX_NT], vd[LMX_NT];
+#pragma unroll
+      for (int t = 0; t < LMX_NT; t++) {
+        const int i = lane + 32 * t;
+        x[t] = i < n ? ww[i] : 0.0;
+        vd[t] = i < n ? vv[i] : 0.0;
+      }
+      lmx_solve(A, dT, n, LD, lane, x);
+      double xv = 0.0, v2 = 0.0;
+#pragma unroll
+      for (int t = 0; t < LMX_NT; t++) xv += x[t] * vd[t], v2 += vd[t] * vd[t];
+      xv = warp_sum(xv);
+      v2 = warp_sum(v2);
+      const double cf = v2 > 0.0 ? xv / v2 : 0.0;
+#pragma unroll
+      for (int t = 0; t < LMX_NT; t++) {
+        const int i = lane + 32 * t;
+        if (i < n) ww[i] = x[t] - cf * vd[t];
+      }
+    }
+    __syncthreads();
+    if (tid < n) {
+      const double dl = ww[tid];
+      if (dl != 0.0 && isfinite(dl)) {
+        Num<NL> corr = mp::mul_2exp(mp::from_double<NL>(dl), rexp - emax);
+        smem_put<NL>(vsm, tid, nsub(vi, corr));
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (done && !failed) {
+      stm<NL>(out, out_at, rho);
+      flags[b] = 0;
+    } else {
+      flags[b] = 1;
+    }
+  }
+}
+
+static size_t lmx_smem_bytes(int n, int NL) {
+  const int LD = n | 1;
+  return sizeof(double) * ((size_t)n * LD + 4 * (size_t)n + LMX_THREADS + 16) +
+         sizeof(uint32_t) * ((size_t)n + LMX_THREADS + 33) * (NL + 2);
+}
+static bool lmx_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CLRSDP_LAMBDA_MIXED");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, const int* d_out_index, int* d_flags) {
   if (W.n > 512) throw SolverError(-1, "lambda_min: n > 512 not supported");
   int cx = std::min(1024, ((W.n + 31) / 32) * 32);
   int P = std::max(1, 512 / cx);
   dim3 blk(cx, P, 1);
   DISPATCH_NL(nl, {
-    size_t words = (size_t)(5 * W.n + 33 + 8 + P * cx) * (NL + 2);
     static bool attr[17] = {false};
     if (!attr[NL]) {
       CLR_CUDA(cudaFuncSetAttribute(lambda_min_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CLR_CUDA(cudaFuncSetAttribute(lambda_min_mixed_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       attr[NL] = true;
     }
-    std::string nm = "lambda_min_n" + std::to_string(W.n);
+    // production path: FP64 factorisation + multiprecision refinement; matrices it flags (and sizes that do not fit
+    // its shared-memory working set) go through the all-multiprecision kernel
+    const size_t mixed_bytes = lmx_smem_bytes(W.n, NL);
+    const bool mixed = d_flags && lmx_enabled() && W.n <= 32 * LMX_NT && mixed_bytes <= 226 * 1024;
+    if (mixed) {
+      std::string nm = "lambda_min_mixed_n" + std::to_string(W.n);
+      int tk = ctx.begin(nm.c_str());
+      lambda_min_mixed_kernel<NL><<<W.batch, LMX_THREADS, mixed_bytes, ctx.stream>>>(W.t, W.d_off, W.n, out, d_out_index, d_flags);
+      ctx.end(tk);
+    }
+    size_t words = (size_t)(5 * W.n + 33 + 8 + P * cx) * (NL + 2);
+    std::string nm = (mixed ? "lambda_min_fallback_n" : "lambda_min_n") + std::to_string(W.n);
     int tk = ctx.begin(nm.c_str());
-    lambda_min_kernel<NL><<<W.batch, blk, words * sizeof(uint32_t), ctx.stream>>>(W.t, W.d_off, W.n, out, d_out_index);
+    lambda_min_kernel<NL><<<W.batch, blk, words * sizeof(uint32_t), ctx.stream>>>(W.t, W.d_off, W.n, out, d_out_index,
+                                                                                   mixed ? d_flags : nullptr);
     ctx.end(tk);
   });
 }

@@ -40,7 +40,9 @@ void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, boo
 // Replaces approx_eig_qr! + min over real parts (MPMP.jl:1857-1870) by Householder tridiagonalisation
 // + multisection with Sturm counts.
 // out[d_out_index ? d_out_index[b] : b] receives the result of matrix b.
-void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, const int* d_out_index);
+// With d_flags (batch ints of scratch) the FP64-preconditioned refinement kernel runs first (n^3 work in FP64, O(n^2)
+// multiprecision work per refinement step) and the all-multiprecision kernel only handles the matrices it flags.
+void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, const int* d_out_index, int* d_flags = nullptr);
 
 // ---- elementwise ---------------------------------------------------------------------------------------
 // out[i] = sa*a[i] + sb*b[i], sa,sb in {-1,0,+1}; i in [0,n) at offsets (oo, ao, bo)

@@ -240,6 +240,7 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
   work.alloc(std::max<size_t>({(size_t)4096, reduce_work_elems(), gemv_work_elems(n_y, sumS), gemv_work_elems(sumS, n_y)}), nl);
   n_status = 2 * (int)blocks_.size() + J + 1;  // X blocks, Y blocks, S_j, Q
   d_status.ensure(sizeof(int) * n_status);
+  d_lamflag.ensure(sizeof(int) * 2 * std::max<size_t>(1, blocks_.size()));
   h_status.assign(n_status, 0);
   uploaded_.assign(J, 0);
   structure_set = true;
@@ -842,7 +843,7 @@ void Solver::step_lengths() {
     o.dst = T2d.t(), o.rs = g.nb, o.cs = 1;
     gemm_->multiply(g.sLinv, g.sB, plan_of(nb2, g.nb, g.nb), o);
     ew_symmetrize(ctx, nl, blkbatch2(g, W2), T2d.t());
-    lambda_min(ctx, nl, blkbatch2(g, W2), lam.t(), g.lamIdx2.as<int>());
+    lambda_min(ctx, nl, blkbatch2(g, W2), lam.t(), g.lamIdx2.as<int>(), d_lamflag.as<int>());
   }
   reduce_min(ctx, nl, lam.t(), 0, (int64_t)blocks_.size(), scal.t(), SL_LAM_X, work.t());
   reduce_min(ctx, nl, lam.t(), (int64_t)blocks_.size(), (int64_t)blocks_.size(), scal.t(), SL_LAM_Y, work.t());
@@ -1290,7 +1291,9 @@ void Solver::op_lambda_min(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* 
   for (int i = 0; i < batch; i++) off[i] = (int64_t)i * n * n;
   DevBuf doff;
   upload(doff, off, ctx.stream);
-  lambda_min(ctx, nl, MatBatch{a.t(), doff.as<int64_t>(), batch, n}, out.t(), nullptr);
+  DevBuf fl;
+  fl.ensure(sizeof(int) * std::max(1, batch));
+  lambda_min(ctx, nl, MatBatch{a.t(), doff.as<int64_t>(), batch, n}, out.t(), nullptr, fl.as<int>());
   ctx.sync();
   to_host(out, 0, batch, lamo, 0);
 }

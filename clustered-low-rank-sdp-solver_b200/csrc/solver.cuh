@@ -138,7 +138,7 @@ class Solver {
   uint64_t graph_epoch_ = 0;
   int direct_iters_ = 0;
   int64_t graph_launches_ = 0;
-  DevBuf d_status, d_flags, d_scal_out, d_qoff, d_status_any;
+  DevBuf d_status, d_flags, d_scal_out, d_qoff, d_status_any, d_lamflag;
   std::vector<int> h_status;
   int n_status = 0;
   // iteration bookkeeping
