@@ -224,8 +224,13 @@ def main():
     # ---- per-kernel pass: the same iterations again with CUDA events around every launch (roofline numbers) ----
     h.profile_reset(True)
     prof_s = 0.0
+    phase_names = ["decomposition", "predictor", "corrector", "step_length", "factor_XY+X_inv", "R", "residuals", "schur",
+                   "chol_S", "LinvB", "Q", "chol_Q", "Z", "rhs_x", "system", "dX", "dY"]
+    phases = np.zeros(len(phase_names))
     for _ in range(args.steps):
-        prof_s += h.iterate().seconds
+        rr = h.iterate()
+        prof_s += rr.seconds
+        phases += np.array(list(rr.timings)[:len(phase_names)])
     prof = h.profile_dump()
     h.profile_reset(False)
 
@@ -237,11 +242,18 @@ def main():
     d2h = h2d + ctypes.sizeof(type(r))
     barrier()
     t0 = time.perf_counter()
+    e2e_parts = np.zeros(4)
     for _ in range(args.steps):
+        ta = time.perf_counter()
         h.upload_point(*state)
+        tb = time.perf_counter()
         h.prepare()
+        tc = time.perf_counter()
         r = h.iterate()
-        state = h.download_point(n_x, n_X, n_y)
+        td = time.perf_counter()
+        state = h.download_point(n_x, n_X, n_y, out=state)
+        te = time.perf_counter()
+        e2e_parts += np.array([tb - ta, tc - tb, td - tc, te - td])
     barrier()
     e2e_wall = time.perf_counter() - t0
     if dist is not None:
@@ -286,6 +298,8 @@ def main():
                             "iteration); no explicit flush", **WORKLOAD),
                 wall_ms_per_step=wall / args.steps * 1e3,
                 e2e=dict(value=e2e_wall / args.steps, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         parts_ms=dict(zip(["upload_point", "prepare", "iterate", "download_point"],
+                                           [round(float(v) / args.steps * 1e3, 3) for v in e2e_parts])),
                          note="upload_point + prepare + iterate + download_point through the C ABI with host buffers"),
                 gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline,
                 algorithmic=dict(pmac_per_iter=pmac, int8_mac_per_iter=macs))
@@ -296,7 +310,8 @@ def main():
             line["cpu_baseline"] = dict(error=str(e))
     if args.profile_out:
         with open(args.profile_out, "w") as f:
-            json.dump(dict(per_kernel=prof, steps=args.steps, dev_seconds=prof_s), f, indent=1)
+            json.dump(dict(per_kernel=prof, steps=args.steps, dev_seconds=prof_s,
+                           phase_ms_per_step={k: float(v) / args.steps * 1e3 for k, v in zip(phase_names, phases)}), f, indent=1)
     print(json.dumps(line))
 
 

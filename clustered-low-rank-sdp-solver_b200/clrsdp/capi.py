@@ -177,8 +177,10 @@ class Handle:
         s = [a.c_struct() for a in (x, X, y, Y)]
         self._check(f(self._h, *[ctypes.byref(v) for v in s]), "upload_point")
 
-    def download_point(self, n_x, n_X, n_y):
-        out = [MpArray(n, self.nlimb) for n in (n_x, n_X, n_y, n_X)]
+    def download_point(self, n_x, n_X, n_y, out=None):
+        """x, X, y, Y of the current iterate; `out` (a list returned by an earlier call) is overwritten in place"""
+        if out is None:
+            out = [MpArray(n, self.nlimb) for n in (n_x, n_X, n_y, n_X)]
         f = self._fn("download_point")
         mp = ctypes.POINTER(clrsdp_mp)
         f.argtypes = [ctypes.c_void_p, mp, mp, mp, mp]

@@ -165,16 +165,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
+// one lane of a converged warp; everything around the elected instruction stays warp-uniform, so descriptors and
+// barrier addresses live in uniform registers (issuing from `if (lane == 0)` makes the compiler wrap every tcgen05/TMA
+// instruction in a lane-serialising R2UR loop, ~250 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 struct MmaParams {
-  int T, M, N, batch, nsplit, Kp, Kc, BK, BN, m_tiles, n_tiles, npairs, item0, stages;
+  int T, M, N, batch, nsplit, Kp, Kc, BK, BN, m_tiles, n_tiles, item0, stages;
+  int stack;  // digits of A stacked along the 128 MMA rows (1, 2 or 4): item tiles of 128/stack rows
+  int Mpad;   // rows per item in the block buffer (m_tiles * 128)
   const int* rowA;
   const int* rowB;
-  int32_t* planes;  // [T][nsplit][batch][M][N]
+  int32_t* blocks;  // [T][nsplit][batch][ceil(N/4)][Mpad][4]: block q, lane group r holds the partial plane q + r
   uint32_t idesc, sbo16, layout_type;
+  int debug;  // CLRSDP_MMA_DEBUG (measuring aid): 1 = skip the block stores, 2 = skip the TMEM loads, 32 = cycle counters
+  long long* dbg;
 };
 
-constexpr int MMA_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int MMA_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue (two sets)
 constexpr int MAX_STAGES = 8;
+constexpr int DG = 4;             // digits per operand group: one pipeline stage feeds a DG x DG square of digit pairs
+constexpr int ACC_SLOTS = 8;      // accumulator slots in TMEM (block q lives in slot q % ACC_SLOTS)
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo16, uint32_t layout_type) {
   // K-major canonical layout (cute::UMMA::SmemDescriptor): start>>4 | LBO[16,30) | SBO[32,46) | version=1 at
@@ -187,22 +206,117 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo16
   return d;
 }
 
+template <int STACK>
+__device__ __forceinline__ void mma_issue(const MmaParams& p, uint64_t* bars, uint8_t* smem, uint32_t stage_bytes,
+                                          uint32_t a_tile, uint32_t b_tile, uint32_t a_bytes, uint32_t tmem_base,
+                                          int kblocks) {
+  const int T = p.T, Dmax = (T - 1) / DG;
+  constexpr int QSPAN = (DG - STACK) + (DG - 1);
+  const uint32_t a_step = a_tile >> 4, b_step = b_tile >> 4;  // descriptor address units (16 bytes)
+  const bool two_k = p.BK > 32;
+  int stage = 0;
+  uint32_t phase = 0;
+  long long t_full = 0, t_start = clock64();
+  for (int D = Dmax; D >= 0; D--) {
+    const int sb = (DG * D) & (ACC_SLOTS - 1);  // slot of block 4D
+    const int cmax = T - 1 - DG * D;            // blocks 4D + c with c > cmax do not exist
+    bool first = true;                          // first stage of this anti-diagonal: it creates blocks 4D .. 4D+3
+    for (int I = 0; I <= D; I++) {
+      const int J = D - I;
+      if (DG * I >= T || DG * J >= T) continue;
+      const int na = min(DG / STACK, (T - DG * I + STACK - 1) / STACK), nb = min(DG, T - DG * J);
+      for (int kb = 0; kb < kblocks; kb++) {
+        const long long c0 = p.dbg ? clock64() : 0;
+        mbar_wait(smem_u32(&bars[stage]), phase);
+        if (p.dbg) t_full += clock64() - c0;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint64_t adesc0 = make_smem_desc(sa, p.sbo16, p.layout_type);
+        const uint64_t bdesc0 = make_smem_desc(sa + a_bytes, p.sbo16, p.layout_type);
+        const bool full = !first && na == DG / STACK && nb == DG && cmax >= QSPAN;
+        if (full) {  // interior stage (the common case): no predicates, no waits
+          if (elect_one()) {
+#pragma unroll
+            for (int ia = 0; ia < DG / STACK; ia++) {
+#pragma unroll
+              for (int jb = 0; jb < DG; jb++) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(((sb + ia * STACK + jb) & (ACC_SLOTS - 1)) * p.BN);
+                const uint64_t ad = adesc0 + (uint64_t)(ia * a_step), bd = bdesc0 + (uint64_t)(jb * b_step);
+                umma_i8(d_tmem, ad, bd, p.idesc, 1u);
+                if (two_k) umma_i8(d_tmem, ad + 2, bd + 2, p.idesc, 1u);
+              }
+            }
+            umma_commit(smem_u32(&bars[8 + stage]));
+          }
+        } else if (elect_one()) {  // one lane issues the whole stage
+#pragma unroll
+          for (int ia = 0; ia < DG / STACK; ia++) {
+#pragma unroll
+            for (int jb = 0; jb < DG; jb++) {
+              const int c = ia * STACK + jb;  // block 4D + c, lane group r holds plane 4D + c + r
+              if (ia < na && jb < nb && c <= cmax) {
+                uint32_t acc = 1u;
+                if (ia == 0 && first) {  // (0, jb) is the first pair of the schedule that touches block 4D + jb
+                  acc = 0u;
+                  const uint32_t u = (uint32_t)(T - 1 - (DG * D + c)) >> 3;  // earlier blocks in the same slot
+                  if (u) {  // wait until the epilogue has drained the previous one
+                    mbar_wait(smem_u32(&bars[24 + ((sb + c) & (ACC_SLOTS - 1))]), (u & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                  }
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(((sb + c) & (ACC_SLOTS - 1)) * p.BN);
+                const uint64_t ad = adesc0 + (uint64_t)(ia * a_step), bd = bdesc0 + (uint64_t)(jb * b_step);
+                umma_i8(d_tmem, ad, bd, p.idesc, acc);
+                if (two_k) umma_i8(d_tmem, ad + 2, bd + 2, p.idesc, 1u);
+              }
+            }
+          }
+          umma_commit(smem_u32(&bars[8 + stage]));  // frees the smem slot when these MMAs retire
+        }
+        __syncwarp();
+        first = false;
+        if (++stage == p.stages) stage = 0, phase ^= 1u;
+      }
+    }
+    // blocks that no later anti-diagonal touches are complete
+    const int q_hi = min(T - 1, DG * D + QSPAN);
+    const int q_lo = (D == 0) ? 0 : DG * D + QSPAN - (DG - 1);
+    if (elect_one())
+      for (int q = q_hi; q >= q_lo; q--) umma_commit(smem_u32(&bars[16 + (q & (ACC_SLOTS - 1))]));
+    __syncwarp();
+  }
+  if (p.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    p.dbg[0] = clock64() - t_start;
+    p.dbg[1] = t_full;
+  }
+}
+
+// One CTA = one 128 x BN output tile of one batch item (x one K-split) and ALL its digit planes.
+//
+// The digit pairs (a, b), a + b < T, are visited in DG x DG squares: a pipeline stage holds the tiles of DG digits of A
+// and DG digits of B for one K block (two TMA boxes), and feeds DG*DG/stack MMAs, so every byte brought in from L2 is
+// used DG/2 times more often than in a pair-at-a-time schedule (the L2 -> smem path, ~42 B/clk/SM, is what bounds a
+// digit-pair product at 128 x 64 x 32). Squares are processed by anti-diagonals D = I + J from the least significant
+// end; the pairs of one anti-diagonal touch the blocks q = a + b in [4D, 4D + 6], which live in a ring of 8 TMEM
+// accumulators; when an anti-diagonal is finished its four lowest-order blocks are complete and are drained by the
+// epilogue warps while the next anti-diagonal accumulates into the other slots.
+//
+// Items with at most 64 (32) rows stack 2 (4) consecutive digits of A along the 128 rows of the MMA: rows
+// [r*128/stack, (r+1)*128/stack) of block q then hold the contribution of digit a + r, i.e. of plane q + r, and the
+// carry kernel adds the `stack` lane groups. This keeps all 128 rows of the tensor core busy on the 64 x 64 blocks.
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, MmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  // every operand tile starts on a 1024-byte boundary (required by the 128B swizzle atom)
-  const uint32_t a_bytes = 128u * p.BK, b_bytes = (uint32_t)p.BN * p.BK;
+  const uint32_t a_tile = 128u * p.BK, b_tile = (uint32_t)p.BN * p.BK;
+  const uint32_t a_bytes = a_tile * (DG / p.stack), b_bytes = b_tile * DG;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
   uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
-  // bars[0..7] full, [8..15] empty, [16..17] tmem_full, [18..19] tmem_empty, then tmem base ptr
-  uint32_t* tmem_slot = (uint32_t*)(bars + 20);
+  // bars[0..7] full, [8..15] empty, [16..23] slot_full, [24..31] slot_empty, then the TMEM base pointer
+  uint32_t* tmem_slot = (uint32_t*)(bars + 32);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // decode work: pair fastest so that CTAs sharing operand tiles are co-scheduled (L2 reuse)
   int idx = blockIdx.x;
-  const int pair = idx % p.npairs;
-  idx /= p.npairs;
   const int split = idx % p.nsplit;
   idx /= p.nsplit;
   const int nt = idx % p.n_tiles;
@@ -215,21 +329,20 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int rowB0 = (p.rowB ? p.rowB[gitem] : gitem * p.N) + nt * p.BN;
   const int k_begin = split * p.Kc;
   const int kblocks = (min(p.Kp, k_begin + p.Kc) - k_begin) / p.BK;
-  int planes_t[2];
-  planes_t[0] = p.T - 1 - pair;  // the long plane first
-  planes_t[1] = pair;
-  const int nplanes = (planes_t[0] == planes_t[1]) ? 1 : 2;
+  const int T = p.T, stack = p.stack;
+  const int qspan = (DG - stack) + (DG - 1);  // blocks touched by anti-diagonal D: [4D, 4D + qspan]
+  const int Dmax = (T - 1) / DG;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(ACC_SLOTS * p.BN)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; s++) {
       mbar_init(smem_u32(&bars[s]), 1);
       mbar_init(smem_u32(&bars[8 + s]), 1);
     }
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < ACC_SLOTS; s++) {
       mbar_init(smem_u32(&bars[16 + s]), 1);
-      mbar_init(smem_u32(&bars[18 + s]), 4);
+      mbar_init(smem_u32(&bars[24 + s]), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -245,81 +358,89 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int pl = 0; pl < nplanes; pl++) {
-        const int t = planes_t[pl];
-        for (int a = 0; a <= t; a++)
+      for (int D = Dmax; D >= 0; D--)
+        for (int I = 0; I <= D; I++) {
+          const int J = D - I;
+          if (DG * I >= T || DG * J >= T) continue;
           for (int kb = 0; kb < kblocks; kb++) {
             mbar_wait(smem_u32(&bars[8 + stage]), phase ^ 1u);
             uint32_t full = smem_u32(&bars[stage]);
-            mbar_expect_tx(full, a_bytes + b_bytes);
             uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
             int k0 = k_begin + kb * p.BK;
-            tma_load_3d(sa, &tmA, full, k0, rowA0, a);
-            tma_load_3d(sa + a_bytes, &tmB, full, k0, rowB0, t - a);
+            if (elect_one()) {
+              mbar_expect_tx(full, a_bytes + b_bytes);
+              tma_load_3d(sa, &tmA, full, k0, rowA0, DG * I);            // box (BK, 128/stack rows, DG digits)
+              tma_load_3d(sa + a_bytes, &tmB, full, k0, rowB0, DG * J);  // box (BK, BN rows, DG digits)
+            }
+            __syncwarp();
             if (++stage == p.stages) stage = 0, phase ^= 1u;
           }
-      }
+        }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int pl = 0; pl < nplanes; pl++) {
-        const int t = planes_t[pl];
-        // accumulator buffer pl: first use of each buffer needs no wait (fresh barrier parity trick)
-        mbar_wait(smem_u32(&bars[18 + pl]), 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(pl * p.BN);
-        const int nkb = (t + 1) * kblocks;
-        for (int kb = 0; kb < nkb; kb++) {
-          mbar_wait(smem_u32(&bars[stage]), phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          uint64_t adesc = make_smem_desc(sa, p.sbo16, p.layout_type);
-          uint64_t bdesc = make_smem_desc(sa + a_bytes, p.sbo16, p.layout_type);
-          for (int kk = 0; kk < p.BK / 32; kk++) {
-            umma_i8(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), p.idesc,
-                    (kb > 0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(smem_u32(&bars[8 + stage]));  // frees the smem slot when these MMAs retire
-          if (++stage == p.stages) stage = 0, phase ^= 1u;
-        }
-        umma_commit(smem_u32(&bars[16 + pl]));  // accumulator pl complete
-      }
-    }
+    // The whole warp runs the (warp-uniform) schedule; one elected lane issues. The per-pair path is a handful of
+    // uniform-register instructions: a tcgen05.mma of 128 x 64 x 32 retires every 48 cycles, so anything longer
+    // than that per MMA on this single-warp instruction stream is directly visible as idle tensor pipe.
+    if (stack == 1)
+      mma_issue<1>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks);
+    else if (stack == 2)
+      mma_issue<2>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks);
+    else
+      mma_issue<4>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks);
   } else {
-    // ------------------------------ epilogue: TMEM -> registers -> HBM planes --------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = mt * 128 + q * 32 + lane;
-    for (int pl = 0; pl < nplanes; pl++) {
-      const int t = planes_t[pl];
-      mbar_wait(smem_u32(&bars[16 + pl]), 0u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int32_t* out = p.planes + ((((size_t)t * p.nsplit + split) * p.batch + item) * p.M + row) * (size_t)p.N;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pl * p.BN + c0), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        int col = nt * p.BN + c0;
-        if (row < p.M) {
-          if (col + 16 <= p.N && (p.N & 3) == 0) {
-            int4* o4 = reinterpret_cast<int4*>(out + col);
+    // ------------------------------ epilogue: TMEM -> registers -> HBM blocks --------------------
+    // Two sets of four warps (one warp per TMEM lane quarter) drain alternate blocks, so two drains are in flight;
+    // all TMEM loads of a block are issued before the single wait.
+    const int q4 = warp & 3;              // TMEM lane quarter this warp may access
+    const int eset = (warp - 2) >> 2;     // 0 / 1: handles the blocks with q % 2 == eset
+    const int lrow = q4 * 32 + lane;
+    const int mip = 128 / stack;
+    const int grp = lrow / mip;           // lane group: plane q + grp
+    const bool row_ok = (stack == 1) ? (mt * 128 + lrow < p.M) : ((lrow - grp * mip) < p.M);
+    const int row = mt * 128 + lrow;
+    for (int D = Dmax; D >= 0; D--) {
+      const int q_hi = min(T - 1, DG * D + qspan);
+      const int q_lo = (D == 0) ? 0 : DG * D + qspan - (DG - 1);
+      for (int q = q_hi; q >= q_lo; q--) {
+        if ((q & 1) != eset) continue;
+        const int slot = q & (ACC_SLOTS - 1);
+        const uint32_t u = (uint32_t)(T - 1 - q) >> 3;
+        mbar_wait(smem_u32(&bars[16 + slot]), u & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // chunk-major block layout [N/4][Mpad][4]: the 32 rows of a warp are 512 contiguous bytes per 4-column chunk
+        const int n4 = (p.N + 3) >> 2;
+        int4* out = reinterpret_cast<int4*>(p.blocks) + (((size_t)q * p.nsplit + split) * p.batch + item) * (size_t)n4 * p.Mpad + row;
+        const bool live = row_ok && (q + grp < T) && !(p.debug & 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(slot * p.BN);
+        uint32_t v[4][16];
+        if (!(p.debug & 2)) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) o4[i] = make_int4((int)v[4 * i], (int)v[4 * i + 1], (int)v[4 * i + 2], (int)v[4 * i + 3]);
-          } else {
+          for (int cc = 0; cc < 4; cc++)
+            if (cc * 16 < p.BN) tmem_ld16(taddr + cc * 16, v[cc]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        // the accumulator slot is free as soon as it has been read
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[24 + slot]));
+        if (live) {
 #pragma unroll
-            for (int i = 0; i < 16; i++)
-              if (col + i < p.N) out[col + i] = (int32_t)v[i];
+          for (int cc = 0; cc < 4; cc++) {
+            if (cc * 16 < p.BN) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int chunk = ((nt * p.BN + cc * 16) >> 2) + i;
+                if (chunk < n4)
+                  out[(size_t)chunk * p.Mpad] = make_int4((int)v[cc][4 * i], (int)v[cc][4 * i + 1], (int)v[cc][4 * i + 2], (int)v[cc][4 * i + 3]);
+              }
+            }
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars[18 + pl]));
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -334,7 +455,8 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // 3. carry propagation + renormalisation:  planes -> mp numbers
 // =====================================================================================================
 struct CarryArgs {
-  const int32_t* planes;  // [T][nsplit][batch][M][N]
+  const int32_t* planes;  // blocks [T][nsplit][batch][ceil(N/4)][Mpad][4]; plane p = sum_r block[p - r] rows [r*mip, r*mip + M)
+  int stack, mip, Mpad;
   const int32_t* expA;    // per row of A (global row index)
   const int32_t* expB;
   const int* rowA;
@@ -349,17 +471,28 @@ struct CarryArgs {
   int epi;
 };
 
-template <int NL, int T>
+template <int NL, int T, int STACK>
 __global__ void carry_kernel(CarryArgs c) {
   constexpr int NW = (T + 3) / 4 + 2;
-  int64_t total = (int64_t)c.batch * c.M * c.N;
-  size_t pstride = (size_t)c.nsplit * total;
+  // a warp owns a 4 x 8 patch of one item: its plane reads are two runs of 4 rows x 16 bytes in the chunk-major block
+  // layout, its result stores 4 runs of 8 consecutive entries
+  const int pm = (c.M + 3) >> 2, pn = (c.N + 7) >> 3, n4 = (c.N + 3) >> 2;
+  const int64_t total = (int64_t)c.batch * pm * pn * 32;
+  const size_t sstride = (size_t)c.batch * n4 * c.Mpad * 4;  // one K-split of one block
+  const size_t pstride = (size_t)c.nsplit * sstride;          // one block
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    int j = (int)(idx % c.N);
-    int i = (int)((idx / c.N) % c.M);
-    int b = (int)(idx / ((int64_t)c.N * c.M));
+    const int ln = (int)(idx & 31);
+    int64_t patch = idx >> 5;
+    const int pj = (int)(patch % pn);
+    patch /= pn;
+    const int pi = (int)(patch % pm);
+    const int b = (int)(patch / pm);
+    const int i = 4 * pi + (ln >> 3), j = 8 * pj + (ln & 7);
+    if (i >= c.M || j >= c.N) continue;
     int gb = c.item0 + b;
+    const size_t e0 = (((size_t)b * n4 + (j >> 2)) * c.Mpad + i) * 4 + (j & 3);  // entry (b, i, j) in lane group 0
+    const size_t gstride = (size_t)c.mip * 4;                                      // next lane group
     uint32_t W[NW];
 #pragma unroll
     for (int q = 0; q < NW; q++) W[q] = 0;
@@ -372,14 +505,16 @@ __global__ void carry_kernel(CarryArgs c) {
       int64_t acc[CH];
 #pragma unroll
       for (int u = 0; u < CH; u++) acc[u] = 0;
-      for (int s = 0; s < c.nsplit; s++) {
-        const int32_t* ps = c.planes + (size_t)s * total + idx;
-        int32_t v32[CH];
+      for (int s = 0; s < c.nsplit; s++)
 #pragma unroll
-        for (int u = 0; u < CH; u++) v32[u] = (c0 - u >= 0) ? ps[(size_t)(c0 - u >= 0 ? c0 - u : 0) * pstride] : 0;
+        for (int r = 0; r < STACK; r++) {  // plane t = sum over lane groups r of block t - r
+          const int32_t* ps = c.planes + (size_t)s * sstride + e0 + (size_t)r * gstride;
+          int32_t v32[CH];
 #pragma unroll
-        for (int u = 0; u < CH; u++) acc[u] += v32[u];
-      }
+          for (int u = 0; u < CH; u++) v32[u] = (c0 - u - r >= 0) ? ps[(size_t)(c0 - u - r >= 0 ? c0 - u - r : 0) * pstride] : 0;
+#pragma unroll
+          for (int u = 0; u < CH; u++) acc[u] += v32[u];
+        }
 #pragma unroll
       for (int u = 0; u < CH; u++) {
         const int t = c0 - u;
@@ -462,12 +597,12 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-static CUtensorMap make_map(const Slice& s, int box_rows, int BK) {
+static CUtensorMap make_map(const Slice& s, int box_rows, int BK, int box_digits) {
   CUtensorMap tm;
   // rows past rows_total (tiles of the last item) are out of bounds => zero-filled by TMA
   cuuint64_t dims[3] = {(cuuint64_t)s.Kp, (cuuint64_t)s.rows_total, (cuuint64_t)s.S};
   cuuint64_t strides[2] = {(cuuint64_t)s.Kp, (cuuint64_t)s.Kp * s.rows_total};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)box_digits};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapSwizzle sw = BK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (BK == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s.digits.p, dims, strides, box, estr,
@@ -518,6 +653,14 @@ void GemmEngine::slice(const OperandDesc& op, Slice& out) {
   }
 }
 
+static int bk_cap() {
+  static int v = -1;
+  if (v < 0) v = 64;
+  return v;
+}
+static int stack_of(int M) { return M <= 32 ? 4 : (M <= 64 ? 2 : 1); }
+static int bn_of(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : 64); }
+
 void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, int item0, int nitems, int nsplit,
                          int Kc) {
   MmaParams p;
@@ -529,61 +672,95 @@ void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, i
   p.nsplit = nsplit;
   p.Kp = A.Kp;
   p.Kc = Kc;
-  p.BK = std::min(A.Kp, 128);
-  p.BN = std::min(256, ((plan.N + 15) / 16) * 16);
+  p.BK = std::min(A.Kp, bk_cap());
+  p.BN = bn_of(plan.N);
+  p.stack = stack_of(plan.M);
   p.m_tiles = ceil_div(plan.M, 128);
+  p.Mpad = p.m_tiles * 128;
   p.n_tiles = ceil_div(plan.N, p.BN);
-  p.npairs = (p.T + 1) / 2;
   p.item0 = item0;
   p.rowA = plan.d_rowA;
   p.rowB = plan.d_rowB;
-  p.planes = planes_.as<int32_t>();
+  p.blocks = planes_.as<int32_t>();
+  {
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("CLRSDP_MMA_DEBUG") ? atoi(getenv("CLRSDP_MMA_DEBUG")) : 0;
+    p.debug = dbg;
+  }
   // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 (2) at [4,6), a/b format INT8 (1) at
   // [7,10)/[10,13), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
   p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.sbo16 = (8u * p.BK) >> 4;
   p.layout_type = p.BK == 128 ? 2u : (p.BK == 64 ? 4u : 6u);
-  size_t stage_bytes = (size_t)128 * p.BK + ((((size_t)p.BN * p.BK) + 1023) & ~(size_t)1023);
-  p.stages = (int)std::min<size_t>(MAX_STAGES, (200 * 1024) / stage_bytes);
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
-  CUtensorMap tmA = make_map(A, 128, p.BK), tmB = make_map(B, p.BN, p.BK);
-  int64_t grid = (int64_t)nitems * p.m_tiles * p.n_tiles * nsplit * p.npairs;
-  double macs = (double)nitems * p.m_tiles * 128.0 * p.n_tiles * p.BN * (double)A.Kp * (p.T * (p.T + 1) / 2.0);
+  size_t a_bytes = (size_t)128 * p.BK * (DG / p.stack), b_bytes = (size_t)p.BN * p.BK * DG;
+  size_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~(size_t)1023);
+  // dynamic smem: [1 KB alignment slack][stages][1 KB of barriers]
+  p.stages = (int)std::min<size_t>(MAX_STAGES, (196 * 1024) / stage_bytes);
+  size_t smem = 1024 + (size_t)p.stages * stage_bytes + 1024;
+  CUtensorMap tmA = make_map(A, 128 / p.stack, p.BK, DG), tmB = make_map(B, p.BN, p.BK, DG);
+  int64_t grid = (int64_t)nitems * p.m_tiles * p.n_tiles * nsplit;
+  double macs = (double)nitems * p.m_tiles * 128.0 * p.n_tiles * p.BN * (double)A.Kp * (p.T * (p.T + 1) / 2.0) / p.stack;
   last_int8_macs += macs;
   // algorithmic MACs: M*N*K * s(s+1)/2 with s = p/8, no guard digits, no tile padding
   double s_alg = 4.0 * nl_;
   double alg = (double)nitems * plan.M * plan.N * (double)A.K * (s_alg * (s_alg + 1) / 2.0);
   std::string nm = "mma_planes_M" + std::to_string(plan.M) + "_N" + std::to_string(plan.N) + "_K" + std::to_string(A.K) + "_b" + std::to_string(nitems);
   int tk = ctx_.begin(nm.c_str(), alg);
+  static long long* d_dbg = nullptr;
+  if (p.debug & 32) {
+    if (!d_dbg) CLR_CUDA(cudaMalloc(&d_dbg, 64));
+    p.dbg = d_dbg;
+  }
   mma_planes_kernel<<<(unsigned)grid, MMA_THREADS, smem, ctx_.stream>>>(tmA, tmB, p);
   ctx_.end(tk);
+  if (p.debug & 32) {
+    long long h[8];
+    CLR_CUDA(cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[mma dbg] %s grid=%lld stages=%d stack=%d BN=%d BK=%d: issuer cycles %lld, waiting for TMA %lld\n", nm.c_str(),
+            (long long)grid, p.stages, p.stack, p.BN, p.BK, h[0], h[1]);
+  }
 }
 
 template <int NL>
 static void carry_impl(Ctx& ctx, const CarryArgs& c) {
   constexpr int T = 4 * NL + GUARD_DIGITS;
   int64_t total = (int64_t)c.batch * c.M * c.N;
-  int grid = (int)std::min<int64_t>(ceil_div(total, 128), (int64_t)ctx.sm_count * 32);
+  int64_t threads = (int64_t)c.batch * ((c.M + 3) / 4) * ((c.N + 7) / 8) * 32;
+  int grid = (int)std::min<int64_t>(ceil_div(threads, 128), (int64_t)ctx.sm_count * 32);
   // algorithmic bytes: read T int32 planes (x nsplit), write (p/8+4)
   int tk = ctx.begin("carry", (double)total * (4.0 * T * c.nsplit + 4.0 * (NL + 1)));
-  carry_kernel<NL, T><<<grid, 128, 0, ctx.stream>>>(c);
+  if (c.stack == 1)
+    carry_kernel<NL, T, 1><<<grid, 128, 0, ctx.stream>>>(c);
+  else if (c.stack == 2)
+    carry_kernel<NL, T, 2><<<grid, 128, 0, ctx.stream>>>(c);
+  else
+    carry_kernel<NL, T, 4><<<grid, 128, 0, ctx.stream>>>(c);
   ctx.end(tk);
+}
+
+// K is cut into chunks for int32 exactness ((t+1) * Kc * 2^14 < 2^31  =>  T * Kc <= 131071) and, when there are fewer
+// output tiles than SMs, for parallelism (the chunks of one tile run on different SMs and are summed by the carry kernel)
+static void split_k(int sm_count, int T, int Kp, int BK, int64_t tiles, int& Kc, int& nsplit) {
+  int kc_safe = (131071 / T) / BK * BK;
+  Kc = std::min(Kp, kc_safe);
+  if (tiles < sm_count && Kp >= 512) {
+    int want = (int)std::min<int64_t>(ceil_div(sm_count, tiles), Kp / 256);
+    if (want > 1) Kc = std::min(Kc, ceil_div(ceil_div(Kp, want), BK) * BK);
+  }
+  nsplit = ceil_div(Kp, Kc);
 }
 
 void GemmEngine::multiply(const Slice& A, const Slice& B, const GemmPlan& plan, const OutDesc& C, int epi,
                           const mp::Tensor* extra) {
   if (A.Kp != B.Kp || A.S != S_ || B.S != S_) throw SolverError(-1, "gemm: operand mismatch");
   const int T = S_;
-  int BK = std::min(A.Kp, 128);
-  // int32 exactness: (t+1) * Kc * 2^14 < 2^31  =>  T * Kc <= 131071
-  int kc_safe = (131071 / T) / BK * BK;
-  int Kc = std::min(A.Kp, kc_safe);
-  int BN = std::min(256, ((plan.N + 15) / 16) * 16);
-  int64_t tiles = (int64_t)plan.batch * ceil_div(plan.M, 128) * ceil_div(plan.N, BN) * ((T + 1) / 2);
-  if (tiles < 2 * ctx_.sm_count && A.Kp >= 2048) Kc = std::min(Kc, 1024);  // split-K for parallelism
-  int nsplit = ceil_div(A.Kp, Kc);
-  // chunk the batch so that the plane workspace stays bounded
-  size_t per_item = (size_t)T * nsplit * plan.M * plan.N * sizeof(int32_t);
+  const int BK = std::min(A.Kp, bk_cap()), BN = bn_of(plan.N), stack = stack_of(plan.M);
+  const int m_tiles = ceil_div(plan.M, 128), Mpad = m_tiles * 128;
+  int64_t tiles = (int64_t)plan.batch * m_tiles * ceil_div(plan.N, BN);
+  int Kc, nsplit;
+  split_k(ctx_.sm_count, T, A.Kp, BK, tiles, Kc, nsplit);
+  // chunk the batch so that the block workspace stays bounded
+  size_t per_item = (size_t)T * nsplit * Mpad * (((size_t)plan.N + 3) / 4 * 4) * sizeof(int32_t);
   size_t cap = (size_t)1536 << 20;
   int chunk = (int)std::max<size_t>(1, std::min<size_t>(plan.batch, cap / std::max<size_t>(per_item, 1)));
   planes_.ensure(per_item * chunk);
@@ -593,6 +770,9 @@ void GemmEngine::multiply(const Slice& A, const Slice& B, const GemmPlan& plan, 
     CarryArgs c;
     memset(&c, 0, sizeof(c));
     c.planes = planes_.as<int32_t>();
+    c.stack = stack;
+    c.mip = 128 / stack;
+    c.Mpad = Mpad;
     c.expA = A.exps.as<int32_t>();
     c.expB = B.exps.as<int32_t>();
     c.rowA = plan.d_rowA;
@@ -624,14 +804,28 @@ void GemmEngine::multiply(const Slice& A, const Slice& B, const GemmPlan& plan, 
 
 void GemmEngine::planes_only(const Slice& A, const Slice& B, const GemmPlan& plan, int32_t* h_planes, int* T_out) {
   const int T = S_;
-  int BK = std::min(A.Kp, 128);
+  int BK = std::min(A.Kp, bk_cap());
   int kc_safe = (131071 / T) / BK * BK;
   if (A.Kp > kc_safe) throw SolverError(-1, "planes_only: K too large for a single split");
-  size_t bytes = (size_t)T * plan.batch * plan.M * plan.N * sizeof(int32_t);
+  const int stack = stack_of(plan.M), mip = 128 / stack, Mpad = ceil_div(plan.M, 128) * 128;
+  const int n4 = (plan.N + 3) / 4;
+  size_t bytes = (size_t)T * plan.batch * Mpad * n4 * 4 * sizeof(int32_t);
   planes_.ensure(bytes);
   run_mma(A, B, plan, 0, plan.batch, 1, A.Kp);
-  CLR_CUDA(cudaMemcpyAsync(h_planes, planes_.p, bytes, cudaMemcpyDeviceToHost, ctx_.stream));
+  std::vector<int32_t> blk(bytes / sizeof(int32_t));
+  CLR_CUDA(cudaMemcpyAsync(blk.data(), planes_.p, bytes, cudaMemcpyDeviceToHost, ctx_.stream));
   ctx_.sync();
+  // plane t = sum over the lane groups r of block t - r (exact integer sums)
+  const size_t bstride = (size_t)plan.batch * n4 * Mpad * 4;
+  for (int t = 0; t < T; t++)
+    for (int b = 0; b < plan.batch; b++)
+      for (int i = 0; i < plan.M; i++)
+        for (int j = 0; j < plan.N; j++) {
+          int32_t v = 0;
+          for (int r = 0; r < stack && r <= t; r++)
+            v += blk[(size_t)(t - r) * bstride + (((size_t)b * n4 + (j >> 2)) * Mpad + r * mip + i) * 4 + (j & 3)];
+          h_planes[(((size_t)t * plan.batch + b) * plan.M + i) * plan.N + j] = v;
+        }
   *T_out = T;
 }
 

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstring>
 #include <map>
+#include <thread>
 #include <tuple>
 
 namespace clr {
@@ -86,41 +87,95 @@ void Solver::allreduce(MpBuf& t, int64_t off, int64_t n, int op) {
 }
 
 // ---- wire <-> device -------------------------------------------------------------------------------
+// Wire format <-> planar HBM layout. The limb planes have the same order on both sides, so a transfer is one strided
+// DMA ((nl+1) rows of `count` words, cudaMemcpy2DAsync) through a pinned, grow-only staging buffer; the host side only
+// moves the limb planes into / out of the staging buffer and converts sign/exp <-> header word, split over a few
+// threads (this copy sits inside the timed region of the end-to-end path: upload_point / download_point).
+namespace {
+struct PinnedStage {
+  uint32_t* p = nullptr;
+  size_t words = 0;
+  ~PinnedStage() {
+    if (p) cudaFreeHost(p);
+  }
+  uint32_t* ensure(size_t w) {
+    if (w > words) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      CLR_CUDA(cudaHostAlloc((void**)&p, w * sizeof(uint32_t), cudaHostAllocDefault));
+      words = w;
+    }
+    return p;
+  }
+};
+PinnedStage& stage_buf() {
+  static thread_local PinnedStage s;
+  return s;
+}
+template <class F>
+void parallel_ranges(int64_t count, F&& f) {
+  int nt = 1;
+  if (count >= (1 << 16)) nt = (int)std::min<int64_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+  if (nt <= 1) {
+    f((int64_t)0, count);
+    return;
+  }
+  std::vector<std::thread> th;
+  int64_t per = (count + nt - 1) / nt;
+  for (int t = 0; t < nt; t++) {
+    int64_t lo = t * per, hi = std::min(count, lo + per);
+    if (lo < hi) th.emplace_back([=, &f] { f(lo, hi); });
+  }
+  for (auto& t : th) t.join();
+}
+}  // namespace
+
 void Solver::to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpBuf& dst, int64_t dst_off) {
   if (count <= 0) return;
-  std::vector<uint32_t> stage((size_t)(nl + 1) * count);
-  for (int k = 0; k < nl; k++)
-    memcpy(&stage[(size_t)k * count], src->limb + (size_t)k * src->n + src_off, (size_t)count * 4);
-  uint32_t* hdr = &stage[(size_t)nl * count];
-  for (int64_t i = 0; i < count; i++) {
-    int8_t s = src->sign[src_off + i];
-    if (s == 0) {
-      hdr[i] = mp::pack_hdr(mp::EXP_ZERO, 0);
-      for (int k = 0; k < nl; k++) stage[(size_t)k * count + i] = 0;
-    } else {
-      hdr[i] = mp::pack_hdr((int32_t)src->exp[src_off + i], s < 0 ? 1u : 0u);
+  uint32_t* stage = stage_buf().ensure((size_t)(nl + 1) * count);
+  const int nlv = nl;
+  parallel_ranges(count, [&](int64_t lo, int64_t hi) {
+    for (int k = 0; k < nlv; k++)
+      memcpy(stage + (size_t)k * count + lo, src->limb + (size_t)k * src->n + src_off + lo, (size_t)(hi - lo) * 4);
+    uint32_t* hdr = stage + (size_t)nlv * count;
+    for (int64_t i = lo; i < hi; i++) {
+      int8_t sg = src->sign[src_off + i];
+      if (sg == 0) {
+        hdr[i] = mp::pack_hdr(mp::EXP_ZERO, 0);
+        for (int k = 0; k < nlv; k++) stage[(size_t)k * count + i] = 0;
+      } else {
+        hdr[i] = mp::pack_hdr((int32_t)src->exp[src_off + i], sg < 0 ? 1u : 0u);
+      }
     }
-  }
-  for (int k = 0; k <= nl; k++)
-    CLR_CUDA(cudaMemcpyAsync(dst.w() + (size_t)k * dst.n + dst_off, &stage[(size_t)k * count], (size_t)count * 4,
-                             cudaMemcpyHostToDevice, ctx.stream));
-  CLR_CUDA(cudaStreamSynchronize(ctx.stream));  // staging buffer goes out of scope
+  });
+  CLR_CUDA(cudaMemcpy2DAsync(dst.w() + dst_off, dst.n * sizeof(uint32_t), stage, (size_t)count * sizeof(uint32_t),
+                             (size_t)count * sizeof(uint32_t), (size_t)(nl + 1), cudaMemcpyHostToDevice, ctx.stream));
+  CLR_CUDA(cudaStreamSynchronize(ctx.stream));  // the staging buffer is reused by the next transfer
 }
 void Solver::to_host(const MpBuf& src, int64_t src_off, int64_t count, clrsdp_mp_out* dst, int64_t dst_off) {
   if (count <= 0) return;
-  std::vector<uint32_t> stage((size_t)(nl + 1) * count);
-  for (int k = 0; k <= nl; k++)
-    CLR_CUDA(cudaMemcpyAsync(&stage[(size_t)k * count], src.w() + (size_t)k * src.n + src_off, (size_t)count * 4,
-                             cudaMemcpyDeviceToHost, ctx.stream));
+  uint32_t* stage = stage_buf().ensure((size_t)(nl + 1) * count);
+  CLR_CUDA(cudaMemcpy2DAsync(stage, (size_t)count * sizeof(uint32_t), src.w() + src_off, src.n * sizeof(uint32_t),
+                             (size_t)count * sizeof(uint32_t), (size_t)(nl + 1), cudaMemcpyDeviceToHost, ctx.stream));
   CLR_CUDA(cudaStreamSynchronize(ctx.stream));
-  const uint32_t* hdr = &stage[(size_t)nl * count];
-  for (int64_t i = 0; i < count; i++) {
-    int32_t e = ((int32_t)hdr[i]) >> 1;
-    bool z = (e == mp::EXP_ZERO);
-    dst->sign[dst_off + i] = z ? 0 : ((hdr[i] & 1u) ? -1 : 1);
-    dst->exp[dst_off + i] = z ? 0 : e;
-    for (int k = 0; k < nl; k++) dst->limb[(size_t)k * dst->n + dst_off + i] = z ? 0u : stage[(size_t)k * count + i];
-  }
+  const int nlv = nl;
+  parallel_ranges(count, [&](int64_t lo, int64_t hi) {
+    const uint32_t* hdr = stage + (size_t)nlv * count;
+    bool any_zero = false;
+    for (int64_t i = lo; i < hi; i++) {
+      int32_t e = ((int32_t)hdr[i]) >> 1;
+      bool z = (e == mp::EXP_ZERO);
+      any_zero |= z;
+      dst->sign[dst_off + i] = z ? 0 : ((hdr[i] & 1u) ? -1 : 1);
+      dst->exp[dst_off + i] = z ? 0 : e;
+    }
+    for (int k = 0; k < nlv; k++)
+      memcpy(dst->limb + (size_t)k * dst->n + dst_off + lo, stage + (size_t)k * count + lo, (size_t)(hi - lo) * 4);
+    if (any_zero)
+      for (int64_t i = lo; i < hi; i++)
+        if ((((int32_t)hdr[i]) >> 1) == mp::EXP_ZERO)
+          for (int k = 0; k < nlv; k++) dst->limb[(size_t)k * dst->n + dst_off + i] = 0u;
+  });
 }
 
 // ---- structure ------------------------------------------------------------------------------------
