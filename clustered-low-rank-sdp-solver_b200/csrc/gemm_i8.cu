@@ -190,7 +190,8 @@ struct MmaParams {
   long long* dbg;
 };
 
-constexpr int MMA_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue (two sets)
+constexpr int EPI_SETS = 4;       // epilogue warp sets: block q is drained by set q % EPI_SETS
+constexpr int MMA_THREADS = 64 + 128 * EPI_SETS;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then the epilogue sets
 constexpr int MAX_STAGES = 8;
 constexpr int DG = 4;             // digits per operand group: one pipeline stage feeds a DG x DG square of digit pairs
 constexpr int ACC_SLOTS = 8;      // accumulator slots in TMEM (block q lives in slot q % ACC_SLOTS)
@@ -393,10 +394,11 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mma_issue<4>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks);
   } else {
     // ------------------------------ epilogue: TMEM -> registers -> HBM blocks --------------------
-    // Two sets of four warps (one warp per TMEM lane quarter) drain alternate blocks, so two drains are in flight;
+    // EPI_SETS sets of four warps (one warp per TMEM lane quarter) drain the blocks round-robin, so several drains
+    // (barrier wake-up, TMEM load, stores) are in flight;
     // all TMEM loads of a block are issued before the single wait.
     const int q4 = warp & 3;              // TMEM lane quarter this warp may access
-    const int eset = (warp - 2) >> 2;     // 0 / 1: handles the blocks with q % 2 == eset
+    const int eset = (warp - 2) >> 2;     // handles the blocks with q % EPI_SETS == eset
     const int lrow = q4 * 32 + lane;
     const int mip = 128 / stack;
     const int grp = lrow / mip;           // lane group: plane q + grp
@@ -406,7 +408,7 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int q_hi = min(T - 1, DG * D + qspan);
       const int q_lo = (D == 0) ? 0 : DG * D + qspan - (DG - 1);
       for (int q = q_hi; q >= q_lo; q--) {
-        if ((q & 1) != eset) continue;
+        if ((q % EPI_SETS) != eset) continue;
         const int slot = q & (ACC_SLOTS - 1);
         const uint32_t u = (uint32_t)(T - 1 - q) >> 3;
         mbar_wait(smem_u32(&bars[16 + slot]), u & 1u);

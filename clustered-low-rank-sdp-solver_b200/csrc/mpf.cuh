@@ -133,9 +133,21 @@ MP_HD void shl_bits(uint32_t (&x)[N], uint32_t r) {  // 0 <= r < 32
 #pragma unroll
   for (int i = N - 1; i >= 0; i--) x[i] = funnel_l((i > 0) ? x[(i > 0) ? i - 1 : 0] : 0u, x[i], r);
 }
+// On the device the limb loops are PTX carry chains (add.cc / addc.cc / sub.cc / subc.cc / mad.lo.cc / madc.hi.cc): one
+// instruction per limb instead of the compare-and-select sequences the compiler derives from 64-bit C arithmetic.
+// Every chain starts with an instruction that sets the carry flag without reading it, and nothing the compiler emits
+// between the (volatile) statements touches the flag.
 // x += y, returns carry out
 template <int N>
 MP_HD uint32_t add_n(uint32_t (&x)[N], const uint32_t (&y)[N]) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(x[0]) : "r"(y[0]));
+#pragma unroll
+  for (int i = 1; i < N; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+  uint32_t c;
+  asm volatile("addc.u32 %0, 0, 0;" : "=r"(c));
+  return c;
+#else
   uint32_t c = 0;
 #pragma unroll
   for (int i = 0; i < N; i++) {
@@ -144,10 +156,19 @@ MP_HD uint32_t add_n(uint32_t (&x)[N], const uint32_t (&y)[N]) {
     c = (uint32_t)(s >> 32);
   }
   return c;
+#endif
 }
-// x -= y (requires x >= y), returns borrow
+// x -= y, returns borrow (1 if x < y: the result is then the two's complement of y - x)
 template <int N>
 MP_HD uint32_t sub_n(uint32_t (&x)[N], const uint32_t (&y)[N]) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(x[0]) : "r"(y[0]));
+#pragma unroll
+  for (int i = 1; i < N; i++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+  uint32_t b;
+  asm volatile("subc.u32 %0, 0, 0;" : "=r"(b));  // 0 - 0 - borrow = 0 or 0xffffffff
+  return b & 1u;
+#else
   uint32_t b = 0;
 #pragma unroll
   for (int i = 0; i < N; i++) {
@@ -156,6 +177,44 @@ MP_HD uint32_t sub_n(uint32_t (&x)[N], const uint32_t (&y)[N]) {
     b = (uint32_t)(s >> 63);
   }
   return b;
+#endif
+}
+// x = -x (two's complement)
+template <int N>
+MP_HD void neg_n(uint32_t (&x)[N]) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("sub.cc.u32 %0, 0, %0;" : "+r"(x[0]));
+#pragma unroll
+  for (int i = 1; i < N; i++) asm volatile("subc.cc.u32 %0, 0, %0;" : "+r"(x[i]));
+#else
+  uint32_t c = 1;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint64_t s = (uint64_t)(~x[i]) + c;
+    x[i] = (uint32_t)s;
+    c = (uint32_t)(s >> 32);
+  }
+#endif
+}
+// x += c (c = 0 or 1), returns carry out
+template <int N>
+MP_HD uint32_t inc_n(uint32_t (&x)[N], uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(x[0]) : "r"(c));
+#pragma unroll
+  for (int i = 1; i < N; i++) asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(x[i]));
+  uint32_t co;
+  asm volatile("addc.u32 %0, 0, 0;" : "=r"(co));
+  return co;
+#else
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint64_t s = (uint64_t)x[i] + c;
+    x[i] = (uint32_t)s;
+    c = (uint32_t)(s >> 32);
+  }
+  return c;
+#endif
 }
 // compare magnitudes of two N-limb arrays: -1, 0, 1
 template <int N>
@@ -170,32 +229,30 @@ MP_HD int cmp_n(const uint32_t (&x)[N], const uint32_t (&y)[N]) {
 template <int N>
 MP_HD int normalize_n(uint32_t (&x)[N]) {
   uint32_t q = 0;
-  bool found = false;
+  if (x[N - 1] == 0) {  // rare (deep cancellation): whole-limb shift
+    bool found = false;
 #pragma unroll
-  for (int i = N - 1; i >= 0; i--) {
-    if (!found) {
-      if (x[i] == 0)
-        q++;
-      else
-        found = true;
+    for (int i = N - 1; i >= 0; i--) {
+      if (!found) {
+        if (x[i] == 0)
+          q++;
+        else
+          found = true;
+      }
     }
+    if (!found) return -1;
+    shl_limbs<N>(x, q);
   }
-  if (!found) return -1;
-  shl_limbs<N>(x, q);
   uint32_t r = (uint32_t)clz32(x[N - 1]);
-  shl_bits<N>(x, r);
+  if (r) shl_bits<N>(x, r);
   return (int)(32 * q + r);
 }
 // round an (NL+1)-limb normalised mantissa g|m (g = guard limb x[0]) to NL limbs; adjusts e on overflow
 template <int NL>
 MP_HD void round_guard(Num<NL>& out, const uint32_t (&x)[NL + 1], int32_t e, uint32_t negf) {
-  uint32_t c = x[0] >> 31;
 #pragma unroll
-  for (int i = 0; i < NL; i++) {
-    uint64_t s = (uint64_t)x[i + 1] + c;
-    out.m[i] = (uint32_t)s;
-    c = (uint32_t)(s >> 32);
-  }
+  for (int i = 0; i < NL; i++) out.m[i] = x[i + 1];
+  uint32_t c = inc_n<NL>(out.m, x[0] >> 31);
   if (c) {  // mantissa was all ones: becomes 1.000.. = 0.1 * 2
     out.m[NL - 1] = 0x80000000u;
     e += 1;
@@ -229,8 +286,8 @@ MP_HD Num<NL> add(const Num<NL>& a, const Num<NL>& b) {
     out.neg = nx;
     return out;
   }
-  shr_limbs<NL + 1>(Y, d >> 5);
-  shr_bits<NL + 1>(Y, d & 31u);
+  if (d >> 5) shr_limbs<NL + 1>(Y, d >> 5);
+  if (d & 31u) shr_bits<NL + 1>(Y, d & 31u);
   if (nx == ny) {
     uint32_t c = add_n<NL + 1>(X, Y);
     if (c) {
@@ -241,17 +298,11 @@ MP_HD Num<NL> add(const Num<NL>& a, const Num<NL>& b) {
     round_guard<NL>(out, X, ex, nx);
     return out;
   }
-  // opposite signs: subtract the smaller magnitude from the larger
-  if (d == 0 && cmp_n<NL + 1>(X, Y) < 0) {
-#pragma unroll
-    for (int i = 0; i <= NL; i++) {
-      uint32_t t = X[i];
-      X[i] = Y[i];
-      Y[i] = t;
-    }
+  // opposite signs: X - Y; a borrow (only possible when the exponents are equal) means |Y| > |X|: negate, flip the sign
+  if (sub_n<NL + 1>(X, Y)) {
+    neg_n<NL + 1>(X);
     nx = ny;
   }
-  sub_n<NL + 1>(X, Y);
   int sh = normalize_n<NL + 1>(X);
   if (sh < 0) return zero<NL>();
   round_guard<NL>(out, X, ex - sh, nx);
@@ -265,6 +316,30 @@ MP_HD Num<NL> sub(const Num<NL>& a, const Num<NL>& b) { return add(a, neg(b)); }
 template <int NL>
 MP_HD void mul_raw(const Num<NL>& a, const Num<NL>& b, uint32_t (&P)[NL + 2]) {
   constexpr int C0 = (NL >= 2) ? NL - 2 : 0;
+#if defined(__CUDA_ARCH__)
+  // column sums in a three-word accumulator t2:t1:t0; one product = mad.lo.cc + madc.hi.cc + addc
+  uint32_t t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+  for (int c = C0; c <= 2 * NL - 2; c++) {
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      const int j = c - i;
+      if (j >= 0 && j < NL)
+        asm volatile(
+            "mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32 %2, %2, 0;"
+            : "+r"(t0), "+r"(t1), "+r"(t2)
+            : "r"(a.m[i]), "r"(b.m[j]));
+    }
+    P[c - C0 + (NL >= 2 ? 0 : 1)] = t0;
+    t0 = t1;
+    t1 = t2;
+    t2 = 0;
+  }
+  P[NL + 1] = t0;
+  if (NL < 2) P[0] = 0;
+#else
   uint64_t lo = 0;
   uint32_t hi = 0;
 #pragma unroll
@@ -284,6 +359,7 @@ MP_HD void mul_raw(const Num<NL>& a, const Num<NL>& b, uint32_t (&P)[NL + 2]) {
   }
   P[NL + 1] = (uint32_t)lo;
   if (NL < 2) P[0] = 0;
+#endif
 }
 template <int NL>
 MP_HD Num<NL> mul(const Num<NL>& a, const Num<NL>& b) {
@@ -330,8 +406,8 @@ MP_HD Num<NL> mul_sub_mul(const Num<NL>& a, const Num<NL>& b, const Num<NL>& c, 
   }
   uint32_t dd = (uint32_t)(ex - ey);
   if (dd < 32u * (NL + 2)) {
-    shr_limbs<NL + 2>(Y, dd >> 5);
-    shr_bits<NL + 2>(Y, dd & 31u);
+    if (dd >> 5) shr_limbs<NL + 2>(Y, dd >> 5);
+    if (dd & 31u) shr_bits<NL + 2>(Y, dd & 31u);
     if (nx == ny) {
       uint32_t cy = add_n<NL + 2>(X, Y);
       if (cy) {
@@ -339,17 +415,9 @@ MP_HD Num<NL> mul_sub_mul(const Num<NL>& a, const Num<NL>& b, const Num<NL>& c, 
         X[NL + 1] |= 0x80000000u;
         ex += 1;
       }
-    } else {
-      if (cmp_n<NL + 2>(X, Y) < 0) {
-#pragma unroll
-        for (int i = 0; i < NL + 2; i++) {
-          uint32_t t = X[i];
-          X[i] = Y[i];
-          Y[i] = t;
-        }
-        nx = ny;
-      }
-      sub_n<NL + 2>(X, Y);
+    } else if (sub_n<NL + 2>(X, Y)) {  // |Y| > |X| (possible when the exponents are equal or X is not normalised)
+      neg_n<NL + 2>(X);
+      nx = ny;
     }
   }
   int sh = normalize_n<NL + 2>(X);

@@ -39,6 +39,10 @@ Solver::Solver(int prec_bits, int device) : nl(prec_bits / 32), prec(prec_bits) 
   ctx.sm_count = prop.multiProcessorCount;
   CLR_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
   gemm_.reset(new GemmEngine(ctx, nl));
+  gemm_side_.reset(new GemmEngine(ctx, nl));  // own block workspace: used by the branch that runs beside the main stream
+  CLR_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+  CLR_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  CLR_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
   scal.alloc(SL_COUNT, nl);
   work.alloc(4096, nl);
   d_flags.ensure(4 * sizeof(int));
@@ -49,6 +53,7 @@ Solver::Solver(int prec_bits, int device) : nl(prec_bits / 32), prec(prec_bits) 
   memset(h_scal, 0, sizeof(h_scal));
   memset(h_flags, 0, sizeof(h_flags));
   if (const char* g = getenv("CLRSDP_GRAPH")) use_graph_ = atoi(g) != 0;
+  if (const char* g = getenv("CLRSDP_SIDE")) use_side_ = atoi(g) != 0;
 }
 
 Solver::~Solver() {
@@ -57,7 +62,11 @@ Solver::~Solver() {
   if (comm_.comm) NcclApi::get().CommDestroy(comm_.comm);
   for (auto e : ev_) cudaEventDestroy(e);
   for (auto e : ctx.pool) cudaEventDestroy(e);
+  if (main_stream_) ctx.stream = main_stream_;
   if (ctx.stream) cudaStreamDestroy(ctx.stream);
+  if (side_stream_) cudaStreamDestroy(side_stream_);
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  if (ev_join_) cudaEventDestroy(ev_join_);
 }
 
 // ---- multi-GPU ------------------------------------------------------------------------------------------
@@ -579,8 +588,12 @@ static OutDesc out_sub(const MatBatch& m, int r0, int c0) {
 }
 
 void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv,
-                          int* d_stat, bool want_u) {
+                          int* d_stat, bool want_u, bool side) {
   const int n = A.n, batch = A.batch;
+  GemmEngine* gemm_ = side ? this->gemm_side_.get() : this->gemm_.get();
+  Slice& fs1_ = side ? this->fs1s_ : this->fs1_;
+  Slice& fs2_ = side ? this->fs2s_ : this->fs2_;
+  MpBuf& tscr = side ? this->tscr_side_ : this->tscr;
   const int PANEL = panel_width(nl);
   (void)Vw;
   if (n <= PANEL && !want_u) {
@@ -799,13 +812,18 @@ void Solver::decomposition() {
     allreduce(Q, 0, (int64_t)n_y * n_y, COMB_SUM);  // the cross-cluster reduction (sum(Q), :1494)
   }
   mark(-1 - CLRSDP_T_Q);
+  // The factorisation of Q is one n_y x n_y matrix: a latency chain of n_y/32 panels that occupies a handful of SMs.
+  // It runs on a side stream (with its own GEMM workspace) beside the residuals and the first half of the
+  // predictor, which do not need it; search_direction() joins before the Q^-1 solve.
+  fork_side();
   mark(CLRSDP_T_CHOL_Q);
   {
     MatBatch A{Q.t(), d_qoff.as<int64_t>(), 1, n_y}, U{Uq.t(), d_qoff.as<int64_t>(), 1, n_y};
     MatBatch V{Vq.t(), d_qoff.as<int64_t>(), 1, n_y}, Li{Linvq.t(), d_qoff.as<int64_t>(), 1, n_y};
-    chol_inverse(A, U, V, Li, d_status.as<int>() + 2 * (int)blocks_.size() + J);
+    chol_inverse(A, U, V, Li, d_status.as<int>() + 2 * (int)blocks_.size() + J, false, true);
   }
   mark(-1 - CLRSDP_T_CHOL_Q);
+  end_side();
 }
 
 // compute_search_direction (MPMP.jl:1682-1824)
@@ -844,6 +862,7 @@ void Solver::search_direction() {
     allreduce(tmpy, 0, n_y, COMB_SUM);  // sum(temp_y), :1761
     ew_lincomb(ctx, nl, dyr.t(), 0, p.t(), 0, 1, tmpy.t(), 0, -1, n_y);  // p - sum_j B^T U^-1 t_j (:1761)
     // dy = Q^-1 dyr = Lq^-T (Lq^-1 dyr)
+    join_side();  // the factor of Q comes from the side stream
     GemvArgs q1;
     q1.A = Linvq.t(), q1.x = dyr.t(), q1.out = zvec.t();
     q1.rs = n_y, q1.ks = 1, q1.rows = n_y, q1.K = n_y;
@@ -903,6 +922,26 @@ void Solver::step_lengths() {
   reduce_min(ctx, nl, lam.t(), 0, (int64_t)blocks_.size(), scal.t(), SL_LAM_X, work.t());
   reduce_min(ctx, nl, lam.t(), (int64_t)blocks_.size(), (int64_t)blocks_.size(), scal.t(), SL_LAM_Y, work.t());
   allreduce(scal, SL_LAM_X, 2, COMB_MIN);  // global minimum over all ranks (:1890-1891); LAM_X, LAM_Y adjacent
+}
+
+// ---- side stream: fork after the current point of the main stream, join before the first consumer ------
+void Solver::fork_side() {
+  if (!use_side_) return;
+  CLR_CUDA(cudaEventRecord(ev_fork_, ctx.stream));
+  CLR_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
+  main_stream_ = ctx.stream;
+  ctx.stream = side_stream_;
+}
+void Solver::end_side() {
+  if (!use_side_) return;
+  CLR_CUDA(cudaEventRecord(ev_join_, ctx.stream));
+  ctx.stream = main_stream_;
+  join_pending_ = true;
+}
+void Solver::join_side() {
+  if (!join_pending_) return;
+  CLR_CUDA(cudaStreamWaitEvent(ctx.stream, ev_join_, 0));
+  join_pending_ = false;
 }
 
 // ---- timing marks: bucket >= 0 begins a bucket, -1-bucket ends it -----------------------------------
@@ -1078,6 +1117,8 @@ int Solver::iterate(clrsdp_iter_info* info) {
   if (!prepared) return CLRSDP_ERR_STATE;
   CLR_CUDA(cudaSetDevice(ctx.device));
   double t0 = now_s();
+  if (main_stream_) ctx.stream = main_stream_;  // a failed iteration may have left the side stream selected
+  join_pending_ = false;
   ev_marks_.clear();
   CLR_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int) * n_status, ctx.stream));
   mark(CLRSDP_T_COUNT);  // whole iteration (extra bucket, reported as `seconds`)

@@ -97,7 +97,11 @@ class Solver {
   // Linv = (chol A)^-1 for a batch of SPD matrices: blocked right-looking Cholesky, panels on the CUDA cores,
   // trailing updates and the off-diagonal inverse panels through the sliced tensor-core GEMM
   void chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv, int* d_status,
-                    bool want_u = false);
+                    bool want_u = false, bool side = false);
+  // a second stream for work that is off the critical path (see decomposition())
+  void fork_side();
+  void end_side();
+  void join_side();
   int check_status();
   int check_status_local();
   void upload_ntot();
@@ -107,7 +111,12 @@ class Solver {
   void iteration_body();
   void drop_graph();
 
-  std::unique_ptr<GemmEngine> gemm_;
+  std::unique_ptr<GemmEngine> gemm_, gemm_side_;
+  cudaStream_t side_stream_ = nullptr, main_stream_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+  bool use_side_ = true, join_pending_ = false;
+  Slice fs1s_, fs2s_;
+  MpBuf tscr_side_;
   Comm comm_;
   int ntot_local = 0;
   // structure

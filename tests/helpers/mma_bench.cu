@@ -31,15 +31,16 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 
 // pattern: 0 = all MMAs into one accumulator, 1 = round-robin over 512/N accumulators
 template <int KIND>
-__global__ void __launch_bounds__(128, 1) bench(int N, int iters, int pattern, int layout_bk, long long* out) {
+__global__ void __launch_bounds__(128, 1) bench(int N, int iters, int pattern, int layout_bk, long long* out, int commit_every = 0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x01010101u * (i & 1);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar2)), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -62,7 +63,11 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int pattern, i
     long long t0 = clock64();
     int slot = 0;
     for (int i = 0; i < iters; i++) {
-      if (elect_one()) mma<KIND>(tmem_base + slot * N, adesc, bdesc, idesc, 1u);
+      if (elect_one()) {
+        mma<KIND>(tmem_base + slot * N, adesc, bdesc, idesc, 1u);
+        if (commit_every && (i % commit_every) == commit_every - 1)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+      }
       __syncwarp();
       if (++slot == nslots) slot = 0;
     }
@@ -103,6 +108,13 @@ void run(const char* name, int kbytes) {
         printf("%-7s swz%-3d N=%-3d %-11s issue %.1f cyc/mma, complete %.1f cyc/mma -> %.0f MAC/clk/SM (%s)\n", name, bk, N,
                pattern ? "round-robin" : "one-acc", (double)h[0] / iters, cyc, 128.0 * N * kbytes / cyc, cudaGetErrorString(e));
       }
+  for (int ce : {1, 4, 16}) {
+    bench<KIND><<<1, 128, 80 * 1024>>>(64, 2000, 1, 64, d, ce);
+    cudaDeviceSynchronize();
+    long long h2[2];
+    cudaMemcpy(h2, d, 16, cudaMemcpyDeviceToHost);
+    printf("%-7s N=64 round-robin, tcgen05.commit every %d MMAs: issue %.1f cyc/mma, complete %.1f cyc/mma\n", name, ce, (double)h2[0] / 2000, (double)h2[1] / 2000);
+  }
   // all SMs busy: does the rate hold chip-wide?
   bench<KIND><<<148, 128, 80 * 1024>>>(256, 2000, 0, 128, d);
   cudaDeviceSynchronize();
@@ -114,7 +126,6 @@ void run(const char* name, int kbytes) {
 
 int main() {
   run<0>("i8", 32);
-  run<1>("f8f6f4", 32);
-  run<2>("f16", 16);
+
   return 0;
 }
