@@ -5,6 +5,7 @@
 #include "comm.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 namespace clr {
 using mp::Num;
@@ -218,10 +219,10 @@ __device__ __forceinline__ void panel_elim(uint32_t* Us, uint32_t* Gs, int w, in
   Num<NL> gam = mp::mul_2exp(smem_get<NL>(Us, pk_u(w, k, r)), -ek);
   if (qp <= k) {
     int at = pk_g(r, qp);
-    smem_put<NL>(Gs, at, nmsm(mu, smem_get<NL>(Gs, at), gam, smem_get<NL>(Gs, pk_g(k, qp))));
+    smem_put<NL>(Gs, at, mp::mul_sub_mul(mu, smem_get<NL>(Gs, at), gam, smem_get<NL>(Gs, pk_g(k, qp))));
   } else {
     int q = qp + (r - k - 1), at = pk_u(w, r, q);
-    smem_put<NL>(Us, at, nmsm(mu, smem_get<NL>(Us, at), gam, smem_get<NL>(Us, pk_u(w, k, q))));
+    smem_put<NL>(Us, at, mp::mul_sub_mul(mu, smem_get<NL>(Us, at), gam, smem_get<NL>(Us, pk_u(w, k, q))));
   }
 }
 template <int NL>
@@ -1354,7 +1355,7 @@ __global__ void gemv_kernel(GemvDev g) {
   int k0 = part * chunk, k1 = min(K, k0 + chunk);
   Num<NL> acc = mp::zero<NL>();
   for (int k = k0 + lane; k < k1; k += 32)
-    acc = nadd(acc, nmul(ldm<NL>(g.A, ab + (int64_t)rl * rs + (int64_t)k * ks), ldm<NL>(g.x, xb + k)));
+    acc = mp::add(acc, mp::mul(ldm<NL>(g.A, ab + (int64_t)rl * rs + (int64_t)k * ks), ldm<NL>(g.x, xb + k)));
 #pragma unroll 1
   for (int o = 16; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
   if (lane == 0) {
@@ -1393,6 +1394,105 @@ void gemv(Ctx& ctx, int nl, const GemvArgs& a, mp::Tensor work) {
       gemv_sum_kernel<NL><<<ceil_div(a.rows, 128), 128, 0, ctx.stream>>>(g);
       ctx.end(tk);
     }
+  });
+}
+
+// =========================================================================================================
+// small batched products on the CUDA cores
+// =========================================================================================================
+// C[b][i][j] (epi) sum_k A(b,i,k) * B(b,j,k) for products too small to amortise the tensor-core pipeline (slice,
+// 45 pipeline stages per tile, carry: ~90 us of latency whatever the size). KS adjacent lanes share one output
+// entry (K split KS ways, shuffle reduction); plain multiprecision multiply-add, the oracle's own error model.
+struct SmallGemmDev {
+  mp::Tensor A, B, C, E;
+  const int64_t* offA;
+  const int64_t* offB;
+  const int64_t* offC;
+  int64_t a0, abs_, ars, aks, b0, bbs, brs, bks, c0, cbs, crs, ccs;
+  int batch, M, N, K, ks_log, epi;
+};
+template <int NL>
+__global__ void __launch_bounds__(256) small_gemm_kernel(SmallGemmDev g) {
+  const int KS = 1 << g.ks_log;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t out = gid >> g.ks_log;
+  const int part = (int)(gid & (KS - 1));
+  const int64_t total = (int64_t)g.batch * g.M * g.N;
+  const bool live = out < total;
+  Num<NL> acc = mp::zero<NL>();
+  int b = 0, i = 0, j = 0;
+  if (live) {
+    j = (int)(out % g.N);
+    i = (int)((out / g.N) % g.M);
+    b = (int)(out / ((int64_t)g.N * g.M));
+    const int64_t ab = g.a0 + (g.offA ? g.offA[b] : (int64_t)b * g.abs_) + (int64_t)i * g.ars;
+    const int64_t bb = g.b0 + (g.offB ? g.offB[b] : (int64_t)b * g.bbs) + (int64_t)j * g.brs;
+    for (int k = part; k < g.K; k += KS)
+      acc = mp::add(acc, mp::mul(ldm<NL>(g.A, ab + (int64_t)k * g.aks), ldm<NL>(g.B, bb + (int64_t)k * g.bks)));
+  }
+#pragma unroll 1
+  for (int o = KS >> 1; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
+  if (live && part == 0) {
+    const int64_t at = g.c0 + (g.offC ? g.offC[b] : (int64_t)b * g.cbs) + (int64_t)i * g.crs + (int64_t)j * g.ccs;
+    if (g.epi == 4) {  // EPI_NEG
+      acc = mp::neg(acc);
+    } else if (g.epi != 0) {
+      Num<NL> e = ldm<NL>(g.E, at);
+      if (g.epi == 1)  // EPI_SUB_FROM: E - A*B
+        acc = nsub(e, acc);
+      else if (g.epi == 2)  // EPI_MINUS_SUB: A*B - E
+        acc = nsub(acc, e);
+      else
+        acc = nadd(acc, e);
+    }
+    stm<NL>(g.C, at, acc);
+  }
+}
+// C(b,i,j) = S(b,i,j) for rectangular strided blocks (C addressing as in SmallGemmArgs; S through the a* fields)
+template <int NL>
+__global__ void rect_copy_kernel(SmallGemmDev g) {
+  const int64_t total = (int64_t)g.batch * g.M * g.N;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % g.N), i = (int)((idx / g.N) % g.M), b = (int)(idx / ((int64_t)g.N * g.M));
+    const int64_t from = g.a0 + (g.offA ? g.offA[b] : (int64_t)b * g.abs_) + (int64_t)i * g.ars + (int64_t)j * g.aks;
+    const int64_t to = g.c0 + (g.offC ? g.offC[b] : (int64_t)b * g.cbs) + (int64_t)i * g.crs + (int64_t)j * g.ccs;
+    stm<NL>(g.C, to, ldm<NL>(g.A, from));
+  }
+}
+void rect_copy(Ctx& ctx, int nl, const SmallGemmArgs& a) {
+  SmallGemmDev g;
+  memset(&g, 0, sizeof(g));
+  g.A = a.A, g.C = a.C;
+  g.offA = a.offA, g.offC = a.offC;
+  g.a0 = a.a0, g.abs_ = a.abs_, g.ars = a.ars, g.aks = a.aks;
+  g.c0 = a.c0, g.cbs = a.cbs, g.crs = a.crs, g.ccs = a.ccs;
+  g.batch = a.batch, g.M = a.M, g.N = a.N;
+  const int64_t total = (int64_t)a.batch * a.M * a.N;
+  if (total <= 0) return;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("rect_copy", (double)total * 8.0 * (NL + 1));
+    rect_copy_kernel<NL><<<(int)std::min<int64_t>(ceil_div(total, 128), (int64_t)ctx.sm_count * 16), 128, 0, ctx.stream>>>(g);
+    ctx.end(tk);
+  });
+}
+void small_gemm(Ctx& ctx, int nl, const SmallGemmArgs& a) {
+  SmallGemmDev g;
+  g.A = a.A, g.B = a.B, g.C = a.C, g.E = a.E.w ? a.E : a.C;
+  g.offA = a.offA, g.offB = a.offB, g.offC = a.offC;
+  g.a0 = a.a0, g.abs_ = a.abs_, g.ars = a.ars, g.aks = a.aks;
+  g.b0 = a.b0, g.bbs = a.bbs, g.brs = a.brs, g.bks = a.bks;
+  g.c0 = a.c0, g.cbs = a.cbs, g.crs = a.crs, g.ccs = a.ccs;
+  g.batch = a.batch, g.M = a.M, g.N = a.N, g.K = a.K, g.epi = a.epi;
+  const int64_t outs = (int64_t)a.batch * a.M * a.N;
+  if (outs <= 0) return;
+  // split K over adjacent lanes until the grid fills the machine (about 4 x 256 threads per SM)
+  int ks_log = 0;
+  while (ks_log < 5 && (2 << ks_log) <= a.K && (outs << ks_log) < (int64_t)ctx.sm_count * 1024) ks_log++;
+  g.ks_log = ks_log;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("small_gemm", (double)outs * a.K);
+    small_gemm_kernel<NL><<<ceil_div(outs << ks_log, 256), 256, 0, ctx.stream>>>(g);
+    ctx.end(tk);
   });
 }
 

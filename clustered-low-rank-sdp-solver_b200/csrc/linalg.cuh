@@ -96,6 +96,22 @@ struct GemvArgs {
 void gemv(Ctx& ctx, int nl, const GemvArgs& g, mp::Tensor work);
 size_t gemv_work_elems(int rows, int K);
 
+// ---- small batched products on the CUDA cores ---------------------------------------------------------------
+// C(b,i,j) = epi( sum_k A(b,i,k) * B(b,j,k) ): element (b,r,k) of an operand at off(b) + r*rs + k*ks with
+// off(b) = x0 + (offX ? offX[b] : b*xbs); C element (b,i,j) at off(b) + i*crs + j*ccs; epi as in gemm_i8.cuh.
+// For products whose size does not amortise the latency of the sliced tensor-core pipeline.
+struct SmallGemmArgs {
+  mp::Tensor A, B, C, E;  // E = extra operand of the epilogue (C's addressing); E.w == nullptr -> C itself
+  const int64_t* offA = nullptr;
+  const int64_t* offB = nullptr;
+  const int64_t* offC = nullptr;
+  int64_t a0 = 0, abs_ = 0, ars = 0, aks = 1, b0 = 0, bbs = 0, brs = 0, bks = 1, c0 = 0, cbs = 0, crs = 0, ccs = 1;
+  int batch = 1, M = 0, N = 0, K = 0, epi = 0;
+};
+void small_gemm(Ctx& ctx, int nl, const SmallGemmArgs& a);
+// C(b,i,j) = A(b,i,j): strided rectangular copy (A element (b,i,j) at offA(b) + i*ars + j*aks)
+void rect_copy(Ctx& ctx, int nl, const SmallGemmArgs& a);
+
 // ---- structure-aware kernels ------------------------------------------------------------------------------
 // device tables describing the clustered structure (BlockInfo, MPMP.jl:467-479)
 struct StructTables {

@@ -587,6 +587,30 @@ static OutDesc out_sub(const MatBatch& m, int r0, int c0) {
   return o;
 }
 
+// One product of the blocked factorisation: C = epi(A * B^T-operand form). Products below ~1.5 M multiprecision
+// multiply-adds go to the CUDA-core kernel (one launch, a few microseconds), the others through slice / tensor cores
+// / carry.
+static constexpr int64_t SMALL_GEMM_PMAC = 1500000;
+void Solver::product(GemmEngine* ge, Slice& sa, Slice& sb, const OperandDesc& a, const OperandDesc& b, int M, int N,
+                     const OutDesc& c, int epi, const mp::Tensor* extra) {
+  const int64_t pmac = (int64_t)a.batch * M * N * a.K;
+  if (pmac <= SMALL_GEMM_PMAC) {
+    SmallGemmArgs g;
+    g.A = a.src, g.B = b.src, g.C = c.dst;
+    if (extra) g.E = *extra;
+    g.offA = a.d_off, g.offB = b.d_off, g.offC = c.d_off;
+    g.a0 = a.off0, g.abs_ = a.bstride, g.ars = a.rs, g.aks = a.ks;
+    g.b0 = b.off0, g.bbs = b.bstride, g.brs = b.rs, g.bks = b.ks;
+    g.c0 = c.off0, g.cbs = c.bstride, g.crs = c.rs, g.ccs = c.cs;
+    g.batch = a.batch, g.M = M, g.N = N, g.K = a.K, g.epi = epi;
+    small_gemm(ctx, nl, g);
+    return;
+  }
+  ge->slice(a, sa);
+  if (&sa != &sb) ge->slice(b, sb);
+  ge->multiply(sa, sb, plan_of(a.batch, M, N), c, epi, extra);
+}
+
 void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv,
                           int* d_stat, bool want_u, bool side) {
   const int n = A.n, batch = A.batch;
@@ -606,35 +630,44 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
     return;
   }
   mat_zero(ctx, nl, Linv);
+  tscr.alloc(std::max<size_t>(tscr.n, (size_t)batch * PANEL * n), nl);
   for (int k0 = 0; k0 < n; k0 += PANEL) {
     const int wk = std::min(PANEL, n - k0), n2 = n - k0 - wk;
     panel_factor(ctx, nl, Uw.sub(k0, k0, wk), Linv.sub(k0, k0, wk), want_u, d_stat);
     if (n2 > 0) {
-      // U12 = L11^-1 A12
-      gemm_->slice(op_rows(Linv, k0, k0, wk, wk), fs1_);
-      gemm_->slice(op_cols(Uw, k0, k0 + wk, n2, wk), fs2_);
-      gemm_->multiply(fs1_, fs2_, plan_of(batch, wk, n2), out_sub(Uw, k0, k0 + wk));
+      // U12 = L11^-1 A12 (overwrites A12). The CUDA-core kernel reads its operands while other threads store, so
+      // there the product goes to scratch first; the tensor path slices its operands before it writes.
+      if ((int64_t)batch * wk * n2 * wk <= SMALL_GEMM_PMAC) {
+        OutDesc os;
+        os.dst = tscr.t(), os.bstride = (int64_t)PANEL * n, os.rs = n2, os.cs = 1;
+        product(gemm_, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), op_cols(Uw, k0, k0 + wk, n2, wk), wk, n2, os, EPI_STORE,
+                nullptr);
+        SmallGemmArgs cp;
+        cp.A = tscr.t(), cp.abs_ = (int64_t)PANEL * n, cp.ars = n2, cp.aks = 1;
+        OutDesc od = out_sub(Uw, k0, k0 + wk);
+        cp.C = od.dst, cp.offC = od.d_off, cp.c0 = od.off0, cp.crs = od.rs, cp.ccs = od.cs;
+        cp.batch = batch, cp.M = wk, cp.N = n2;
+        rect_copy(ctx, nl, cp);
+      } else {
+        product(gemm_, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), op_cols(Uw, k0, k0 + wk, n2, wk), wk, n2,
+                out_sub(Uw, k0, k0 + wk), EPI_STORE, nullptr);
+      }
       // A22 -= U12^T U12
-      gemm_->slice(op_cols(Uw, k0, k0 + wk, n2, wk), fs2_);
       mp::Tensor ut = Uw.t;
-      gemm_->multiply(fs2_, fs2_, plan_of(batch, n2, n2), out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
+      OperandDesc u12 = op_cols(Uw, k0, k0 + wk, n2, wk);
+      product(gemm_, fs2_, fs2_, u12, u12, n2, n2, out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
     }
   }
   // off-diagonal panels of L^-1:  Linv[p, 0:k0] = -Linv_pp * ( L[p, 0:k0] * Linv[0:k0, 0:k0] )
-  tscr.alloc(std::max<size_t>(tscr.n, (size_t)batch * PANEL * n), nl);
   for (int k0 = PANEL; k0 < n; k0 += PANEL) {
     const int wk = std::min(PANEL, n - k0);
     // T[i][c] = sum_r U[r][k0+i] * Linv[r][c], stored transposed: Tt[c][i]
-    gemm_->slice(op_cols(Uw, 0, k0, wk, k0), fs1_);
-    gemm_->slice(op_cols(Linv, 0, 0, k0, k0), fs2_);
     OutDesc ot;
     ot.dst = tscr.t(), ot.bstride = (int64_t)PANEL * n, ot.rs = 1, ot.cs = wk;
-    gemm_->multiply(fs1_, fs2_, plan_of(batch, wk, k0), ot);
-    gemm_->slice(op_rows(Linv, k0, k0, wk, wk), fs1_);
+    product(gemm_, fs1_, fs2_, op_cols(Uw, 0, k0, wk, k0), op_cols(Linv, 0, 0, k0, k0), wk, k0, ot, EPI_STORE, nullptr);
     OperandDesc tb;
     tb.src = tscr.t(), tb.batch = batch, tb.bstride = (int64_t)PANEL * n, tb.rs = wk, tb.ks = 1, tb.rows = k0, tb.K = wk;
-    gemm_->slice(tb, fs2_);
-    gemm_->multiply(fs1_, fs2_, plan_of(batch, wk, k0), out_sub(Linv, k0, 0), EPI_NEG);
+    product(gemm_, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), tb, wk, k0, out_sub(Linv, k0, 0), EPI_NEG, nullptr);
   }
 }
 

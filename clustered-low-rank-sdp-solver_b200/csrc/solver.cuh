@@ -98,6 +98,8 @@ class Solver {
   // trailing updates and the off-diagonal inverse panels through the sliced tensor-core GEMM
   void chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv, int* d_status,
                     bool want_u = false, bool side = false);
+  void product(GemmEngine* ge, Slice& sa, Slice& sb, const OperandDesc& a, const OperandDesc& b, int M, int N,
+               const OutDesc& c, int epi, const mp::Tensor* extra);
   // a second stream for work that is off the critical path (see decomposition())
   void fork_side();
   void end_side();
