@@ -14,6 +14,7 @@ SOURCES = ["gemm_i8.cu", "linalg.cu", "solver.cu", "capi.cu"]
 HEADERS = ["mpf.cuh", "common.cuh", "gemm_i8.cuh", "linalg.cuh", "solver.cuh", "comm.cuh", os.path.join("..", "..", "include", "clrsdp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+FLAGS += os.environ.get("CLRSDP_EXTRA_NVCC_FLAGS", "").split()
 LIB = os.path.join(CSRC, "libclrsdp.so")
 
 

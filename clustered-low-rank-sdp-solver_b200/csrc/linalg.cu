@@ -599,6 +599,14 @@ lambda_min_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, mp::Ten
 // FP64 factorisation breaks down, is flagged and handled by lambda_min_kernel (flags[b] = 1).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LMX_THREADS = 256;
+// -DCLRSDP_LMX_TIMING: per-phase clock64 deltas of block 0 (measuring aid)
+#ifdef CLRSDP_LMX_TIMING
+#define LMX_T(i) lmx_t[i] = clock64()
+#define LMX_COUNT_ITER lmx_iters++
+#else
+#define LMX_T(i)
+#define LMX_COUNT_ITER
+#endif
 constexpr int LMX_NT = 5;  // vector slots per lane of warp 0: n <= 160
 constexpr int LMX_MAX_ITERS = 64;
 
@@ -666,12 +674,16 @@ lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, m
   uint32_t* vsm = reinterpret_cast<uint32_t*>(sc + 16);        // mp vector v
   uint32_t* psm = vsm + (size_t)n * (NL + 2);                  // mp partial sums [LMX_THREADS]
   uint32_t* red = psm + (size_t)LMX_THREADS * (NL + 2);        // block_reduce scratch [33]
-  __shared__ int s_int[8];
+  __shared__ int s_int[LMX_THREADS / 32 + 2];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t ow = offW[b];
   const int64_t out_at = out_index ? out_index[b] : b;
   const uint32_t* hdr = W.w + (size_t)NL * W.n;
 
+#ifdef CLRSDP_LMX_TIMING
+  long long lmx_t[6] = {0, 0, 0, 0, 0, 0};
+  int lmx_iters = 0;
+#endif
   if (n == 1) {
     if (tid == 0) {
       stm<NL>(out, out_at, ldm<NL>(W, ow));
@@ -721,6 +733,7 @@ lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, m
   }
   __syncthreads();
 
+  LMX_T(0);
   // ---- 1. Householder tridiagonalisation in FP64 (full symmetric storage) ----
   const int R = ((n + 31) / 32) * 32;
   const int parts = LMX_THREADS / R > 0 ? LMX_THREADS / R : 1;
@@ -800,6 +813,7 @@ lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, m
     eT[n - 1] = 0.0;
   }
   __syncthreads();
+  LMX_T(1);
   // ---- Gershgorin bounds of T ----
   if (warp == 0) {
     double lo = 1e300, hi = -1e300;
@@ -849,6 +863,7 @@ lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, m
   const double lam0 = sc[4];
   const double sigma = lam0 - nrm * 0x1p-36;
   __syncthreads();
+  LMX_T(2);
   // ---- 2. Cholesky of Wd - sigma I (factor kept in both triangles) ----
   load_fp64();
   __syncthreads();
@@ -896,6 +911,7 @@ lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, m
     if (tid == 0) flags[b] = 1;
     return;
   }
+  LMX_T(3);
   // ---- FP64 inverse iteration (warp 0) ----
   if (warp == 0) {
     double x[LMX_NT];
@@ -928,6 +944,7 @@ lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, m
     }
   }
   __syncthreads();
+  LMX_T(4);
   // ---- 3. multiprecision refinement ----
   // exponent of |W| as an mp quantity: nrm * 2^emax
   int nrm_e;
@@ -936,14 +953,16 @@ lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, m
   const int target = nrm_e - (32 * NL - 12);
   int prev_rexp = 1 << 30, stalls = 0;
   bool done = false, failed = false;
-  Num<NL> rho = mp::zero<NL>();
+  Num<NL> svv = mp::zero<NL>(), svw = mp::zero<NL>();
+  const int nwv = (n + 31) >> 5;
   for (int iter = 0; iter < LMX_MAX_ITERS; iter++) {
+    LMX_COUNT_ITER;
     // w = W v (W symmetric: column `row` is read as row-major W[j][row], coalesced over the threads)
     {
       Num<NL> acc = mp::zero<NL>();
       if (row < n && prt < parts)
         for (int j = prt; j < n; j += parts)
-          acc = nadd(acc, nmul(ldm<NL>(W, ow + (int64_t)j * n + row), smem_get<NL>(vsm, j)));
+          acc = mp::add(acc, mp::mul(ldm<NL>(W, ow + (int64_t)j * n + row), smem_get<NL>(vsm, j)));
       smem_put<NL>(psm, tid, acc);
     }
     __syncthreads();
@@ -952,15 +971,40 @@ lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, m
       for (int q = 0; q < parts; q++) wi = nadd(wi, smem_get<NL>(psm, q * R + tid));
       vi = smem_get<NL>(vsm, tid);
     }
-    Num<NL> svv = block_reduce<NL, RED_ADD>(tid < n ? nmul(vi, vi) : mp::zero<NL>(), red);
-    Num<NL> svw = block_reduce<NL, RED_ADD>(tid < n ? nmul(vi, wi) : mp::zero<NL>(), red);
+    // v'v and v'w: only the first ceil(n/32) warps hold entries; both sums go through the shuffles together
+    {
+      Num<NL> sa = mp::zero<NL>(), sb = mp::zero<NL>();
+      if (tid < n) {
+        sa = nmul(vi, vi);
+        sb = nmul(vi, wi);
+      }
+      if (warp < nwv) {
+#pragma unroll 1
+        for (int o = 16; o; o >>= 1) {
+          Num<NL> ta = shfl_xor_num(sa, o), tb = shfl_xor_num(sb, o);
+          sa = nadd(sa, ta);
+          sb = nadd(sb, tb);
+        }
+        if (lane == 0) {
+          smem_put<NL>(red, 2 * warp, sa);
+          smem_put<NL>(red, 2 * warp + 1, sb);
+        }
+      }
+    }
+    __syncthreads();
+    svv = smem_get<NL>(red, 0);
+    svw = smem_get<NL>(red, 1);
+    for (int q = 1; q < nwv; q++) {
+      svv = nadd(svv, smem_get<NL>(red, 2 * q));
+      svw = nadd(svw, smem_get<NL>(red, 2 * q + 1));
+    }
     if (mp::is_zero(svv)) {
       failed = true;
       break;
     }
-    rho = ndiv(svw, svv);
+    // scaled residual r' = (v'v) w - (v'w) v = (v'v) (W v - rho v): no division inside the loop (v'v = 1 + O(2^-52))
     Num<NL> ri = mp::zero<NL>();
-    if (tid < n) ri = nsub(wi, nmul(rho, vi));
+    if (tid < n) ri = nmsm(svv, wi, svw, vi);
     int rexp = __reduce_max_sync(0xffffffffu, ri.e);
     __syncthreads();
     if (lane == 0) s_int[warp] = rexp;
@@ -1021,9 +1065,15 @@ lambda_min_mixed_kernel(mp::Tensor W, const int64_t* __restrict__ offW, int n, m
     }
     __syncthreads();
   }
+  LMX_T(5);
+#ifdef CLRSDP_LMX_TIMING
+  if (tid == 0 && b == 0)
+    printf("[lmx] n=%d cycles: tridiag %lld bisect %lld chol %lld invit %lld refine %lld (%d iterations)\n", n, lmx_t[1] - lmx_t[0],
+           lmx_t[2] - lmx_t[1], lmx_t[3] - lmx_t[2], lmx_t[4] - lmx_t[3], lmx_t[5] - lmx_t[4], lmx_iters);
+#endif
   if (tid == 0) {
     if (done && !failed) {
-      stm<NL>(out, out_at, rho);
+      stm<NL>(out, out_at, ndiv(svw, svv));  // Rayleigh quotient of the converged vector
       flags[b] = 0;
     } else {
       flags[b] = 1;
