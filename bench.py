@@ -272,9 +272,10 @@ def main():
         if k.startswith("mma_planes"):
             for f in mma:
                 mma[f] += v[f]
-    # int8 dense tensor peak: not in MEASURED_PEAKS.json; nominal 2x the measured bf16 rate (B200_PROFILING.md
-    # gives int8 = fp8 = 2x bf16 nominal), stated as such
-    int8_peak_tops = 2.0 * peaks["bf16_tflops"]
+    # int8 dense tensor peak: not in MEASURED_PEAKS.json, so it is measured here, in this run, on this GPU
+    # (clrsdp_measure_int8_peak: back-to-back tcgen05.mma kind::i8 128x256x32 on every SM, operands resident in smem)
+    int8_peak_macs = h.measure_int8_peak()
+    int8_peak_tops = 2.0 * int8_peak_macs / 1e12
     mma_tops = (2.0 * mma["work"] / (mma["ms"] * 1e-3) / 1e12) if mma["ms"] > 0 else 0.0
     agg = {}
     for k, v in prof.items():
@@ -285,7 +286,10 @@ def main():
     top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]
     roofline = dict(bound="tensor", kernel="mma_planes_kernel", achieved=mma_tops, peak=int8_peak_tops, unit="TOP/s (int8)",
                     frac=mma_tops / int8_peak_tops if int8_peak_tops else None, traffic=None,
-                    peak_source=f"2 x bf16_tflops ({peaks['source']}); int8 peak itself not measured",
+                    peak_source="measured in this run (tcgen05.mma kind::i8 issue loop on all SMs); MEASURED_PEAKS.json has "
+                                f"no int8 entry (its bf16 figure: {peaks['bf16_tflops']} TFLOP/s, {peaks['source']})",
+                    achieved_note="ALGORITHMIC int8 ops (M*N*K*s(s+1)/2 MACs per product, s = p/8; no guard digits, no tile "
+                                  "padding) of all sliced-GEMM launches of the step / their summed CUDA-event time",
                     launches=mma["launches"], ms_per_launch=mma["ms"] / max(1, mma["launches"]),
                     share_of_step=mma["ms"] * 1e-3 / prof_s if prof_s else None,
                     kernel_ms_per_step={k: round(v["ms"] / args.steps, 4) for k, v in top})

@@ -286,6 +286,14 @@ class Handle:
         return c
 
     # ---- product-only helpers ----------------------------------------------------------------------
+    def measure_int8_peak(self) -> float:
+        """int8 MAC/s of the tensor pipe, measured on this device (product library only)"""
+        f = self._fn("measure_int8_peak")
+        f.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+        v = ctypes.c_double(0.0)
+        self._check(f(self._h, ctypes.byref(v)), "measure_int8_peak")
+        return float(v.value)
+
     def launch_count(self) -> int:
         f = getattr(self.lib, self.prefix + "launch_count")
         f.restype = ctypes.c_int64

@@ -183,6 +183,13 @@ CAPI int clrsdp_comm_init(clrsdp_handle h, int n_ranks, int rank, const uint8_t 
     return 0;
   });
 }
+CAPI int clrsdp_measure_int8_peak(clrsdp_handle h, double* macs_per_second) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!macs_per_second) return (int)CLRSDP_ERR_BAD_ARG;
+    *macs_per_second = s.measure_i8_peak();
+    return 0;
+  });
+}
 CAPI int64_t clrsdp_launch_count(clrsdp_handle h) { return (h && h->s) ? h->s->ctx.launches : 0; }
 CAPI int clrsdp_profile_reset(clrsdp_handle h, int enable) {
   return guard(h, [&](clr::Solver& s) {

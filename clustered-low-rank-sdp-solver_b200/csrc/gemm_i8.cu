@@ -804,6 +804,70 @@ void GemmEngine::multiply(const Slice& A, const Slice& B, const GemmPlan& plan, 
   }
 }
 
+// ---- measured int8 tensor peak (the denominator of bench.py's roofline) ---------------------------------------------
+// Every SM issues `iters` back-to-back tcgen05.mma kind::i8 128 x 256 x 32 on operands resident in shared memory (no
+// loads, one accumulator, one commit at the end): the rate at which the tensor pipe retires int8 MACs, nothing else.
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x01010101u * (i & 1);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t adesc = make_smem_desc(smem_u32(smem), (8u * 128) >> 4, 2u);
+    const uint64_t bdesc = make_smem_desc(smem_u32(smem) + 16384, (8u * 128) >> 4, 2u);
+    for (int i = 0; i < iters; i++) {
+      if (elect_one()) umma_i8(tmem_base, adesc, bdesc, idesc, 1u);
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+double GemmEngine::measure_i8_peak() {
+  const int iters = 4000;
+  CLR_CUDA(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  cudaEvent_t a, b;
+  CLR_CUDA(cudaEventCreate(&a));
+  CLR_CUDA(cudaEventCreate(&b));
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CLR_CUDA(cudaEventRecord(a, ctx_.stream));
+    i8_peak_kernel<<<ctx_.sm_count, 128, 56 * 1024, ctx_.stream>>>(iters);
+    CLR_CUDA(cudaEventRecord(b, ctx_.stream));
+    CLR_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    CLR_CUDA(cudaEventElapsedTime(&ms, a, b));
+    double macs = (double)ctx_.sm_count * iters * 128.0 * 256.0 * 32.0;
+    if (rep > 0) best = std::max(best, macs / (ms * 1e-3));  // first launch = warm-up
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return best;
+}
+
 void GemmEngine::planes_only(const Slice& A, const Slice& B, const GemmPlan& plan, int32_t* h_planes, int* T_out) {
   const int T = S_;
   int BK = std::min(A.Kp, bk_cap());

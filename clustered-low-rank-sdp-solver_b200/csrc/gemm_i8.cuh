@@ -63,6 +63,8 @@ class GemmEngine {
   // exact integer planes for tests: planes [T][batch][M][N] (splits already summed must be 1)
   void planes_only(const Slice& A, const Slice& B, const GemmPlan& plan, int32_t* h_planes, int* T_out);
   int digits() const { return S_; }
+  // int8 MACs per second of back-to-back tcgen05.mma kind::i8 128x256x32 on all SMs (measured denominator of the roofline)
+  double measure_i8_peak();
   double last_int8_macs = 0;  // executed digit-product MACs of the last multiply (incl. guard digits)
 
  private:

@@ -59,6 +59,10 @@ class Solver {
   int solve(clrsdp_iter_info* rows, int max_rows, int* n_rows);
   int64_t fetch(const char* name, int j, int l, clrsdp_mp_out* out);
   void comm_init(int n_ranks, int rank, const uint8_t* id);
+  double measure_i8_peak() {
+    CLR_CUDA(cudaSetDevice(ctx.device));
+    return gemm_->measure_i8_peak();
+  }
   // phase-level ops
   void op_gemm(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, clrsdp_mp_out* C);
   void op_gemm_planes(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, int32_t* planes,

@@ -198,6 +198,11 @@ int clrsdp_op_elementwise(clrsdp_handle h, int op, const clrsdp_mp* a, const clr
 int clrsdp_comm_unique_id(uint8_t id[128]);
 int clrsdp_comm_init(clrsdp_handle h, int n_ranks, int rank, const uint8_t id[128]);
 
+/* measured dense int8 tensor rate of this device: int8 multiply-accumulates per second of back-to-back
+ * tcgen05.mma kind::i8 (128x256x32) on every SM with resident operands. bench.py's roofline denominator for the
+ * sliced GEMM (MEASURED_PEAKS.json has no int8 figure). No reference counterpart. */
+int clrsdp_measure_int8_peak(clrsdp_handle h, double* macs_per_second);
+
 /* number of kernels of this library launched since the handle was created (bench `gpu_launches`) */
 int64_t clrsdp_launch_count(clrsdp_handle h);
 /* CUDA-event time (ms) and launch count accumulated for kernels whose name contains `pattern`
