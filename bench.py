@@ -237,6 +237,7 @@ def main():
     # ---- end to end: the iterate lives in host buffers between iterations ----
     n_x, n_X, n_y = int(sum(bi.dim_S)), int(sum(s * s for row in bi.Y_blocksizes for s in row)), bi.n_y
     state = h.download_point(n_x, n_X, n_y)
+    h.pin(*state)   # the iterate's host buffers are page-locked once; every step DMAs from / into them
     bytes_per_num = 4 * h.nlimb + 8 + 1
     h2d = (n_x + n_y + 2 * n_X) * bytes_per_num
     d2h = h2d + ctypes.sizeof(type(r))

@@ -286,6 +286,14 @@ class Handle:
         return c
 
     # ---- product-only helpers ----------------------------------------------------------------------
+    def pin(self, *arrays):
+        """register the numpy buffers of MpArrays (kept alive by the caller) for direct DMA (product library only)"""
+        f = self._fn("pin_host")
+        f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        for a in arrays:
+            for buf in (a.sign, a.exp, a.limb):
+                self._check(f(self._h, buf.ctypes.data, buf.nbytes), "pin_host")
+
     def measure_int8_peak(self) -> float:
         """int8 MAC/s of the tensor pipe, measured on this device (product library only)"""
         f = self._fn("measure_int8_peak")

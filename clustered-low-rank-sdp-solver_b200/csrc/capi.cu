@@ -183,6 +183,18 @@ CAPI int clrsdp_comm_init(clrsdp_handle h, int n_ranks, int rank, const uint8_t 
     return 0;
   });
 }
+CAPI int clrsdp_pin_host(clrsdp_handle h, void* p, size_t bytes) {
+  return guard(h, [&](clr::Solver& s) {
+    s.pin_host(p, bytes);
+    return 0;
+  });
+}
+CAPI int clrsdp_unpin_host(clrsdp_handle h, void* p) {
+  return guard(h, [&](clr::Solver& s) {
+    s.unpin_host(p);
+    return 0;
+  });
+}
 CAPI int clrsdp_measure_int8_peak(clrsdp_handle h, double* macs_per_second) {
   return guard(h, [&](clr::Solver& s) {
     if (!macs_per_second) return (int)CLRSDP_ERR_BAD_ARG;

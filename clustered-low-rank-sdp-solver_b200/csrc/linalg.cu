@@ -1448,6 +1448,49 @@ void gemv(Ctx& ctx, int nl, const GemvArgs& a, mp::Tensor work) {
 }
 
 // =========================================================================================================
+// wire format <-> header word (the pinned transfer path of solver.cu)
+// =========================================================================================================
+template <int NL>
+__global__ void wire_pack_kernel(mp::Tensor t, int64_t off, int64_t n, const int8_t* __restrict__ sign,
+                                 const int64_t* __restrict__ exp) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int sg = sign[i];
+    uint32_t* hdr = t.w + (size_t)NL * t.n + off + i;
+    if (sg == 0) {
+      *hdr = mp::pack_hdr(mp::EXP_ZERO, 0);
+#pragma unroll
+      for (int k = 0; k < NL; k++) t.w[(size_t)k * t.n + off + i] = 0;
+    } else {
+      *hdr = mp::pack_hdr((int32_t)exp[i], sg < 0 ? 1u : 0u);
+    }
+  }
+}
+template <int NL>
+__global__ void wire_unpack_kernel(mp::Tensor t, int64_t off, int64_t n, int8_t* __restrict__ sign, int64_t* __restrict__ exp) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t h = t.w[(size_t)NL * t.n + off + i];
+    const int32_t e = ((int32_t)h) >> 1;
+    const bool z = e == mp::EXP_ZERO;
+    sign[i] = z ? 0 : ((h & 1u) ? -1 : 1);
+    exp[i] = z ? 0 : e;
+  }
+}
+void wire_pack(Ctx& ctx, int nl, mp::Tensor t, int64_t off, int64_t n, const int8_t* d_sign, const int64_t* d_exp) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("wire_pack", (double)n * 13.0);
+    wire_pack_kernel<NL><<<(int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx.sm_count * 8), 256, 0, ctx.stream>>>(t, off, n, d_sign, d_exp);
+    ctx.end(tk);
+  });
+}
+void wire_unpack(Ctx& ctx, int nl, mp::Tensor t, int64_t off, int64_t n, int8_t* d_sign, int64_t* d_exp) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("wire_unpack", (double)n * 13.0);
+    wire_unpack_kernel<NL><<<(int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx.sm_count * 8), 256, 0, ctx.stream>>>(t, off, n, d_sign, d_exp);
+    ctx.end(tk);
+  });
+}
+
+// =========================================================================================================
 // small batched products on the CUDA cores
 // =========================================================================================================
 // C[b][i][j] (epi) sum_k A(b,i,k) * B(b,j,k) for products too small to amortise the tensor-core pipeline (slice,

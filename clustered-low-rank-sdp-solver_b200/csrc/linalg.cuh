@@ -96,6 +96,10 @@ struct GemvArgs {
 void gemv(Ctx& ctx, int nl, const GemvArgs& g, mp::Tensor work);
 size_t gemv_work_elems(int rows, int K);
 
+// ---- wire format <-> header word: t[off + i] gets / yields (sign, exp); a zero sign also clears the limbs ------
+void wire_pack(Ctx& ctx, int nl, mp::Tensor t, int64_t off, int64_t n, const int8_t* d_sign, const int64_t* d_exp);
+void wire_unpack(Ctx& ctx, int nl, mp::Tensor t, int64_t off, int64_t n, int8_t* d_sign, int64_t* d_exp);
+
 // ---- small batched products on the CUDA cores ---------------------------------------------------------------
 // C(b,i,j) = epi( sum_k A(b,i,k) * B(b,j,k) ): element (b,r,k) of an operand at off(b) + r*rs + k*ks with
 // off(b) = x0 + (offX ? offX[b] : b*xbs); C element (b,i,j) at off(b) + i*crs + j*ccs; epi as in gemm_i8.cuh.

@@ -58,6 +58,7 @@ Solver::Solver(int prec_bits, int device) : nl(prec_bits / 32), prec(prec_bits) 
 
 Solver::~Solver() {
   cudaSetDevice(ctx.device);
+  for (auto& r : pinned_) cudaHostUnregister((void*)r.first);
   drop_graph();
   if (comm_.comm) NcclApi::get().CommDestroy(comm_.comm);
   for (auto e : ev_) cudaEventDestroy(e);
@@ -139,8 +140,57 @@ void parallel_ranges(int64_t count, F&& f) {
 }
 }  // namespace
 
+// ---- caller-pinned host buffers: DMA straight from / into the wire arrays ------------------------------
+// clrsdp_pin_host registers a long-lived caller buffer with the CUDA driver. A wire tensor whose three arrays all lie
+// in registered ranges skips the staging copy: the limb planes go by one strided DMA, sign/exp by two small copies and
+// the header words are packed / unpacked by a kernel (linalg.cu: wire_pack / wire_unpack).
+void Solver::pin_host(void* p, size_t bytes) {
+  if (!p || !bytes) throw SolverError(CLRSDP_ERR_BAD_ARG, "pin_host: empty range");
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  for (auto& r : pinned_)
+    if (r.first == (const char*)p && r.second >= bytes) return;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw SolverError(CLRSDP_ERR_CUDA, std::string("pin_host: cudaHostRegister failed: ") + cudaGetErrorString(e));
+  }
+  pinned_.emplace_back((const char*)p, bytes);
+}
+void Solver::unpin_host(void* p) {
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  for (size_t i = 0; i < pinned_.size(); i++)
+    if (pinned_[i].first == (const char*)p) {
+      CLR_CUDA(cudaStreamSynchronize(ctx.stream));
+      cudaHostUnregister(p);
+      pinned_.erase(pinned_.begin() + i);
+      return;
+    }
+  throw SolverError(CLRSDP_ERR_BAD_ARG, "unpin_host: range was not pinned");
+}
+bool Solver::is_pinned(const void* p, size_t bytes) const {
+  const char* c = (const char*)p;
+  for (auto& r : pinned_)
+    if (c >= r.first && c + bytes <= r.first + r.second) return true;
+  return false;
+}
+bool Solver::wire_pinned(const int8_t* sign, const int64_t* exp, const uint32_t* limb, int64_t n) const {
+  return n >= 4096 && is_pinned(sign, (size_t)n) && is_pinned(exp, (size_t)n * 8) && is_pinned(limb, (size_t)n * 4 * nl);
+}
+
 void Solver::to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpBuf& dst, int64_t dst_off) {
   if (count <= 0) return;
+  if (wire_pinned(src->sign, src->exp, src->limb, src->n)) {
+    wire_se_.ensure((size_t)count * 9);
+    int8_t* d_sign = wire_se_.as<int8_t>() + (size_t)count * 8;
+    int64_t* d_exp = wire_se_.as<int64_t>();
+    CLR_CUDA(cudaMemcpy2DAsync(dst.w() + dst_off, dst.n * sizeof(uint32_t), src->limb + src_off, (size_t)src->n * sizeof(uint32_t),
+                               (size_t)count * sizeof(uint32_t), (size_t)nl, cudaMemcpyHostToDevice, ctx.stream));
+    CLR_CUDA(cudaMemcpyAsync(d_sign, src->sign + src_off, (size_t)count, cudaMemcpyHostToDevice, ctx.stream));
+    CLR_CUDA(cudaMemcpyAsync(d_exp, src->exp + src_off, (size_t)count * 8, cudaMemcpyHostToDevice, ctx.stream));
+    wire_pack(ctx, nl, dst.t(), dst_off, count, d_sign, d_exp);
+    CLR_CUDA(cudaStreamSynchronize(ctx.stream));  // the scratch is reused by the next transfer
+    return;
+  }
   uint32_t* stage = stage_buf().ensure((size_t)(nl + 1) * count);
   const int nlv = nl;
   parallel_ranges(count, [&](int64_t lo, int64_t hi) {
@@ -163,6 +213,18 @@ void Solver::to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpB
 }
 void Solver::to_host(const MpBuf& src, int64_t src_off, int64_t count, clrsdp_mp_out* dst, int64_t dst_off) {
   if (count <= 0) return;
+  if (wire_pinned(dst->sign, dst->exp, dst->limb, dst->n)) {
+    wire_se_.ensure((size_t)count * 9);
+    int8_t* d_sign = wire_se_.as<int8_t>() + (size_t)count * 8;
+    int64_t* d_exp = wire_se_.as<int64_t>();
+    wire_unpack(ctx, nl, src.t(), src_off, count, d_sign, d_exp);
+    CLR_CUDA(cudaMemcpy2DAsync(dst->limb + dst_off, (size_t)dst->n * sizeof(uint32_t), src.w() + src_off, src.n * sizeof(uint32_t),
+                               (size_t)count * sizeof(uint32_t), (size_t)nl, cudaMemcpyDeviceToHost, ctx.stream));
+    CLR_CUDA(cudaMemcpyAsync(dst->sign + dst_off, d_sign, (size_t)count, cudaMemcpyDeviceToHost, ctx.stream));
+    CLR_CUDA(cudaMemcpyAsync(dst->exp + dst_off, d_exp, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    CLR_CUDA(cudaStreamSynchronize(ctx.stream));
+    return;
+  }
   uint32_t* stage = stage_buf().ensure((size_t)(nl + 1) * count);
   CLR_CUDA(cudaMemcpy2DAsync(stage, (size_t)count * sizeof(uint32_t), src.w() + src_off, src.n * sizeof(uint32_t),
                              (size_t)count * sizeof(uint32_t), (size_t)(nl + 1), cudaMemcpyDeviceToHost, ctx.stream));

@@ -59,6 +59,8 @@ class Solver {
   int solve(clrsdp_iter_info* rows, int max_rows, int* n_rows);
   int64_t fetch(const char* name, int j, int l, clrsdp_mp_out* out);
   void comm_init(int n_ranks, int rank, const uint8_t* id);
+  void pin_host(void* p, size_t bytes);
+  void unpin_host(void* p);
   double measure_i8_peak() {
     CLR_CUDA(cudaSetDevice(ctx.device));
     return gemm_->measure_i8_peak();
@@ -81,6 +83,8 @@ class Solver {
   // helpers
   void to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpBuf& dst, int64_t dst_off);
   void to_host(const MpBuf& src, int64_t src_off, int64_t count, clrsdp_mp_out* dst, int64_t dst_off);
+  bool is_pinned(const void* p, size_t bytes) const;
+  bool wire_pinned(const int8_t* sign, const int64_t* exp, const uint32_t* limb, int64_t n) const;
   void upload_tables();
   void build_static_slices();
   MatBatch blkbatch(BlockGroup& g, MpBuf& t) { return MatBatch{t.t(), g.offBlk.as<int64_t>(), (int)g.blocks.size(), g.nb}; }
@@ -117,6 +121,8 @@ class Solver {
   void iteration_body();
   void drop_graph();
 
+  std::vector<std::pair<const char*, size_t>> pinned_;  // host ranges registered through pin_host
+  DevBuf wire_se_;                                     // sign / exponent scratch of the pinned transfer path
   std::unique_ptr<GemmEngine> gemm_, gemm_side_;
   cudaStream_t side_stream_ = nullptr, main_stream_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;

@@ -29,6 +29,7 @@
 #ifndef CLRSDP_H
 #define CLRSDP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -197,6 +198,14 @@ int clrsdp_op_elementwise(clrsdp_handle h, int op, const clrsdp_mp* a, const clr
  * as fixed-point int64 lanes over NCCL inside iterate. */
 int clrsdp_comm_unique_id(uint8_t id[128]);
 int clrsdp_comm_init(clrsdp_handle h, int n_ranks, int rank, const uint8_t id[128]);
+
+/* Optional: register a long-lived caller buffer (e.g. the arrays of the iterate a front end keeps across
+ * iterations) with the CUDA driver. upload_point / download_point / fetch DMA directly from / into wire tensors whose
+ * sign, exp and limb arrays all lie inside registered ranges (no staging copy; the header words are converted on
+ * the device). The buffer must stay allocated until clrsdp_unpin_host or clrsdp_destroy. No reference counterpart
+ * (the reference keeps its iterate in Julia heap objects, MPMP.jl:660-686). */
+int clrsdp_pin_host(clrsdp_handle h, void* p, size_t bytes);
+int clrsdp_unpin_host(clrsdp_handle h, void* p);
 
 /* measured dense int8 tensor rate of this device: int8 multiply-accumulates per second of back-to-back
  * tcgen05.mma kind::i8 (128x256x32) on every SM with resident operands. bench.py's roofline denominator for the

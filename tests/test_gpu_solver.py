@@ -180,6 +180,35 @@ def test_warm_start_roundtrip():
     assert np.array_equal(a.limb, o.limb) and np.array_equal(a.exp, o.exp)     # bit-identical
 
 
+def test_pinned_host_buffers_roundtrip_is_bit_identical():
+    """clrsdp_pin_host: the direct-DMA path (limb planes by strided copy, header words converted on the device) moves
+    exactly the same bits as the staged path, in both directions, including zero entries."""
+    prec = 256
+    cons, b, _ = instances.synthetic_clustered_sdp(J=2, delta=48, K=50, n_y=5, prec=prec)
+    bi = solver.get_block_info(cons)
+    h = solver.product_handle(prec)
+    solver.load_problem(h, cons, b, bi)
+    h.set_params(solver.real_params(h.nlimb))
+    h.init_point()                       # omega * I: the off-diagonal entries are exact zeros
+    h.prepare()
+    h.iterate()
+    n_x, n_X = sum(bi.dim_S), sum(s * s for row in bi.Y_blocksizes for s in row)
+    assert n_X >= 4096                   # large enough for the direct path
+    staged = h.download_point(n_x, n_X, bi.n_y)
+    pinned = h.download_point(n_x, n_X, bi.n_y)
+    h.pin(*pinned)
+    pinned = h.download_point(n_x, n_X, bi.n_y, out=pinned)
+    for a, o in zip(staged, pinned):
+        assert np.array_equal(a.sign, o.sign) and np.array_equal(a.exp, o.exp) and np.array_equal(a.limb, o.limb)
+    # upload from pinned buffers (with some exact zeros), read back through the staged path
+    pinned[1].sign[:7] = 0
+    h.upload_point(*pinned)
+    back = h.download_point(n_x, n_X, bi.n_y)
+    assert np.all(back[1].sign[:7] == 0) and np.all(back[1].limb[:, :7] == 0)
+    assert np.array_equal(back[1].sign[7:], staged[1].sign[7:]) and np.array_equal(back[1].limb[:, 7:], staged[1].limb[:, 7:])
+    assert np.array_equal(back[3].limb, staged[3].limb) and np.array_equal(back[3].exp, staged[3].exp)
+
+
 def test_call_order_and_argument_errors():
     h = solver.product_handle(256)
     with pytest.raises(ClrsdpError) as e:
