@@ -264,6 +264,10 @@ def main():
         e2e_wall = float(t[0])
     sampler.join(timeout=2)
 
+    if dist is not None:
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
     if rank != 0:
         return
     peaks = measured_peaks()
@@ -317,7 +321,9 @@ def main():
         with open(args.profile_out, "w") as f:
             json.dump(dict(per_kernel=prof, steps=args.steps, dev_seconds=prof_s,
                            phase_ms_per_step={k: float(v) / args.steps * 1e3 for k, v in zip(phase_names, phases)}), f, indent=1)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
