@@ -27,7 +27,14 @@ sys.path.insert(0, os.path.join(ROOT, "clustered-low-rank-sdp-solver_b200"))
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = dict(J_per_gpu=64, delta=64, K=128, n_y=256, prec=256, seed=20261018)
+WORKLOADS = {
+    # BASELINE config 3 per GPU (the configuration the metric is quoted on; at N = 8 the north star's 512 clusters)
+    "cfg3": dict(J_per_gpu=64, delta=64, K=128, n_y=256, prec=256, seed=20261018),
+    # one GPU's share of BASELINE config 5 on 8 GPUs (512 clusters / 8, block 128, 512 bit): not the headline, run with
+    # `--workload cfg5shard --no-cpu-baseline` to see the kernels at the sizes they were designed for
+    "cfg5shard": dict(J_per_gpu=64, delta=128, K=256, n_y=1024, prec=512, seed=20261019),
+}
+WORKLOAD = dict(WORKLOADS["cfg3"])
 METRIC = "sec/IPM iteration at 256-bit (Schur build+Cholesky), 1/2/4/8 B200 vs CPU"
 UNIT = "s/iteration"
 
@@ -155,8 +162,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table here")
     args = ap.parse_args()
+    WORKLOAD.clear()
+    WORKLOAD.update(WORKLOADS[args.workload])
     if args.impl == "reference":
         return run_reference(args)
 
@@ -301,7 +311,8 @@ def main():
     line = dict(metric=METRIC, value=sec_per_iter, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec_per_iter * 1e3, higher_is_better=False, scaling="weak", vs_baseline=None,
                 dtype=f"u{prec} fixed-limb float (int8 slices, int32 accumulate)", data="synthetic",
-                config=dict(workload="synthetic clustered low-rank SDP, BASELINE config 3 per GPU "
+                config=dict(workload=("synthetic clustered low-rank SDP, BASELINE config 3 per GPU " if args.workload == "cfg3" else
+                                      "synthetic clustered low-rank SDP, one GPU's share (64 clusters) of BASELINE config 5 ") +
                                      "(manufactured strictly feasible; iterations from omega*I)",
                             clusters_total=world * Jloc, l2="working set > L2 (several hundred MB of arenas touched per "
                             "iteration); no explicit flush", **WORKLOAD),
