@@ -309,6 +309,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
 mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, MmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  if (p.dbg && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.dbg[blockIdx.x == 0 ? 2 : 4] = (long long)gt;
+  }
   const uint32_t a_tile = 128u * p.BK, b_tile = (uint32_t)p.BN * p.BK;
   const uint32_t a_bytes = a_tile * (DG / p.stack), b_bytes = b_tile * DG;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
@@ -450,6 +455,11 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+  if (p.dbg && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.dbg[blockIdx.x == 0 ? 3 : 5] = (long long)gt;
   }
 }
 
@@ -717,9 +727,10 @@ void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, i
   ctx_.end(tk);
   if (p.debug & 32) {
     long long h[8];
+    CLR_CUDA(cudaStreamSynchronize(ctx_.stream));
     CLR_CUDA(cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[mma dbg] %s grid=%lld stages=%d stack=%d BN=%d BK=%d: issuer cycles %lld, waiting for TMA %lld\n", nm.c_str(),
-            (long long)grid, p.stages, p.stack, p.BN, p.BK, h[0], h[1]);
+    fprintf(stderr, "[mma dbg] %s grid=%lld stages=%d stack=%d BN=%d BK=%d: issuer cycles %lld, waiting for TMA %lld; CTA0 life %lld ns, last CTA starts %+lld ns after CTA0 and lives %lld ns\n", nm.c_str(),
+            (long long)grid, p.stages, p.stack, p.BN, p.BK, h[0], h[1], h[3] - h[2], h[4] - h[2], h[5] - h[4]);
   }
 }
 
@@ -746,7 +757,8 @@ static void split_k(int sm_count, int T, int Kp, int BK, int64_t tiles, int& Kc,
   int kc_safe = (131071 / T) / BK * BK;
   Kc = std::min(Kp, kc_safe);
   if (tiles < sm_count && Kp >= 512) {
-    int want = (int)std::min<int64_t>(ceil_div(sm_count, tiles), Kp / 256);
+    // one wave: at most sm_count CTAs (one CTA per SM: 512 TMEM columns, ~200 KB smem), chunks of equal length
+    int want = (int)std::min<int64_t>(sm_count / tiles, Kp / 256);
     if (want > 1) Kc = std::min(Kc, ceil_div(ceil_div(Kp, want), BK) * BK);
   }
   nsplit = ceil_div(Kp, Kc);
