@@ -178,6 +178,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+
 struct MmaParams {
   int T, M, N, batch, nsplit, Kp, Kc, BK, BN, m_tiles, n_tiles, item0, stages;
   int stack;  // digits of A stacked along the 128 MMA rows (1, 2 or 4): item tiles of 128/stack rows
@@ -191,7 +197,9 @@ struct MmaParams {
 };
 
 constexpr int EPI_SETS = 4;       // epilogue warp sets: block q is drained by set q % EPI_SETS
-constexpr int MMA_THREADS = 64 + 128 * EPI_SETS;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then the epilogue sets
+constexpr int NISSUE = 2;         // MMA-issuing warps: stage s is issued by warp 1 + s % NISSUE
+constexpr int FIRST_EPI = 1 + NISSUE;
+constexpr int MMA_THREADS = 32 * (FIRST_EPI + 4 * EPI_SETS);  // warp 0: TMA producer, warps 1..NISSUE: MMA issuers, then the epilogue sets
 constexpr int MAX_STAGES = 8;
 constexpr int DG = 4;             // digits per operand group: one pipeline stage feeds a DG x DG square of digit pairs
 constexpr int ACC_SLOTS = 8;      // accumulator slots in TMEM (block q lives in slot q % ACC_SLOTS)
@@ -207,88 +215,134 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo16
   return d;
 }
 
+// Issuer `which` of NISSUE: the warps share the stages round-robin, so the barrier wait, the descriptor set-up and
+// the commit of one stage (~600 cycles on this single-lane instruction stream) run while the tensor pipe works through
+// the MMAs of the other warp's stage. Every MMA accumulates (the epilogue hands the accumulators back zeroed), so the
+// order in which the two warps' MMAs reach the pipe does not matter: the sums are integers.
 template <int STACK>
 __device__ __forceinline__ void mma_issue(const MmaParams& p, uint64_t* bars, uint8_t* smem, uint32_t stage_bytes,
                                           uint32_t a_tile, uint32_t b_tile, uint32_t a_bytes, uint32_t tmem_base,
-                                          int kblocks) {
+                                          int kblocks, int which) {
   const int T = p.T, Dmax = (T - 1) / DG;
   constexpr int QSPAN = (DG - STACK) + (DG - 1);
   const uint32_t a_step = a_tile >> 4, b_step = b_tile >> 4;  // descriptor address units (16 bytes)
   const bool two_k = p.BK > 32;
-  int stage = 0;
+  int stage = 0, turn = 0;
   uint32_t phase = 0;
-  long long t_full = 0, t_start = clock64();
+  long long t_full = 0, t_slot = 0, t_start = clock64();
+  mbar_wait(smem_u32(&bars[32]), 0u);  // accumulators zeroed
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   for (int D = Dmax; D >= 0; D--) {
     const int sb = (DG * D) & (ACC_SLOTS - 1);  // slot of block 4D
     const int cmax = T - 1 - DG * D;            // blocks 4D + c with c > cmax do not exist
-    bool first = true;                          // first stage of this anti-diagonal: it creates blocks 4D .. 4D+3
+    // The new blocks 4D .. 4D+3 of this anti-diagonal need their slots back from the epilogue; those of 4D .. 4D+2 were
+    // handed over for draining only at the end of the previous anti-diagonal. A warp's first stage of D therefore
+    // issues its pairs into the older slots first and waits for the fresh ones in the middle of the stage. Both warps
+    // wait, also a warp without a stage in this D: its commits below must not overtake the other warp's commits of the
+    // slot's previous block.
+    bool need_wait = true;
+    auto wait_slots = [&]() {
+      const long long cs0 = p.dbg ? clock64() : 0;
+      for (int c = 0; c <= min(DG - 1, cmax); c++) {
+        const uint32_t u = (uint32_t)(T - 1 - (DG * D + c)) >> 3;  // earlier blocks in the same slot
+        if (u) mbar_wait(smem_u32(&bars[24 + ((sb + c) & (ACC_SLOTS - 1))]), (u & 1u) ^ 1u);
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p.dbg) t_slot += clock64() - cs0;
+    };
     for (int I = 0; I <= D; I++) {
       const int J = D - I;
       if (DG * I >= T || DG * J >= T) continue;
       const int na = min(DG / STACK, (T - DG * I + STACK - 1) / STACK), nb = min(DG, T - DG * J);
       for (int kb = 0; kb < kblocks; kb++) {
-        const long long c0 = p.dbg ? clock64() : 0;
-        mbar_wait(smem_u32(&bars[stage]), phase);
-        if (p.dbg) t_full += clock64() - c0;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint64_t adesc0 = make_smem_desc(sa, p.sbo16, p.layout_type);
-        const uint64_t bdesc0 = make_smem_desc(sa + a_bytes, p.sbo16, p.layout_type);
-        const bool full = !first && na == DG / STACK && nb == DG && cmax >= QSPAN;
-        if (full) {  // interior stage (the common case): no predicates, no waits
-          if (elect_one()) {
+        if (turn == which) {
+          const long long c0 = p.dbg ? clock64() : 0;
+          mbar_wait(smem_u32(&bars[stage]), phase);
+          if (p.dbg) t_full += clock64() - c0;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc0 = make_smem_desc(sa, p.sbo16, p.layout_type);
+          const uint64_t bdesc0 = make_smem_desc(sa + a_bytes, p.sbo16, p.layout_type);
+          const bool full = na == DG / STACK && nb == DG && cmax >= QSPAN && !need_wait;
+          if (full) {  // interior stage (the common case): no predicates
+            if (elect_one()) {
 #pragma unroll
-            for (int ia = 0; ia < DG / STACK; ia++) {
+              for (int ia = 0; ia < DG / STACK; ia++) {
 #pragma unroll
-              for (int jb = 0; jb < DG; jb++) {
-                const uint32_t d_tmem = tmem_base + (uint32_t)(((sb + ia * STACK + jb) & (ACC_SLOTS - 1)) * p.BN);
-                const uint64_t ad = adesc0 + (uint64_t)(ia * a_step), bd = bdesc0 + (uint64_t)(jb * b_step);
-                umma_i8(d_tmem, ad, bd, p.idesc, 1u);
-                if (two_k) umma_i8(d_tmem, ad + 2, bd + 2, p.idesc, 1u);
+                for (int jb = 0; jb < DG; jb++) {
+                  const uint32_t d_tmem = tmem_base + (uint32_t)(((sb + ia * STACK + jb) & (ACC_SLOTS - 1)) * p.BN);
+                  const uint64_t ad = adesc0 + (uint64_t)(ia * a_step), bd = bdesc0 + (uint64_t)(jb * b_step);
+                  umma_i8(d_tmem, ad, bd, p.idesc, 1u);
+                  if (two_k) umma_i8(d_tmem, ad + 2, bd + 2, p.idesc, 1u);
+                }
               }
+              umma_commit(smem_u32(&bars[8 + stage]));
             }
-            umma_commit(smem_u32(&bars[8 + stage]));
-          }
-        } else if (elect_one()) {  // one lane issues the whole stage
+          } else {
+            // my first stage of this D: first the pairs into block 4D+3 and above (a slot that has been free for a
+            // whole anti-diagonal, or blocks carried over), then - after the slot wait - those into 4D .. 4D+2
+            const bool split = need_wait;
+            if (split) {
+              const uint32_t u3 = (uint32_t)(T - 1 - (DG * D + DG - 1)) >> 3;
+              if (DG - 1 <= cmax && u3) mbar_wait(smem_u32(&bars[24 + ((sb + DG - 1) & (ACC_SLOTS - 1))]), (u3 & 1u) ^ 1u);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            if (elect_one()) {
 #pragma unroll
-          for (int ia = 0; ia < DG / STACK; ia++) {
+              for (int ia = 0; ia < DG / STACK; ia++) {
 #pragma unroll
-            for (int jb = 0; jb < DG; jb++) {
-              const int c = ia * STACK + jb;  // block 4D + c, lane group r holds plane 4D + c + r
-              if (ia < na && jb < nb && c <= cmax) {
-                uint32_t acc = 1u;
-                if (ia == 0 && first) {  // (0, jb) is the first pair of the schedule that touches block 4D + jb
-                  acc = 0u;
-                  const uint32_t u = (uint32_t)(T - 1 - (DG * D + c)) >> 3;  // earlier blocks in the same slot
-                  if (u) {  // wait until the epilogue has drained the previous one
-                    mbar_wait(smem_u32(&bars[24 + ((sb + c) & (ACC_SLOTS - 1))]), (u & 1u) ^ 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int jb = 0; jb < DG; jb++) {
+                  const int c = ia * STACK + jb;  // block 4D + c, lane group r holds plane 4D + c + r
+                  if (ia < na && jb < nb && c <= cmax && (!split || c >= DG - 1)) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(((sb + c) & (ACC_SLOTS - 1)) * p.BN);
+                    const uint64_t ad = adesc0 + (uint64_t)(ia * a_step), bd = bdesc0 + (uint64_t)(jb * b_step);
+                    umma_i8(d_tmem, ad, bd, p.idesc, 1u);
+                    if (two_k) umma_i8(d_tmem, ad + 2, bd + 2, p.idesc, 1u);
                   }
                 }
-                const uint32_t d_tmem = tmem_base + (uint32_t)(((sb + c) & (ACC_SLOTS - 1)) * p.BN);
-                const uint64_t ad = adesc0 + (uint64_t)(ia * a_step), bd = bdesc0 + (uint64_t)(jb * b_step);
-                umma_i8(d_tmem, ad, bd, p.idesc, acc);
-                if (two_k) umma_i8(d_tmem, ad + 2, bd + 2, p.idesc, 1u);
               }
             }
+            __syncwarp();
+            if (split) {
+              wait_slots();
+              need_wait = false;
+              if (elect_one()) {
+#pragma unroll
+                for (int ia = 0; ia < DG / STACK; ia++) {
+#pragma unroll
+                  for (int jb = 0; jb < DG; jb++) {
+                    const int c = ia * STACK + jb;
+                    if (ia < na && jb < nb && c <= cmax && c < DG - 1) {
+                      const uint32_t d_tmem = tmem_base + (uint32_t)(((sb + c) & (ACC_SLOTS - 1)) * p.BN);
+                      const uint64_t ad = adesc0 + (uint64_t)(ia * a_step), bd = bdesc0 + (uint64_t)(jb * b_step);
+                      umma_i8(d_tmem, ad, bd, p.idesc, 1u);
+                      if (two_k) umma_i8(d_tmem, ad + 2, bd + 2, p.idesc, 1u);
+                    }
+                  }
+                }
+              }
+              __syncwarp();
+            }
+            if (elect_one()) umma_commit(smem_u32(&bars[8 + stage]));  // frees the smem slot when these MMAs retire
           }
-          umma_commit(smem_u32(&bars[8 + stage]));  // frees the smem slot when these MMAs retire
+          __syncwarp();
         }
-        __syncwarp();
-        first = false;
+        if (++turn == NISSUE) turn = 0;
         if (++stage == p.stages) stage = 0, phase ^= 1u;
       }
     }
-    // blocks that no later anti-diagonal touches are complete
+    if (need_wait) wait_slots();  // a warp without a stage in this D (see above)
+    // blocks that no later anti-diagonal touches are complete once BOTH warps' MMAs have retired: each warp commits
     const int q_hi = min(T - 1, DG * D + QSPAN);
     const int q_lo = (D == 0) ? 0 : DG * D + QSPAN - (DG - 1);
     if (elect_one())
       for (int q = q_hi; q >= q_lo; q--) umma_commit(smem_u32(&bars[16 + (q & (ACC_SLOTS - 1))]));
     __syncwarp();
   }
-  if (p.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+  if (p.dbg && blockIdx.x == 0 && which == 0 && (threadIdx.x & 31) == 0) {
     p.dbg[0] = clock64() - t_start;
     p.dbg[1] = t_full;
+    p.dbg[6] = t_slot;
   }
 }
 
@@ -318,8 +372,9 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t a_bytes = a_tile * (DG / p.stack), b_bytes = b_tile * DG;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
   uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
-  // bars[0..7] full, [8..15] empty, [16..23] slot_full, [24..31] slot_empty, then the TMEM base pointer
-  uint32_t* tmem_slot = (uint32_t*)(bars + 32);
+  // bars[0..7] full, [8..15] empty, [16..23] slot_full, [24..31] slot_empty, [32] accumulators zeroed, then the TMEM
+  // base pointer
+  uint32_t* tmem_slot = (uint32_t*)(bars + 33);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   int idx = blockIdx.x;
@@ -347,9 +402,10 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(smem_u32(&bars[8 + s]), 1);
     }
     for (int s = 0; s < ACC_SLOTS; s++) {
-      mbar_init(smem_u32(&bars[16 + s]), 1);
+      mbar_init(smem_u32(&bars[16 + s]), NISSUE);
       mbar_init(smem_u32(&bars[24 + s]), 4);
     }
+    mbar_init(smem_u32(&bars[32]), 4 * EPI_SETS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -386,24 +442,32 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    // The whole warp runs the (warp-uniform) schedule; one elected lane issues. The per-pair path is a handful of
-    // uniform-register instructions: a tcgen05.mma of 128 x 64 x 32 retires every 48 cycles, so anything longer
-    // than that per MMA on this single-warp instruction stream is directly visible as idle tensor pipe.
+  } else if (warp < FIRST_EPI) {
+    // ------------------------------ MMA issuers -------------------------------
+    // Each warp runs the (warp-uniform) schedule and one elected lane issues its stages. A tcgen05.mma of
+    // 128 x 64 x 32 retires every 48 cycles and the issuing thread is throttled to that rate, so every other
+    // instruction on this path would be idle tensor pipe if a single warp issued everything.
     if (stack == 1)
-      mma_issue<1>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks);
+      mma_issue<1>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks, warp - 1);
     else if (stack == 2)
-      mma_issue<2>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks);
+      mma_issue<2>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks, warp - 1);
     else
-      mma_issue<4>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks);
+      mma_issue<4>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks, warp - 1);
   } else {
     // ------------------------------ epilogue: TMEM -> registers -> HBM blocks --------------------
     // EPI_SETS sets of four warps (one warp per TMEM lane quarter) drain the blocks round-robin, so several drains
     // (barrier wake-up, TMEM load, stores) are in flight;
     // all TMEM loads of a block are issued before the single wait.
-    const int q4 = warp & 3;              // TMEM lane quarter this warp may access
-    const int eset = (warp - 2) >> 2;     // handles the blocks with q % EPI_SETS == eset
+    const int q4 = warp & 3;                      // TMEM lane quarter this warp may access
+    const int eset = (warp - FIRST_EPI) >> 2;     // handles the blocks with q % EPI_SETS == eset
+    {  // hand every accumulator to the issuers zeroed: set e clears the slots e, e + EPI_SETS, ...
+      for (int sl = eset; sl < ACC_SLOTS; sl += EPI_SETS)
+        for (int c0 = 0; c0 < p.BN; c0 += 16) tmem_st16_zero(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sl * p.BN + c0));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[32]));
+    }
     const int lrow = q4 * 32 + lane;
     const int mip = 128 / stack;
     const int grp = lrow / mip;           // lane group: plane q + grp
@@ -430,7 +494,11 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (cc * 16 < p.BN) tmem_ld16(taddr + cc * 16, v[cc]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
-        // the accumulator slot is free as soon as it has been read
+        // the accumulator slot goes back as soon as it has been read and cleared
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++)
+          if (cc * 16 < p.BN) tmem_st16_zero(taddr + cc * 16);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[24 + slot]));
@@ -729,8 +797,8 @@ void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, i
     long long h[8];
     CLR_CUDA(cudaStreamSynchronize(ctx_.stream));
     CLR_CUDA(cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[mma dbg] %s grid=%lld stages=%d stack=%d BN=%d BK=%d: issuer cycles %lld, waiting for TMA %lld; CTA0 life %lld ns, last CTA starts %+lld ns after CTA0 and lives %lld ns\n", nm.c_str(),
-            (long long)grid, p.stages, p.stack, p.BN, p.BK, h[0], h[1], h[3] - h[2], h[4] - h[2], h[5] - h[4]);
+    fprintf(stderr, "[mma dbg] %s grid=%lld stages=%d stack=%d BN=%d BK=%d: issuer cycles %lld, waiting for TMA %lld, for accumulator slots %lld; CTA0 life %lld ns, last CTA starts %+lld ns after CTA0 and lives %lld ns\n", nm.c_str(),
+            (long long)grid, p.stages, p.stack, p.BN, p.BK, h[0], h[1], h[6], h[3] - h[2], h[4] - h[2], h[5] - h[4]);
   }
 }
 
