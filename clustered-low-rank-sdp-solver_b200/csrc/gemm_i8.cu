@@ -76,6 +76,56 @@ __device__ __forceinline__ void slice_entry(const GatherArgs& g, int row, int k,
   }
 }
 
+// Four consecutive entries k4 .. k4+3 of one row: their digits are packed into one 32-bit word per digit plane, so a
+// warp writes 128 contiguous bytes per plane and store instruction instead of 32.
+template <int NL, int S>
+__device__ __forceinline__ void slice_entry4(const GatherArgs& g, int row, int k4, int32_t rexp, int8_t* __restrict__ digits) {
+  constexpr int NLW = NL + 2;
+  static_assert(8 * S + 2 <= 32 * NLW, "digit window too small");
+  uint32_t out[S];
+#pragma unroll
+  for (int i = 0; i < S; i++) out[i] = 0;
+  const int b = row / g.rows, r = row % g.rows;
+  const int64_t base = item_off(g, b) + (int64_t)r * g.rs;
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int k = k4 + e;
+    uint32_t W[NLW];
+#pragma unroll
+    for (int i = 0; i < NLW; i++) W[i] = 0;
+    bool negf = false;
+    if (k < g.K) {
+      mp::Num<NL> x = mp::load<NL>(g.w, g.n, (size_t)(base + (int64_t)k * g.ks));
+      if (!mp::is_zero(x)) {
+        uint32_t d = (uint32_t)(rexp - x.e);
+        uint32_t sr = 32u * NLW - 8u * S + 2u + d;
+        if (sr < 32u * NLW) {
+#pragma unroll
+          for (int i = 0; i < NL; i++) W[i + 2] = x.m[i];
+          if (sr >> 5) mp::shr_limbs<NLW>(W, sr >> 5);
+          if (sr & 31u) mp::shr_bits<NLW>(W, sr & 31u);
+          negf = x.neg != 0;
+        }
+      }
+    }
+    if (negf) mp::neg_n<NLW>(W);
+    int carry = 0;
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      int v = (int)((W[i >> 2] >> (8 * (i & 3))) & 0xFFu) + carry;
+      carry = v >= 128 ? 1 : 0;
+      out[i] |= (uint32_t)(v & 0xFF) << (8 * e);
+    }
+  }
+  uint32_t* o = reinterpret_cast<uint32_t*>(digits + ((size_t)(S - 1) * g.rows_total + row) * g.Kp + k4);
+  const size_t pstride4 = ((size_t)g.rows_total * g.Kp) >> 2;
+#pragma unroll
+  for (int i = 0; i < S; i++) {
+    *o = out[i];
+    o -= pstride4;
+  }
+}
+
 // Row exponent + slicing in one launch. A block of 8 warps owns 8/WPR rows (WPR warps per row): pass 1 takes the
 // maximum exponent over the row's non-zero entries (EXP_ZERO for an all-zero row), pass 2 converts the row.
 // The second read of the row hits L1/L2.
@@ -108,7 +158,11 @@ __global__ void __launch_bounds__(SLICE_THREADS, 3) slice_rows_kernel(GatherArgs
     }
     if (live) {
       if (sub == 0 && lane == 0) exps[row] = mx;
-      for (int k = sub * 32 + lane; k < g.Kp; k += 32 * wpr) slice_entry<NL, S>(g, row, k, mx, digits);
+      if (g.Kp >= 256) {  // long rows: four entries per thread, packed 32-bit digit stores
+        for (int k4 = 4 * (sub * 32 + lane); k4 < g.Kp; k4 += 128 * wpr) slice_entry4<NL, S>(g, row, k4, mx, digits);
+      } else {            // short rows: one entry per thread keeps all lanes busy
+        for (int k = sub * 32 + lane; k < g.Kp; k += 32 * wpr) slice_entry<NL, S>(g, row, k, mx, digits);
+      }
     }
   }
 }
