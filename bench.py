@@ -102,7 +102,7 @@ def algorithmic_int8_macs(bi, prec):
             pmac += 2 * nb * nb * Nv                               # Z V for trace_A, two directions
             pmac += 2 * (2 * nb ** 3)                              # L^-1 dM L^-T for X and Y
         pmac += dimS * dimS * bi.n_y                               # W = L^-1 B
-        pmac += bi.n_y * bi.n_y * dimS                             # Q
+        pmac += bi.n_y * (bi.n_y + 1) // 2 * dimS                  # Q = W^T W: symmetric, upper triangle computed (SYRK)
     return pmac * per, pmac
 
 

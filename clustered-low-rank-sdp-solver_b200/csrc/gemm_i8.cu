@@ -244,6 +244,8 @@ struct MmaParams {
   int Mpad;   // rows per item in the block buffer (m_tiles * 128)
   const int* rowA;
   const int* rowB;
+  const int2* tile_map;  // symmetric product (A == B): the (mt, nt) tiles that touch the upper triangle; nullptr = all tiles
+  int n_tile_pairs;
   int32_t* blocks;  // [T][nsplit][batch][ceil(N/4)][Mpad][4]: block q, lane group r holds the partial plane q + r
   uint32_t idesc, sbo16, layout_type;
   int debug;  // CLRSDP_MMA_DEBUG (measuring aid): 1 = skip the block stores, 2 = skip the TMEM loads, 32 = cycle counters
@@ -434,10 +436,17 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   int idx = blockIdx.x;
   const int split = idx % p.nsplit;
   idx /= p.nsplit;
-  const int nt = idx % p.n_tiles;
-  idx /= p.n_tiles;
-  const int mt = idx % p.m_tiles;
-  idx /= p.m_tiles;
+  int nt, mt;
+  if (p.tile_map) {
+    const int2 t = p.tile_map[idx % p.n_tile_pairs];
+    idx /= p.n_tile_pairs;
+    mt = t.x, nt = t.y;
+  } else {
+    nt = idx % p.n_tiles;
+    idx /= p.n_tiles;
+    mt = idx % p.m_tiles;
+    idx /= p.m_tiles;
+  }
   const int item = idx;  // local item in this launch
   const int gitem = p.item0 + item;
   const int rowA0 = (p.rowA ? p.rowA[gitem] : gitem * p.M) + mt * 128;
@@ -591,6 +600,7 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 struct CarryArgs {
   const int32_t* planes;  // blocks [T][nsplit][batch][ceil(N/4)][Mpad][4]; plane p = sum_r block[p - r] rows [r*mip, r*mip + M)
   int stack, mip, Mpad;
+  int sym_bn;  // > 0: symmetric product computed on the tiles touching the upper triangle only (tile width sym_bn)
   const int32_t* expA;    // per row of A (global row index)
   const int32_t* expB;
   const int* rowA;
@@ -625,7 +635,10 @@ __global__ void carry_kernel(CarryArgs c) {
     const int i = 4 * pi + (ln >> 3), j = 8 * pj + (ln & 7);
     if (i >= c.M || j >= c.N) continue;
     int gb = c.item0 + b;
-    const size_t e0 = (((size_t)b * n4 + (j >> 2)) * c.Mpad + i) * 4 + (j & 3);  // entry (b, i, j) in lane group 0
+    // symmetric product: an entry whose tile was skipped is read from its mirror image (same planes, same exponents)
+    int si = i, sj = j;
+    if (c.sym_bn > 0 && (j / c.sym_bn) * c.sym_bn + c.sym_bn - 1 < (i >> 7) * 128) si = j, sj = i;
+    const size_t e0 = (((size_t)b * n4 + (sj >> 2)) * c.Mpad + si) * 4 + (sj & 3);  // entry (b, si, sj) in lane group 0
     const size_t gstride = (size_t)c.mip * 4;                                      // next lane group
     uint32_t W[NW];
 #pragma unroll
@@ -685,7 +698,7 @@ __global__ void carry_kernel(CarryArgs c) {
         cc = (uint32_t)(s >> 32);
       }
     }
-    int ra = (c.rowA ? c.rowA[gb] : gb * c.M) + i, rb = (c.rowB ? c.rowB[gb] : gb * c.N) + j;
+    int ra = (c.rowA ? c.rowA[gb] : gb * c.M) + si, rb = (c.rowB ? c.rowB[gb] : gb * c.N) + sj;
     int32_t ea = c.expA[ra], eb = c.expB[rb];
     mp::Num<NL> r;
     int sh = mp::normalize_n<NW>(W);
@@ -796,7 +809,7 @@ static int stack_of(int M) { return M <= 32 ? 4 : (M <= 64 ? 2 : 1); }
 static int bn_of(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : 64); }
 
 void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, int item0, int nitems, int nsplit,
-                         int Kc) {
+                         int Kc, bool symmetric) {
   MmaParams p;
   memset(&p, 0, sizeof(p));
   p.T = S_;
@@ -832,12 +845,28 @@ void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, i
   p.stages = (int)std::min<size_t>(MAX_STAGES, (196 * 1024) / stage_bytes);
   size_t smem = 1024 + (size_t)p.stages * stage_bytes + 1024;
   CUtensorMap tmA = make_map(A, 128 / p.stack, p.BK, DG), tmB = make_map(B, p.BN, p.BK, DG);
-  int64_t grid = (int64_t)nitems * p.m_tiles * p.n_tiles * nsplit;
+  int64_t tiles_per_item = (int64_t)p.m_tiles * p.n_tiles;
+  if (symmetric) {
+    std::vector<int2> map;
+    for (int mt = 0; mt < p.m_tiles; mt++)
+      for (int nt = 0; nt < p.n_tiles; nt++)
+        if (nt * p.BN + p.BN - 1 >= mt * 128) map.push_back(make_int2(mt, nt));
+    if (sym_map_host_ != map.size() * 1000003 + (size_t)p.m_tiles * 1009 + p.n_tiles) {  // (re)upload when the shape changes
+      sym_map_.ensure(map.size() * sizeof(int2));
+      CLR_CUDA(cudaMemcpyAsync(sym_map_.p, map.data(), map.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx_.stream));
+      CLR_CUDA(cudaStreamSynchronize(ctx_.stream));
+      sym_map_host_ = map.size() * 1000003 + (size_t)p.m_tiles * 1009 + p.n_tiles;
+    }
+    p.tile_map = sym_map_.as<int2>();
+    p.n_tile_pairs = (int)map.size();
+    tiles_per_item = (int64_t)map.size();
+  }
+  int64_t grid = (int64_t)nitems * tiles_per_item * nsplit;
   double macs = (double)nitems * p.m_tiles * 128.0 * p.n_tiles * p.BN * (double)A.Kp * (p.T * (p.T + 1) / 2.0) / p.stack;
   last_int8_macs += macs;
   // algorithmic MACs: M*N*K * s(s+1)/2 with s = p/8, no guard digits, no tile padding
   double s_alg = 4.0 * nl_;
-  double alg = (double)nitems * plan.M * plan.N * (double)A.K * (s_alg * (s_alg + 1) / 2.0);
+  double alg = (double)nitems * (symmetric ? 0.5 * plan.M * (plan.M + 1.0) : (double)plan.M * plan.N) * (double)A.K * (s_alg * (s_alg + 1) / 2.0);
   std::string nm = "mma_planes_M" + std::to_string(plan.M) + "_N" + std::to_string(plan.N) + "_K" + std::to_string(A.K) + "_b" + std::to_string(nitems);
   int tk = ctx_.begin(nm.c_str(), alg);
   static long long* d_dbg = nullptr;
@@ -887,12 +916,19 @@ static void split_k(int sm_count, int T, int Kp, int BK, int64_t tiles, int& Kc,
 }
 
 void GemmEngine::multiply(const Slice& A, const Slice& B, const GemmPlan& plan, const OutDesc& C, int epi,
-                          const mp::Tensor* extra) {
+                          const mp::Tensor* extra, bool symmetric) {
+  if (symmetric && (&A != &B || plan.M != plan.N || plan.d_rowA || plan.d_rowB)) symmetric = false;
   if (A.Kp != B.Kp || A.S != S_ || B.S != S_) throw SolverError(-1, "gemm: operand mismatch");
   const int T = S_;
   const int BK = std::min(A.Kp, bk_cap()), BN = bn_of(plan.N), stack = stack_of(plan.M);
   const int m_tiles = ceil_div(plan.M, 128), Mpad = m_tiles * 128;
   int64_t tiles = (int64_t)plan.batch * m_tiles * ceil_div(plan.N, BN);
+  if (symmetric) {  // only the tiles that touch the upper triangle
+    int cnt = 0;
+    for (int mt = 0; mt < m_tiles; mt++)
+      for (int nt = 0; nt < ceil_div(plan.N, BN); nt++) cnt += (nt * BN + BN - 1 >= mt * 128) ? 1 : 0;
+    tiles = (int64_t)plan.batch * cnt;
+  }
   int Kc, nsplit;
   split_k(ctx_.sm_count, T, A.Kp, BK, tiles, Kc, nsplit);
   // chunk the batch so that the block workspace stays bounded
@@ -902,10 +938,11 @@ void GemmEngine::multiply(const Slice& A, const Slice& B, const GemmPlan& plan, 
   planes_.ensure(per_item * chunk);
   for (int item0 = 0; item0 < plan.batch; item0 += chunk) {
     int n = std::min(chunk, plan.batch - item0);
-    run_mma(A, B, plan, item0, n, nsplit, Kc);
+    run_mma(A, B, plan, item0, n, nsplit, Kc, symmetric);
     CarryArgs c;
     memset(&c, 0, sizeof(c));
     c.planes = planes_.as<int32_t>();
+    c.sym_bn = symmetric ? BN : 0;
     c.stack = stack;
     c.mip = 128 / stack;
     c.Mpad = Mpad;
@@ -1011,7 +1048,7 @@ void GemmEngine::planes_only(const Slice& A, const Slice& B, const GemmPlan& pla
   const int n4 = (plan.N + 3) / 4;
   size_t bytes = (size_t)T * plan.batch * Mpad * n4 * 4 * sizeof(int32_t);
   planes_.ensure(bytes);
-  run_mma(A, B, plan, 0, plan.batch, 1, A.Kp);
+  run_mma(A, B, plan, 0, plan.batch, 1, A.Kp, false);
   std::vector<int32_t> blk(bytes / sizeof(int32_t));
   CLR_CUDA(cudaMemcpyAsync(blk.data(), planes_.p, bytes, cudaMemcpyDeviceToHost, ctx_.stream));
   ctx_.sync();

@@ -58,8 +58,10 @@ class GemmEngine {
   GemmEngine(Ctx& c, int nl);
   void slice(const OperandDesc& op, Slice& out);
   // C = A * B (row-operand form) with optional epilogue; E uses C's addressing on tensor `extra`
+  // `symmetric` (same slice on both sides, C = A A^T): only the tiles touching the upper triangle are computed, the
+  // carry kernel mirrors them
   void multiply(const Slice& A, const Slice& B, const GemmPlan& plan, const OutDesc& C, int epi = EPI_STORE,
-                const mp::Tensor* extra = nullptr);
+                const mp::Tensor* extra = nullptr, bool symmetric = false);
   // exact integer planes for tests: planes [T][batch][M][N] (splits already summed must be 1)
   void planes_only(const Slice& A, const Slice& B, const GemmPlan& plan, int32_t* h_planes, int* T_out);
   int digits() const { return S_; }
@@ -68,10 +70,11 @@ class GemmEngine {
   double last_int8_macs = 0;  // executed digit-product MACs of the last multiply (incl. guard digits)
 
  private:
-  void run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, int item0, int nitems, int nsplit, int Kc);
+  void run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, int item0, int nitems, int nsplit, int Kc, bool symmetric);
   Ctx& ctx_;
   int nl_, S_;
-  DevBuf planes_;
+  DevBuf planes_, sym_map_;
+  size_t sym_map_host_ = 0;
   size_t planes_cap_ = 0;
 };
 

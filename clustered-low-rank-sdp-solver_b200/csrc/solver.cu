@@ -903,7 +903,7 @@ void Solver::decomposition() {
     OutDesc o;
     o.dst = Q.t();
     o.rs = n_y, o.cs = 1;
-    gemm_->multiply(sW, sW, plan_of(1, n_y, n_y), o);
+    gemm_->multiply(sW, sW, plan_of(1, n_y, n_y), o, EPI_STORE, nullptr, true);  // symmetric: upper tiles only
     allreduce(Q, 0, (int64_t)n_y * n_y, COMB_SUM);  // the cross-cluster reduction (sum(Q), :1494)
   }
   mark(-1 - CLRSDP_T_Q);
