@@ -524,9 +524,9 @@ void Solver::build_static_slices() {
     a.d_off = dv.as<int64_t>();
     a.batch = nblk;
     a.rows = g.Nv, a.K = g.delta, a.rs = g.delta, a.ks = 1;  // rows = vectors
-    gemm_->slice(a, g.sVt);
+    ge()->slice(a, g.sVt);
     a.rows = g.delta, a.K = g.Nv, a.rs = 1, a.ks = g.delta;  // rows = basis index, K = vectors
-    gemm_->slice(a, g.sVr);
+    ge()->slice(a, g.sVr);
     ctx.sync();
   }
   for (auto& g : cgroups_) {
@@ -535,7 +535,7 @@ void Solver::build_static_slices() {
     a.d_off = g.offBt.as<int64_t>();
     a.batch = (int)g.clusters.size();
     a.rows = n_y, a.K = g.dimS, a.rs = 1, a.ks = n_y;  // rows = columns of B_j
-    gemm_->slice(a, g.sBt);
+    ge()->slice(a, g.sBt);
   }
   ctx.sync();
 }
@@ -676,7 +676,7 @@ void Solver::product(GemmEngine* ge, Slice& sa, Slice& sb, const OperandDesc& a,
 void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv,
                           int* d_stat, bool want_u, bool side) {
   const int n = A.n, batch = A.batch;
-  GemmEngine* gemm_ = side ? this->gemm_side_.get() : this->gemm_.get();
+  GemmEngine* gemm_loc = side ? this->gemm_side_.get() : this->gemm_.get();
   Slice& fs1_ = side ? this->fs1s_ : this->fs1_;
   Slice& fs2_ = side ? this->fs2s_ : this->fs2_;
   MpBuf& tscr = side ? this->tscr_side_ : this->tscr;
@@ -702,7 +702,7 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
       if ((int64_t)batch * wk * n2 * wk <= SMALL_GEMM_PMAC) {
         OutDesc os;
         os.dst = tscr.t(), os.bstride = (int64_t)PANEL * n, os.rs = n2, os.cs = 1;
-        product(gemm_, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), op_cols(Uw, k0, k0 + wk, n2, wk), wk, n2, os, EPI_STORE,
+        product(gemm_loc, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), op_cols(Uw, k0, k0 + wk, n2, wk), wk, n2, os, EPI_STORE,
                 nullptr);
         SmallGemmArgs cp;
         cp.A = tscr.t(), cp.abs_ = (int64_t)PANEL * n, cp.ars = n2, cp.aks = 1;
@@ -711,13 +711,13 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
         cp.batch = batch, cp.M = wk, cp.N = n2;
         rect_copy(ctx, nl, cp);
       } else {
-        product(gemm_, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), op_cols(Uw, k0, k0 + wk, n2, wk), wk, n2,
+        product(gemm_loc, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), op_cols(Uw, k0, k0 + wk, n2, wk), wk, n2,
                 out_sub(Uw, k0, k0 + wk), EPI_STORE, nullptr);
       }
       // A22 -= U12^T U12
       mp::Tensor ut = Uw.t;
       OperandDesc u12 = op_cols(Uw, k0, k0 + wk, n2, wk);
-      product(gemm_, fs2_, fs2_, u12, u12, n2, n2, out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
+      product(gemm_loc, fs2_, fs2_, u12, u12, n2, n2, out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
     }
   }
   // off-diagonal panels of L^-1:  Linv[p, 0:k0] = -Linv_pp * ( L[p, 0:k0] * Linv[0:k0, 0:k0] )
@@ -726,19 +726,19 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
     // T[i][c] = sum_r U[r][k0+i] * Linv[r][c], stored transposed: Tt[c][i]
     OutDesc ot;
     ot.dst = tscr.t(), ot.bstride = (int64_t)PANEL * n, ot.rs = 1, ot.cs = wk;
-    product(gemm_, fs1_, fs2_, op_cols(Uw, 0, k0, wk, k0), op_cols(Linv, 0, 0, k0, k0), wk, k0, ot, EPI_STORE, nullptr);
+    product(gemm_loc, fs1_, fs2_, op_cols(Uw, 0, k0, wk, k0), op_cols(Linv, 0, 0, k0, k0), wk, k0, ot, EPI_STORE, nullptr);
     OperandDesc tb;
     tb.src = tscr.t(), tb.batch = batch, tb.bstride = (int64_t)PANEL * n, tb.rs = wk, tb.ks = 1, tb.rows = k0, tb.K = wk;
-    product(gemm_, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), tb, wk, k0, out_sub(Linv, k0, 0), EPI_NEG, nullptr);
+    product(gemm_loc, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), tb, wk, k0, out_sub(Linv, k0, 0), EPI_NEG, nullptr);
   }
 }
 
 // XY = X*Y per block (kept: both residual_R calls use it, MPMP.jl:1195,1209)
 void Solver::block_products_XY() {
   for (auto& g : bgroups_) {
-    gemm_->slice(rows_of(g, X), g.sX);
-    gemm_->slice(rows_of(g, Y), g.sY);  // Y symmetric: its rows are its columns
-    gemm_->multiply(g.sX, g.sY, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, XY));
+    ge()->slice(rows_of(g, X), g.sX);
+    ge()->slice(rows_of(g, Y), g.sY);  // Y symmetric: its rows are its columns
+    ge()->multiply(g.sX, g.sY, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, XY));
   }
 }
 
@@ -755,8 +755,8 @@ void Solver::factor_XY() {
 // X^-1 = Lx^-T Lx^-1 (spd_inv!, MPMP.jl:766)
 void Solver::invert_X() {
   for (auto& g : bgroups_) {
-    gemm_->slice(cols_of(g, Linvx), g.sA);  // row operand i = column i of L^-1
-    gemm_->multiply(g.sA, g.sA, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, Xinv));
+    ge()->slice(cols_of(g, Linvx), g.sA);  // row operand i = column i of L^-1
+    ge()->multiply(g.sA, g.sA, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, Xinv));
   }
 }
 
@@ -771,14 +771,14 @@ void Solver::first_gemm_Tt(BlockGroup& g, MpBuf& M, Slice* cached) {
     a.d_off = g.g1_offA.as<int64_t>();
     a.batch = nblk * m * m;
     a.rows = g.delta, a.K = g.delta, a.rs = g.nb, a.ks = 1;
-    gemm_->slice(a, g.sB);
+    ge()->slice(a, g.sB);
     As = &g.sB;
   }
   OutDesc o;
   o.dst = Tt.t();
   o.d_off = g.g1_offC.as<int64_t>();
   o.rs = 1, o.cs = g.delta;  // C[i][b] -> Tt[b*delta + i]
-  gemm_->multiply(*As, g.sVt, plan_of(nblk * m * m, g.delta, g.Nv, nullptr, g.g1_rowB.as<int>()), o);
+  ge()->multiply(*As, g.sVt, plan_of(nblk * m * m, g.delta, g.Nv, nullptr, g.g1_rowB.as<int>()), o);
 }
 
 // bilinear pairings  P[(r,a),(s,b)] = v_a^T M[r,s] v_b  (MPMP.jl:1274-1318)
@@ -788,10 +788,10 @@ void Solver::pairings(MpBuf& M, bool is_xinv, MpBuf& Pout) {
     Slice* cached = nullptr;
     if (m == 1) {
       Slice& s = is_xinv ? g.sXinv : g.sY;
-      if (is_xinv) gemm_->slice(rows_of(g, M), s);  // sY was sliced for X*Y already
+      if (is_xinv) ge()->slice(rows_of(g, M), s);  // sY was sliced for X*Y already
       cached = &s;
     } else if (is_xinv) {
-      gemm_->slice(rows_of(g, M), g.sXinv);  // still needed by the search directions
+      ge()->slice(rows_of(g, M), g.sXinv);  // still needed by the search directions
     }
     first_gemm_Tt(g, M, cached);
     OperandDesc bdesc;
@@ -799,12 +799,12 @@ void Solver::pairings(MpBuf& M, bool is_xinv, MpBuf& Pout) {
     bdesc.d_off = g.g2_offB.as<int64_t>();
     bdesc.batch = nblk * m;
     bdesc.rows = m * g.Nv, bdesc.K = g.delta, bdesc.rs = g.delta, bdesc.ks = 1;
-    gemm_->slice(bdesc, g.sB);
+    ge()->slice(bdesc, g.sB);
     OutDesc o;
     o.dst = Pout.t();
     o.d_off = g.g2_offC.as<int64_t>();
     o.rs = m * g.Nv, o.cs = 1;
-    gemm_->multiply(g.sVt, g.sB, plan_of(nblk * m, g.Nv, m * g.Nv, g.g2_rowA.as<int>(), nullptr), o);
+    ge()->multiply(g.sVt, g.sB, plan_of(nblk * m, g.Nv, m * g.Nv, g.g2_rowA.as<int>(), nullptr), o);
   }
 }
 
@@ -818,12 +818,12 @@ void Solver::weighted_A(MpBuf& a, MpBuf& out, MpBuf& E, int sign) {
     ad.d_off = g.wa_offA.as<int64_t>();
     ad.batch = nblk * g.np;
     ad.rows = g.delta, ad.K = g.Nv, ad.rs = g.Nv, ad.ks = 1;
-    gemm_->slice(ad, g.sB);
+    ge()->slice(ad, g.sB);
     OutDesc o;
     o.dst = QP.t();
     o.d_off = g.wa_offC.as<int64_t>();
     o.rs = g.delta, o.cs = 1;
-    gemm_->multiply(g.sB, g.sVr, plan_of(nblk * g.np, g.delta, g.delta, nullptr, g.wa_rowB.as<int>()), o);
+    ge()->multiply(g.sB, g.sVr, plan_of(nblk * g.np, g.delta, g.delta, nullptr, g.wa_rowB.as<int>()), o);
   }
   assemble_weighted(ctx, nl, st_, QP.t(), out.t(), E.t(), sign, blkN, nullptr);
 }
@@ -862,8 +862,7 @@ void Solver::compute_residuals(bool from_pairings) {
 // compute_T_decomposition (MPMP.jl:1417-1514) with Cholesky instead of LU (S and Q are SPD, :1430-1432)
 void Solver::decomposition() {
   mark(CLRSDP_T_SCHUR);
-  pairings(Xinv, true, Px);
-  pairings(Y, false, Py);
+  pairings(Xinv, true, Px);  // (the pairings with Y were formed on the side stream, see iteration_body)
   schur_assemble(ctx, nl, st_, Px.t(), Py.t(), H.t(), S.t(), sN);
   mark(-1 - CLRSDP_T_SCHUR);
   mark(CLRSDP_T_CHOL_S);
@@ -885,12 +884,12 @@ void Solver::decomposition() {
     bd.d_off = g.offS.as<int64_t>();
     bd.batch = (int)g.clusters.size();
     bd.rows = g.dimS, bd.K = g.dimS, bd.rs = g.dimS, bd.ks = 1;
-    gemm_->slice(bd, g.sLinv);
+    ge()->slice(bd, g.sLinv);
     OutDesc o;
     o.dst = Wt.t();
     o.d_off = g.offW.as<int64_t>();
     o.rs = sumS, o.cs = 1;
-    gemm_->multiply(g.sBt, g.sLinv, plan_of((int)g.clusters.size(), n_y, g.dimS), o);
+    ge()->multiply(g.sBt, g.sLinv, plan_of((int)g.clusters.size(), n_y, g.dimS), o);
   }
   mark(-1 - CLRSDP_T_CINVB);
   mark(CLRSDP_T_Q);
@@ -899,11 +898,11 @@ void Solver::decomposition() {
     OperandDesc a;
     a.src = Wt.t();
     a.batch = 1, a.rows = n_y, a.K = sumS, a.rs = sumS, a.ks = 1;
-    gemm_->slice(a, sW);
+    ge()->slice(a, sW);
     OutDesc o;
     o.dst = Q.t();
     o.rs = n_y, o.cs = 1;
-    gemm_->multiply(sW, sW, plan_of(1, n_y, n_y), o, EPI_STORE, nullptr, true);  // symmetric: upper tiles only
+    ge()->multiply(sW, sW, plan_of(1, n_y, n_y), o, EPI_STORE, nullptr, true);  // symmetric: upper tiles only
     allreduce(Q, 0, (int64_t)n_y * n_y, COMB_SUM);  // the cross-cluster reduction (sum(Q), :1494)
   }
   mark(-1 - CLRSDP_T_Q);
@@ -926,11 +925,11 @@ void Solver::search_direction() {
   mark(CLRSDP_T_Z);
   for (auto& g : bgroups_) {  // Z = sym(X^-1 (P Y - R))
     int nblk = (int)g.blocks.size();
-    gemm_->slice(rows_of(g, P), g.sA);
+    ge()->slice(rows_of(g, P), g.sA);
     mp::Tensor Rt = R.t();
-    gemm_->multiply(g.sA, g.sY, plan_of(nblk, g.nb, g.nb), out_blk(g, T1), EPI_MINUS_SUB, &Rt);
-    gemm_->slice(cols_of(g, T1), g.sB);
-    gemm_->multiply(g.sXinv, g.sB, plan_of(nblk, g.nb, g.nb), out_blk(g, T2));
+    ge()->multiply(g.sA, g.sY, plan_of(nblk, g.nb, g.nb), out_blk(g, T1), EPI_MINUS_SUB, &Rt);
+    ge()->slice(cols_of(g, T1), g.sB);
+    ge()->multiply(g.sXinv, g.sB, plan_of(nblk, g.nb, g.nb), out_blk(g, T2));
     ew_symmetrize(ctx, nl, blkbatch(g, Z), T2.t());
   }
   mark(-1 - CLRSDP_T_Z);
@@ -984,11 +983,11 @@ void Solver::search_direction() {
   mark(CLRSDP_T_DY);
   for (auto& g : bgroups_) {  // dY = sym(X^-1 (R - dX Y))
     int nblk = (int)g.blocks.size();
-    gemm_->slice(rows_of(g, dX), g.sA);
+    ge()->slice(rows_of(g, dX), g.sA);
     mp::Tensor Rt = R.t();
-    gemm_->multiply(g.sA, g.sY, plan_of(nblk, g.nb, g.nb), out_blk(g, T1), EPI_SUB_FROM, &Rt);
-    gemm_->slice(cols_of(g, T1), g.sB);
-    gemm_->multiply(g.sXinv, g.sB, plan_of(nblk, g.nb, g.nb), out_blk(g, T2));
+    ge()->multiply(g.sA, g.sY, plan_of(nblk, g.nb, g.nb), out_blk(g, T1), EPI_SUB_FROM, &Rt);
+    ge()->slice(cols_of(g, T1), g.sB);
+    ge()->multiply(g.sXinv, g.sB, plan_of(nblk, g.nb, g.nb), out_blk(g, T2));
     ew_symmetrize(ctx, nl, blkbatch(g, dY), T2.t());
   }
   mark(-1 - CLRSDP_T_DY);
@@ -1000,17 +999,17 @@ void Solver::step_lengths() {
     int nb2 = 2 * (int)g.blocks.size();
     OperandDesc a;
     a.src = dXY2.t(), a.d_off = g.offBlk2.as<int64_t>(), a.batch = nb2, a.rows = g.nb, a.K = g.nb, a.rs = g.nb, a.ks = 1;
-    gemm_->slice(a, g.sA);
+    ge()->slice(a, g.sA);
     a.src = Linv2.t();
-    gemm_->slice(a, g.sLinv);
+    ge()->slice(a, g.sLinv);
     // T[i][j] = sum_k dM[i][k] Linv[j][k], stored transposed
     OutDesc o;
     o.dst = T1d.t(), o.d_off = g.offBlk2.as<int64_t>(), o.rs = 1, o.cs = g.nb;
-    gemm_->multiply(g.sA, g.sLinv, plan_of(nb2, g.nb, g.nb), o);
+    ge()->multiply(g.sA, g.sLinv, plan_of(nb2, g.nb, g.nb), o);
     a.src = T1d.t();
-    gemm_->slice(a, g.sB);
+    ge()->slice(a, g.sB);
     o.dst = T2d.t(), o.rs = g.nb, o.cs = 1;
-    gemm_->multiply(g.sLinv, g.sB, plan_of(nb2, g.nb, g.nb), o);
+    ge()->multiply(g.sLinv, g.sB, plan_of(nb2, g.nb, g.nb), o);
     ew_symmetrize(ctx, nl, blkbatch2(g, W2), T2d.t());
     lambda_min(ctx, nl, blkbatch2(g, W2), lam.t(), g.lamIdx2.as<int>(), d_lamflag.as<int>());
   }
@@ -1026,11 +1025,13 @@ void Solver::fork_side() {
   CLR_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
   main_stream_ = ctx.stream;
   ctx.stream = side_stream_;
+  on_side_ = true;
 }
 void Solver::end_side() {
   if (!use_side_) return;
   CLR_CUDA(cudaEventRecord(ev_join_, ctx.stream));
   ctx.stream = main_stream_;
+  on_side_ = false;
   join_pending_ = true;
 }
 void Solver::join_side() {
@@ -1151,15 +1152,20 @@ void Solver::iteration_body() {
   reduce_dot(ctx, nl, X.t(), 0, Y.t(), 0, blkN, scal.t(), SL_DOT_XY, work.t());
   allreduce(scal, SL_DOT_XY, 1, COMB_SUM);
   scalar_program(ctx, nl, SP_MU, scal.t(), d_flags.as<int>(), nullptr);
-  // step 4: R = mu_p I - X Y
+  // step 4: R = mu_p I - X Y, and the pairings with Y: neither needs X^-1, so they run on the side stream beside the
+  // factorisations of X and Y (a latency chain) and the product X^-1 = L^-T L^-1
+  fork_side();
   mark(CLRSDP_T_R);
   block_products_XY();
   for (auto& g : bgroups_) ew_residual_R(ctx, nl, blkbatch(g, R), scal.t(), SL_MU_P, XY.t(), nullptr);
   mark(-1 - CLRSDP_T_R);
+  pairings(Y, false, Py);
+  end_side();
   mark(CLRSDP_T_XINV);
   factor_XY();
   invert_X();
   mark(-1 - CLRSDP_T_XINV);
+  join_side();
   mark(CLRSDP_T_DECOMP);
   decomposition();
   mark(-1 - CLRSDP_T_DECOMP);
@@ -1180,9 +1186,9 @@ void Solver::iteration_body() {
   // step 6: R = mu_c I - X Y - dX dY
   mark(CLRSDP_T_R);
   for (auto& g : bgroups_) {
-    gemm_->slice(rows_of(g, dX), g.sA);
-    gemm_->slice(rows_of(g, dY), g.sB);  // dY symmetric
-    gemm_->multiply(g.sA, g.sB, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, T1));
+    ge()->slice(rows_of(g, dX), g.sA);
+    ge()->slice(rows_of(g, dY), g.sB);  // dY symmetric
+    ge()->multiply(g.sA, g.sB, plan_of((int)g.blocks.size(), g.nb, g.nb), out_blk(g, T1));
     mp::Tensor t1 = T1.t();
     ew_residual_R(ctx, nl, blkbatch(g, R), scal.t(), SL_MU_C, XY.t(), &t1);
   }
@@ -1213,6 +1219,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   CLR_CUDA(cudaSetDevice(ctx.device));
   double t0 = now_s();
   if (main_stream_) ctx.stream = main_stream_;  // a failed iteration may have left the side stream selected
+  on_side_ = false;
   join_pending_ = false;
   ev_marks_.clear();
   CLR_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int) * n_status, ctx.stream));
@@ -1392,11 +1399,11 @@ void Solver::op_gemm(int batch, int M, int N, int K, const clrsdp_mp* A, const c
   ad.src = a.t(), ad.batch = batch, ad.rows = M, ad.K = K, ad.rs = K, ad.ks = 1, ad.bstride = (int64_t)M * K;
   bd.src = b2.t(), bd.batch = batch, bd.rows = N, bd.K = K, bd.rs = 1, bd.ks = N, bd.bstride = (int64_t)K * N;
   Slice sa, sb;
-  gemm_->slice(ad, sa);
-  gemm_->slice(bd, sb);
+  ge()->slice(ad, sa);
+  ge()->slice(bd, sb);
   OutDesc o;
   o.dst = c2.t(), o.bstride = (int64_t)M * N, o.rs = N, o.cs = 1;
-  gemm_->multiply(sa, sb, plan_of(batch, M, N), o);
+  ge()->multiply(sa, sb, plan_of(batch, M, N), o);
   ctx.sync();
   to_host(c2, 0, (int64_t)batch * M * N, C, 0);
 }
@@ -1411,12 +1418,12 @@ void Solver::op_gemm_planes(int batch, int M, int N, int K, const clrsdp_mp* A, 
   ad.src = a.t(), ad.batch = batch, ad.rows = M, ad.K = K, ad.rs = K, ad.ks = 1, ad.bstride = (int64_t)M * K;
   bd.src = b2.t(), bd.batch = batch, bd.rows = N, bd.K = K, bd.rs = 1, bd.ks = N, bd.bstride = (int64_t)K * N;
   Slice sa, sb;
-  gemm_->slice(ad, sa);
-  gemm_->slice(bd, sb);
-  if (*n_planes < gemm_->digits()) throw SolverError(CLRSDP_ERR_BAD_ARG, "op_gemm_planes: plane buffer too small");
+  ge()->slice(ad, sa);
+  ge()->slice(bd, sb);
+  if (*n_planes < ge()->digits()) throw SolverError(CLRSDP_ERR_BAD_ARG, "op_gemm_planes: plane buffer too small");
   int T = 0;
-  std::vector<int32_t> tmp((size_t)gemm_->digits() * batch * M * N);
-  gemm_->planes_only(sa, sb, plan_of(batch, M, N), tmp.data(), &T);
+  std::vector<int32_t> tmp((size_t)ge()->digits() * batch * M * N);
+  ge()->planes_only(sa, sb, plan_of(batch, M, N), tmp.data(), &T);
   memcpy(planes, tmp.data(), tmp.size() * sizeof(int32_t));
   *n_planes = T;
   CLR_CUDA(cudaMemcpy(row_exp, sa.exps.p, sizeof(int32_t) * batch * M, cudaMemcpyDeviceToHost));

@@ -126,7 +126,8 @@ class Solver {
   std::unique_ptr<GemmEngine> gemm_, gemm_side_;
   cudaStream_t side_stream_ = nullptr, main_stream_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
-  bool use_side_ = true, join_pending_ = false;
+  bool use_side_ = true, join_pending_ = false, on_side_ = false;
+  GemmEngine* ge() { return on_side_ ? gemm_side_.get() : gemm_.get(); }
   Slice fs1s_, fs2s_;
   MpBuf tscr_side_;
   Comm comm_;
