@@ -22,6 +22,7 @@ struct GatherArgs {
   const int64_t* d_off;
   int64_t off0, bstride, rs, ks;
   int batch, rows, K, Kp, rows_total;
+  const int* kshift;  // optional [batch][K]: entry (b, r, k) is taken as x * 2^-kshift[b*K + k] (exact)
 };
 
 __device__ __forceinline__ int64_t item_off(const GatherArgs& g, int b) {
@@ -43,6 +44,7 @@ __device__ __forceinline__ void slice_entry(const GatherArgs& g, int row, int k,
     int64_t at = item_off(g, b) + (int64_t)r * g.rs + (int64_t)k * g.ks;
     mp::Num<NL> x = mp::load<NL>(g.w, g.n, (size_t)at);
     if (!mp::is_zero(x)) {
+      if (g.kshift) x.e -= g.kshift[b * g.K + k];
       uint32_t d = (uint32_t)(rexp - x.e);
       uint32_t sr = 32u * NLW - 8u * S + 2u + d;
       if (sr < 32u * NLW) {
@@ -97,6 +99,7 @@ __device__ __forceinline__ void slice_entry4(const GatherArgs& g, int row, int k
     if (k < g.K) {
       mp::Num<NL> x = mp::load<NL>(g.w, g.n, (size_t)(base + (int64_t)k * g.ks));
       if (!mp::is_zero(x)) {
+        if (g.kshift) x.e -= g.kshift[b * g.K + k];
         uint32_t d = (uint32_t)(rexp - x.e);
         uint32_t sr = 32u * NLW - 8u * S + 2u + d;
         if (sr < 32u * NLW) {
@@ -143,10 +146,19 @@ __global__ void __launch_bounds__(SLICE_THREADS, 3) slice_rows_kernel(GatherArgs
     const bool live = row < g.rows_total;
     int32_t mx = mp::EXP_ZERO;
     int64_t base = 0;
+    int b = 0;
     if (live) {
-      int b = row / g.rows, r = row % g.rows;
+      b = row / g.rows;
+      const int r = row % g.rows;
       base = item_off(g, b) + (int64_t)r * g.rs;
-      for (int k = sub * 32 + lane; k < g.K; k += 32 * wpr) mx = max(mx, ((int32_t)hdr[base + (int64_t)k * g.ks]) >> 1);
+      if (g.kshift) {
+        for (int k = sub * 32 + lane; k < g.K; k += 32 * wpr) {
+          int32_t e = ((int32_t)hdr[base + (int64_t)k * g.ks]) >> 1;
+          if (e != mp::EXP_ZERO) mx = max(mx, e - g.kshift[b * g.K + k]);
+        }
+      } else {
+        for (int k = sub * 32 + lane; k < g.K; k += 32 * wpr) mx = max(mx, ((int32_t)hdr[base + (int64_t)k * g.ks]) >> 1);
+      }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -777,7 +789,7 @@ static void slice_impl(Ctx& ctx, const OperandDesc& op, Slice& out) {
   size_t bytes = (size_t)S * out.rows_total * Kp;
   out.digits.ensure(bytes);
   out.exps.ensure(sizeof(int32_t) * (size_t)std::max(out.rows_total, 1));
-  GatherArgs g{op.src.w, op.src.n, op.d_off, op.off0, op.bstride, op.rs, op.ks, op.batch, op.rows, K, Kp, out.rows_total};
+  GatherArgs g{op.src.w, op.src.n, op.d_off, op.off0, op.bstride, op.rs, op.ks, op.batch, op.rows, K, Kp, out.rows_total, op.d_kshift};
   int64_t total = (int64_t)out.rows_total * Kp;
   // long rows (or few of them) get a whole block per row, short rows one warp
   int wpr = (Kp > 256 || (int64_t)out.rows_total * 32 < (int64_t)ctx.sm_count * 256) ? 8 : 1;

@@ -24,6 +24,9 @@ struct OperandDesc {
   int64_t off0 = 0, bstride = 0;
   int64_t rs = 0, ks = 1;
   int batch = 1, rows = 0, K = 0;
+  // optional [batch][K] exponents: the operand is sliced as x(b, r, k) * 2^-d_kshift[b*K + k] (exact scaling of the
+  // contraction index, e.g. D^-1 B with the equilibration D of the matrix that B is multiplied into)
+  const int* d_kshift = nullptr;
 };
 // destination of a product: element (b, i, j) at off(b) + i*rs + j*cs, off(b) as above
 struct OutDesc {

@@ -229,7 +229,7 @@ template <int NL>
 __global__ void __launch_bounds__(PANEL_THREADS)
 panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shiftA, int ldA, mp::Tensor Lm,
                     const int64_t* __restrict__ offL, int64_t shiftL, int ldL, int w, int write_u,
-                    int* __restrict__ status) {
+                    int* __restrict__ status, int relaxed) {
   extern __shared__ uint32_t sm[];
   const int ntri = w * (w + 1) / 2;
   uint32_t* Us = sm;                                  // packed upper triangle of the scaled work matrix R'
@@ -245,9 +245,18 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
     if (c <= r) smem_put<NL>(Gs, pk_g(r, c), (r == 0 && c == 0) ? mp::one<NL>() : mp::zero<NL>());
   }
   __syncthreads();
+  // `relaxed` (Schur complement and Q, which the reference factors by LU and never tests for definiteness,
+  // MPMP.jl:1436,1501): a pivot that is not above the rounding level of the equilibrated matrix, 2^-(p-16), is replaced
+  // by that level instead of ending the factorisation - a backward perturbation of the size of the rounding errors
+  // already in the matrix (what a pivoted LU does implicitly when the matrix is singular to working precision).
   if (tid == 0) {
     Num<NL> a = smem_get<NL>(Us, pk_u(w, 0, 0));
-    if (mp::is_zero(a) || a.neg) bad = 1;
+    if (relaxed) {
+      Num<NL> thr = mp::from_pow2<NL>(-(32 * NL - 16));
+      if (mp::is_zero(a) || a.neg || ncmp(a, thr) < 0) smem_put<NL>(Us, pk_u(w, 0, 0), thr);
+    } else if (mp::is_zero(a) || a.neg) {
+      bad = 1;
+    }
   }
   __syncthreads();
   for (int k = 0; k + 1 < w && !bad; k++) {
@@ -261,7 +270,12 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
       __syncwarp();
       if (lane == 0) {
         Num<NL> a = smem_get<NL>(Us, pk_u(w, r, r));
-        if (mp::is_zero(a) || a.neg) bad = 1;
+        if (relaxed) {  // the unpivoted rows carry the scale tau_{k+1} = mu_k tau_k
+          Num<NL> thr = mp::mul_2exp(nmul(mu, smem_get<NL>(Gs, pk_g(k, k))), -(32 * NL - 16));
+          if (mp::is_zero(a) || a.neg || ncmp(a, thr) < 0) smem_put<NL>(Us, pk_u(w, r, r), thr);
+        } else if (mp::is_zero(a) || a.neg) {
+          bad = 1;
+        }
       }
     } else {
       // the common diagonal of the unpivoted rows of G': tau_{k+1} = mu_k tau_k (only row k+1's slot is kept)
@@ -303,7 +317,7 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
   if (tid == 0) status[b] = bad;
 }
 int panel_width(int nl) { (void)nl; return PANEL_W; }
-void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status) {
+void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status, bool relaxed) {
   if (A.n > panel_width(nl)) throw SolverError(-1, "panel_factor: block larger than the panel width");
   DISPATCH_NL(nl, {
     size_t words = ((size_t)A.n * (A.n + 1) + A.n) * (NL + 2);
@@ -316,7 +330,7 @@ void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, boo
     int tk = ctx.begin(nm.c_str());
     panel_factor_kernel<NL><<<A.batch, PANEL_THREADS, words * sizeof(uint32_t), ctx.stream>>>(
         A.t, A.d_off, A.shift, A.stride(), Linv.t, Linv.d_off, Linv.shift, Linv.stride(), A.n, write_u ? 1 : 0,
-        d_status);
+        d_status, relaxed ? 1 : 0);
     ctx.end(tk);
   });
 }
@@ -1252,6 +1266,107 @@ void mat_copy(Ctx& ctx, int nl, const MatBatch& dst, const MatBatch& src, bool u
                                                                      dst.n, upper_only ? 1 : 0);
     ctx.end(tk);
   });
+}
+// ---- symmetric equilibration by powers of two (exact) --------------------------------------------------------
+// s[b*n + i] = ceil(exponent(A_ii) / 2): A' = D^-1 A D^-1 with D = diag(2^s) has its diagonal in [1/4, 1) (0 if A_ii <= 0:
+// the factorisation then reports the matrix as not positive definite).
+template <int NL>
+__global__ void equil_exponents_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shA, int ldA, int batch, int n,
+                                       int* __restrict__ s) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * n) return;
+  int b = idx / n, i = idx - b * n;
+  uint32_t h = A.w[(size_t)NL * A.n + offA[b] + shA + (int64_t)i * ldA + i];
+  int32_t e = ((int32_t)h) >> 1;
+  s[idx] = (e == mp::EXP_ZERO) ? 0 : ((e + 1) >> 1);  // arithmetic shift: ceil(e / 2) for either sign
+}
+// D = upper triangle (mode 1) or all (mode 0) of S, entry (r, c) scaled by 2^-(s_r + s_c)
+template <int NL>
+__global__ void mat_copy_scaled_kernel(mp::Tensor D, const int64_t* __restrict__ offD, int64_t shD, int ldD, mp::Tensor S,
+                                       const int64_t* __restrict__ offS, int64_t shS, int ldS, int batch, int n, int mode,
+                                       const int* __restrict__ sc) {
+  int64_t total = (int64_t)batch * n * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / ((int64_t)n * n));
+    int rem = (int)(idx % ((int64_t)n * n));
+    int r = rem / n, c = rem % n;
+    Num<NL> v = mp::zero<NL>();
+    if (mode == 0 || (mode == 1 && r <= c)) {
+      v = ldm<NL>(S, offS[b] + shS + (int64_t)r * ldS + c);
+      v = mp::mul_2exp(v, -(sc[b * n + r] + sc[b * n + c]));
+    }
+    stm<NL>(D, offD[b] + shD + (int64_t)r * ldD + c, v);
+  }
+}
+// M[r][c] *= 2^(sign * s_c): the column scaling that turns the factors of the equilibrated matrix into those of A
+template <int NL>
+__global__ void col_scale_kernel(mp::Tensor M, const int64_t* __restrict__ offM, int64_t shM, int ldM, int batch, int n, int sign,
+                                 const int* __restrict__ sc) {
+  int64_t total = (int64_t)batch * n * n;
+  uint32_t* hdr = M.w + (size_t)NL * M.n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / ((int64_t)n * n));
+    int rem = (int)(idx % ((int64_t)n * n));
+    int r = rem / n, c = rem % n;
+    const int64_t at = offM[b] + shM + (int64_t)r * ldM + c;
+    const uint32_t h = hdr[at];
+    const int32_t e = ((int32_t)h) >> 1;
+    if (e != mp::EXP_ZERO) hdr[at] = mp::pack_hdr(e + sign * sc[b * n + c], h & 1u);
+  }
+}
+void equil_exponents(Ctx& ctx, int nl, const MatBatch& A, int* d_scale) {
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("equil_exponents");
+    equil_exponents_kernel<NL><<<ceil_div((int64_t)A.batch * A.n, 128), 128, 0, ctx.stream>>>(A.t, A.d_off, A.shift, A.stride(),
+                                                                                               A.batch, A.n, d_scale);
+    ctx.end(tk);
+  });
+}
+void mat_copy_scaled(Ctx& ctx, int nl, const MatBatch& dst, const MatBatch& src, bool upper_only, const int* d_scale) {
+  int64_t total = (int64_t)dst.batch * dst.n * dst.n;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("mat_copy", (double)total * 4.0 * (NL + 1) * 2);
+    mat_copy_scaled_kernel<NL><<<ew_grid(ctx, total), 128, 0, ctx.stream>>>(dst.t, dst.d_off, dst.shift, dst.stride(), src.t,
+                                                                            src.d_off, src.shift, src.stride(), dst.batch,
+                                                                            dst.n, upper_only ? 1 : 0, d_scale);
+    ctx.end(tk);
+  });
+}
+void col_scale(Ctx& ctx, int nl, const MatBatch& M, int sign, const int* d_scale) {
+  int64_t total = (int64_t)M.batch * M.n * M.n;
+  DISPATCH_NL(nl, {
+    int tk = ctx.begin("col_scale", (double)total * 8.0);
+    col_scale_kernel<NL><<<ew_grid(ctx, total), 128, 0, ctx.stream>>>(M.t, M.d_off, M.shift, M.stride(), M.batch, M.n, sign, d_scale);
+    ctx.end(tk);
+  });
+}
+// v[off + i] *= 2^(sign * sc[i]) (headers only); scatter of the per-batch exponents into a vector indexed like x
+__global__ void vec_scale_kernel(uint32_t* __restrict__ hdr, int64_t n, int sign, const int* __restrict__ sc) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t h = hdr[i];
+    const int32_t e = ((int32_t)h) >> 1;
+    if (e != mp::EXP_ZERO) hdr[i] = mp::pack_hdr(e + sign * sc[i], h & 1u);
+  }
+}
+__global__ void scatter_scale_kernel(const int* __restrict__ src, int batch, int n, const int64_t* __restrict__ off,
+                                     int* __restrict__ dst) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * n) return;
+  int b = idx / n, i = idx - b * n;
+  dst[off[b] + i] = src[idx];
+}
+void vec_scale(Ctx& ctx, int nl, mp::Tensor v, int64_t off, int64_t n, int sign, const int* d_scale) {
+  if (n <= 0) return;
+  int tk = ctx.begin("vec_scale", (double)n * 12.0);
+  vec_scale_kernel<<<ew_grid(ctx, n), 128, 0, ctx.stream>>>(v.w + (size_t)nl * v.n + off, n, sign, d_scale);
+  ctx.end(tk);
+}
+void scatter_scale(Ctx& ctx, const int* d_src, int batch, int n, const int64_t* d_off, int* d_dst) {
+  int tk = ctx.begin("scatter_scale", (double)batch * n * 8.0);
+  scatter_scale_kernel<<<ceil_div((int64_t)batch * n, 128), 128, 0, ctx.stream>>>(d_src, batch, n, d_off, d_dst);
+  ctx.end(tk);
 }
 void mat_zero(Ctx& ctx, int nl, const MatBatch& dst) {
   int64_t total = (int64_t)dst.batch * dst.n * dst.n;

@@ -35,7 +35,10 @@ void tri_inverse(Ctx& ctx, int nl, const MatBatch& U, mp::Tensor rdiag, const Ma
 // Fused panel factorisation of w x w SPD blocks (w <= panel_width(nl)): A is overwritten by its upper Cholesky
 // factor U (if write_u) and Linv receives L^-1 = U^-T (lower); both may be sub-blocks of larger matrices.
 int panel_width(int nl);
-void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status);
+// `relaxed`: pivots at or below the rounding level 2^-(p-16) of the (equilibrated) block are raised to it instead of
+// reporting the matrix as not positive definite.
+void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status,
+                  bool relaxed = false);
 // smallest eigenvalue of each symmetric matrix (destroys W): out[out_off + b].
 // Replaces approx_eig_qr! + min over real parts (MPMP.jl:1857-1870) by Householder tridiagonalisation
 // + multisection with Sturm counts.
@@ -61,6 +64,15 @@ void ew_zero(Ctx& ctx, int nl, mp::Tensor t, int64_t off, int64_t n);
 // dst = src for a batch of (sub)matrices; with upper_only the strictly lower part of dst is zeroed instead
 void mat_copy(Ctx& ctx, int nl, const MatBatch& dst, const MatBatch& src, bool upper_only);
 void mat_zero(Ctx& ctx, int nl, const MatBatch& dst);
+// symmetric equilibration by exact powers of two: d_scale[b*n+i] = ceil(exponent(A_ii)/2); scaled copy
+// dst(r,c) = src(r,c) 2^-(s_r+s_c); M(r,c) *= 2^(sign*s_c). Cholesky in floating point is invariant under diagonal
+// scaling, the block-fixed-point GEMMs of the blocked factorisation are not: they see the equilibrated matrix.
+void equil_exponents(Ctx& ctx, int nl, const MatBatch& A, int* d_scale);
+void mat_copy_scaled(Ctx& ctx, int nl, const MatBatch& dst, const MatBatch& src, bool upper_only, const int* d_scale);
+void col_scale(Ctx& ctx, int nl, const MatBatch& M, int sign, const int* d_scale);
+// v[off + i] *= 2^(sign * d_scale[i]); d_dst[d_off[b] + i] = d_src[b*n + i]
+void vec_scale(Ctx& ctx, int nl, mp::Tensor v, int64_t off, int64_t n, int sign, const int* d_scale);
+void scatter_scale(Ctx& ctx, const int* d_src, int batch, int n, const int64_t* d_off, int* d_dst);
 // c[i] = a[i] (op) b[i], op in '+','-','*','/','s' (sqrt of a): the scalar arithmetic of mpf.cuh on the device
 void ew_binary(Ctx& ctx, int nl, int op, mp::Tensor c, mp::Tensor a, mp::Tensor b, int64_t n);
 

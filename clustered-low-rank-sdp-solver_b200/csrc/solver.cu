@@ -358,6 +358,7 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
   for (MpBuf* t : {&Q, &Uq, &Vq, &Linvq}) t->alloc((int64_t)n_y * n_y, nl);
   for (MpBuf* t : {&x, &dx, &d, &c, &rhs, &tvec, &tmpx, &trx, &dx_pred}) t->alloc(sumS, nl);
   for (MpBuf* t : {&y, &dy, &p, &b, &tmpy, &zvec, &dyr, &dy_pred}) t->alloc(n_y, nl);
+  xscale.ensure(sizeof(int) * (size_t)std::max(sumS, 1));
   int64_t maxrd = n_y;
   for (auto& g : bgroups_) maxrd = std::max<int64_t>(maxrd, (int64_t)g.blocks.size() * g.nb);
   for (auto& g : cgroups_) maxrd = std::max<int64_t>(maxrd, (int64_t)g.clusters.size() * g.dimS);
@@ -529,14 +530,7 @@ void Solver::build_static_slices() {
     ge()->slice(a, g.sVr);
     ctx.sync();
   }
-  for (auto& g : cgroups_) {
-    OperandDesc a;
-    a.src = Bmat.t();
-    a.d_off = g.offBt.as<int64_t>();
-    a.batch = (int)g.clusters.size();
-    a.rows = n_y, a.K = g.dimS, a.rs = 1, a.ks = n_y;  // rows = columns of B_j
-    ge()->slice(a, g.sBt);
-  }
+  // (the rows of B_j^T are sliced every iteration, scaled by that iteration's equilibration of S_j: decomposition())
   ctx.sync();
 }
 
@@ -674,7 +668,7 @@ void Solver::product(GemmEngine* ge, Slice& sa, Slice& sb, const OperandDesc& a,
 }
 
 void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv,
-                          int* d_stat, bool want_u, bool side) {
+                          int* d_stat, bool want_u, bool side, bool relaxed, int* d_keep_scale) {
   const int n = A.n, batch = A.batch;
   GemmEngine* gemm_loc = side ? this->gemm_side_.get() : this->gemm_.get();
   Slice& fs1_ = side ? this->fs1s_ : this->fs1_;
@@ -682,20 +676,28 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
   MpBuf& tscr = side ? this->tscr_side_ : this->tscr;
   const int PANEL = panel_width(nl);
   (void)Vw;
-  if (n <= PANEL && !want_u) {
-    panel_factor(ctx, nl, A, Linv, false, d_stat);  // A is only read
-    return;
-  }
-  mat_copy(ctx, nl, Uw, A, true);  // work on the upper triangle
+  // Equilibrate: A' = D^-1 A D^-1, D = diag(2^ceil(e_ii / 2)) (exact). The Schur complements of polynomial programmes
+  // are graded over hundreds of bits (diagonal 2^26 .. 2^290 at degree 40); floating-point Cholesky does not care, but
+  // the block-fixed-point GEMMs of the trailing updates keep a fixed window below each row maximum. On A' (unit-size
+  // diagonal, every entry below 1) that window is the right one. L^-1 = L'^-1 D^-1 and U = U' D afterwards.
+  // With d_keep_scale the exponents are left there and Linv stays L'^-1: a caller whose later products contract over
+  // the index of A scales the other operand by D^-1 instead (slicer's d_kshift), which keeps that index balanced.
+  DevBuf& scb = side ? this->equil_side_ : this->equil_;
+  if (!d_keep_scale) scb.ensure(sizeof(int) * (size_t)batch * n);
+  int* d_scale = d_keep_scale ? d_keep_scale : scb.as<int>();
+  equil_exponents(ctx, nl, A, d_scale);
+  mat_copy_scaled(ctx, nl, Uw, A, true, d_scale);  // work on the upper triangle of the equilibrated matrix
   if (n <= PANEL) {
-    panel_factor(ctx, nl, Uw, Linv, true, d_stat);
+    panel_factor(ctx, nl, Uw, Linv, want_u, d_stat, relaxed);
+    if (!d_keep_scale) col_scale(ctx, nl, Linv, -1, d_scale);
+    if (want_u) col_scale(ctx, nl, Uw, +1, d_scale);
     return;
   }
   mat_zero(ctx, nl, Linv);
   tscr.alloc(std::max<size_t>(tscr.n, (size_t)batch * PANEL * n), nl);
   for (int k0 = 0; k0 < n; k0 += PANEL) {
     const int wk = std::min(PANEL, n - k0), n2 = n - k0 - wk;
-    panel_factor(ctx, nl, Uw.sub(k0, k0, wk), Linv.sub(k0, k0, wk), want_u, d_stat);
+    panel_factor(ctx, nl, Uw.sub(k0, k0, wk), Linv.sub(k0, k0, wk), want_u, d_stat, relaxed);
     if (n2 > 0) {
       // U12 = L11^-1 A12 (overwrites A12). The CUDA-core kernel reads its operands while other threads store, so
       // there the product goes to scratch first; the tensor path slices its operands before it writes.
@@ -731,6 +733,8 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
     tb.src = tscr.t(), tb.batch = batch, tb.bstride = (int64_t)PANEL * n, tb.rs = wk, tb.ks = 1, tb.rows = k0, tb.K = wk;
     product(gemm_loc, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), tb, wk, k0, out_sub(Linv, k0, 0), EPI_NEG, nullptr);
   }
+  if (!d_keep_scale) col_scale(ctx, nl, Linv, -1, d_scale);
+  if (want_u) col_scale(ctx, nl, Uw, +1, d_scale);
 }
 
 // XY = X*Y per block (kept: both residual_R calls use it, MPMP.jl:1195,1209)
@@ -872,13 +876,25 @@ void Solver::decomposition() {
     MatBatch U{Us.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
     MatBatch V{Vs.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
     MatBatch Li{Linvs.t(), g.offS.as<int64_t>(), (int)g.clusters.size(), g.dimS};
-    chol_inverse(A, U, V, Li, d_status.as<int>() + sbase);
+    // Linvs holds L'^-1 of the equilibrated S' = D^-1 S D^-1; D (exponents in g.equil, and in xscale indexed like x)
+    // goes onto the other operand wherever the constraint index is contracted: L^-1 B = L'^-1 (D^-1 B) below,
+    // L^-1 rhs = L'^-1 (D^-1 rhs) and L^-T u = D^-1 (L'^-T u) in search_direction().
+    g.equil.ensure(sizeof(int) * g.clusters.size() * (size_t)g.dimS);
+    chol_inverse(A, U, V, Li, d_status.as<int>() + sbase, false, false, true, g.equil.as<int>());
+    scatter_scale(ctx, g.equil.as<int>(), (int)g.clusters.size(), g.dimS, g.offW.as<int64_t>(), xscale.as<int>());
     sbase += (int)g.clusters.size();
   }
   mark(-1 - CLRSDP_T_CHOL_S);
   mark(CLRSDP_T_CINVB);
   // Wt[a][(j,i)] = (L_j^-1 B_j)[i][a]
   for (auto& g : cgroups_) {
+    OperandDesc bt;  // rows a (n_y) of (D^-1 B_j)^T
+    bt.src = Bmat.t();
+    bt.d_off = g.offBt.as<int64_t>();
+    bt.batch = (int)g.clusters.size();
+    bt.rows = n_y, bt.K = g.dimS, bt.rs = 1, bt.ks = n_y;
+    bt.d_kshift = g.equil.as<int>();
+    ge()->slice(bt, g.sBt);
     OperandDesc bd;
     bd.src = Linvs.t();
     bd.d_off = g.offS.as<int64_t>();
@@ -914,7 +930,7 @@ void Solver::decomposition() {
   {
     MatBatch A{Q.t(), d_qoff.as<int64_t>(), 1, n_y}, U{Uq.t(), d_qoff.as<int64_t>(), 1, n_y};
     MatBatch V{Vq.t(), d_qoff.as<int64_t>(), 1, n_y}, Li{Linvq.t(), d_qoff.as<int64_t>(), 1, n_y};
-    chol_inverse(A, U, V, Li, d_status.as<int>() + 2 * (int)blocks_.size() + J, false, true);
+    chol_inverse(A, U, V, Li, d_status.as<int>() + 2 * (int)blocks_.size() + J, false, true, true);
   }
   mark(-1 - CLRSDP_T_CHOL_Q);
   end_side();
@@ -940,7 +956,8 @@ void Solver::search_direction() {
   mark(-1 - CLRSDP_T_RHS_X);
   mark(CLRSDP_T_SYS);
   {
-    // t_j = L_j^-1 rhs_j
+    // t_j = L_j^-1 rhs_j = L'_j^-1 (D_j^-1 rhs_j)
+    vec_scale(ctx, nl, rhs.t(), 0, sumS, -1, xscale.as<int>());
     GemvArgs a;
     a.A = Linvs.t(), a.x = rhs.t(), a.out = tvec.t();
     a.rows = sumS, a.K = 0;
@@ -975,6 +992,7 @@ void Solver::search_direction() {
     bt.x = tmpx.t(), bt.out = dx.t();
     bt.item_trans = 1;  // A_item[k][r]
     gemv(ctx, nl, bt, work.t());
+    vec_scale(ctx, nl, dx.t(), 0, sumS, -1, xscale.as<int>());  // L^-T = D^-1 L'^-T
   }
   mark(-1 - CLRSDP_T_SYS);
   mark(CLRSDP_T_DX);

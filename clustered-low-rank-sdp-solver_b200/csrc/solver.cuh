@@ -39,8 +39,9 @@ struct ClusterGroup {
   int dimS;
   std::vector<int> clusters;
   DevBuf offS, offBt, offW;
-  Slice sBt;    // static: rows a (n_y) of B_j^T, K = dimS
-  Slice sLinv;  // per iteration: rows of L_j^-1
+  Slice sBt;    // per iteration: rows a (n_y) of (D_j^-1 B_j)^T, K = dimS
+  Slice sLinv;  // per iteration: rows of L'_j^-1
+  DevBuf equil; // per iteration: [clusters][dimS] equilibration exponents of S_j (D_j = diag 2^s)
 };
 
 class Solver {
@@ -105,7 +106,7 @@ class Solver {
   // Linv = (chol A)^-1 for a batch of SPD matrices: blocked right-looking Cholesky, panels on the CUDA cores,
   // trailing updates and the off-diagonal inverse panels through the sliced tensor-core GEMM
   void chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv, int* d_status,
-                    bool want_u = false, bool side = false);
+                    bool want_u = false, bool side = false, bool relaxed = false, int* d_keep_scale = nullptr);
   void product(GemmEngine* ge, Slice& sa, Slice& sb, const OperandDesc& a, const OperandDesc& b, int M, int N,
                const OutDesc& c, int epi, const mp::Tensor* extra);
   // a second stream for work that is off the critical path (see decomposition())
@@ -122,6 +123,8 @@ class Solver {
   void drop_graph();
 
   std::vector<std::pair<const char*, size_t>> pinned_;  // host ranges registered through pin_host
+  DevBuf equil_, equil_side_;                          // equilibration exponents of chol_inverse
+  DevBuf xscale;                                       // [sumS] the exponents of the S_j, indexed like x
   DevBuf wire_se_;                                     // sign / exponent scratch of the pinned transfer path
   std::unique_ptr<GemmEngine> gemm_, gemm_side_;
   cudaStream_t side_stream_ = nullptr, main_stream_ = nullptr;

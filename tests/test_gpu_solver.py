@@ -255,3 +255,124 @@ def test_launch_counter_and_profile():
     assert h.launch_count() - n0 == sum(v["launches"] for v in prof.values()) > 100
     assert any(k.startswith("mma_planes") for k in prof)
     assert r.seconds > 0 and sum(r.timings) > 0
+
+
+def _sphere_golden(d):
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "sphere_packing_512.json")) as f:
+        return [c for c in json.load(f)["cases"] if c["d"] == d][0]
+
+
+def test_sphere_packing_config1_matches_oracle():
+    """BASELINE config 1 (examples/SpherePacking.jl, n = 3, d = 8) at the example's own precision, 512 bits (ex:29-31).
+    The Schur complements of this instance are graded over 2^60 and have condition numbers 2^126 (first iteration) to
+    beyond 2^240 (near the optimum) after equilibration, so two backward-stable methods agree to p - log2(cond) bits,
+    not to p - 16: per iteration the GPU result must be as close to the same iteration at p + 64 bits as the MPFR
+    oracle's (LU) is; over the whole solve: the same number of iterations as the oracle (live and golden), the same
+    log rows, and the objective to 2^-128."""
+    prec = 512
+    solver.set_precision(prec)
+    try:
+        cons, b, _ = instances.sphere_packing_2point(n=3, d=8, prec=prec)
+        bi = solver.get_block_info(cons)
+        assert (bi.J, bi.n_y) == (7, 52)                                         # SURVEY §8(d), cfg1
+        kw = dict(omega_p=100, omega_d=100)
+        hg, ho = pair(cons, b, bi, prec, **kw)
+        for it in range(2):
+            rg, ro = hg.iterate(), ho.iterate()
+            assert rg.alpha_p == pytest.approx(ro.alpha_p, rel=1e-12) and rg.alpha_d == pytest.approx(ro.alpha_d, rel=1e-12)
+            for name in ("dx", "dy", "x", "y"):
+                assert rel_err_bits(hg.fetch(name), ho.fetch(name)) >= prec - 16 - 130, name   # cond(S') = 2^126
+            for j in range(bi.J if it == 0 else 0):                               # the Schur complements of the common
+                assert rel_err_bits(hg.fetch("S", j), ho.fetch("S", j)) >= prec - 16   # starting point: full accuracy
+        g = _sphere_golden(8)
+        og, rg = solver.solverank1sdp(cons, b, bi, verbose=False, return_info=True, **kw)
+        oo, ro = solver.solverank1sdp(cons, b, bi, handle=oracle_handle(prec, 8), verbose=False, return_info=True, **kw)
+        assert len(rg) == len(ro) == g["iterations"]
+        assert rg[-1].terminate == ro[-1].terminate == 3
+        for a, o in zip(rg, ro):
+            assert a.alpha_p == pytest.approx(o.alpha_p, rel=1e-9) and a.alpha_d == pytest.approx(o.alpha_d, rel=1e-9)
+            assert a.mu == pytest.approx(o.mu, rel=1e-9)
+        with mpmath.workprec(prec):
+            tol = mpmath.mpf(2) ** -128
+            assert abs(og[8] - oo[8]) <= abs(oo[8]) * tol and abs(og[9] - oo[9]) <= abs(oo[9]) * tol
+            assert abs(og[8] - mpmath.mpf(g["primal_obj"])) <= tol
+            assert og[7] < mpmath.mpf(10) ** -15
+    finally:
+        solver.set_precision(256)
+
+
+def test_sphere_packing_higher_degree_known_answers():
+    """BASELINE config 2 (SpherePacking at higher polynomial degree on one B200). As specified (d = 40 at 256 bits) the
+    instance is out of reach of 256-bit arithmetic for ANY method: at the first iteration the equilibrated Schur
+    complement of the first cluster has condition number > 2^257 and the oracle's own S is indefinite to working
+    precision (measured with the oracle) - the example itself never runs below 512 bits (ex:29-31).
+    What is checked: (i) the higher degrees that 512 bits do support, against the oracle's golden runs: d = 12 takes
+    the same 91 iterations and gives the same objective; d = 16 (where the oracle needs 168 iterations, wandering at
+    its precision limit) reaches the same optimum; the bounds decrease with the degree towards ~0.813 and stay above
+    the literature value 0.793 (ex:125-126). (ii) d = 40 at 256 bits either raises the reference's "higher precision"
+    error or ends without claiming optimality - never a silent wrong bound."""
+    prec = 512
+    solver.set_precision(prec)
+    try:
+        bounds = {8: -mpmath.mpf(_sphere_golden(8)["primal_obj"])}
+        for d in (12, 16):
+            g = _sphere_golden(d)
+            cons, b, _ = instances.sphere_packing_2point(n=3, d=d, prec=prec)
+            bi = solver.get_block_info(cons)
+            og, rg = solver.solverank1sdp(cons, b, bi, verbose=False, return_info=True, omega_p=100, omega_d=100)
+            assert rg[-1].terminate == 3
+            if d == 12:
+                assert len(rg) == g["iterations"]
+            with mpmath.workprec(prec):
+                assert abs(og[8] - mpmath.mpf(g["primal_obj"])) < mpmath.mpf(10) ** -15   # the duality-gap threshold
+                assert og[7] < mpmath.mpf(10) ** -15
+                bounds[d] = -og[8]
+        assert mpmath.mpf("0.793") <= bounds[16] < bounds[12] < bounds[8] < mpmath.mpf("0.8151")
+    finally:
+        solver.set_precision(256)
+    prec = 256
+    cons, b, _ = instances.sphere_packing_2point(n=3, d=40, prec=prec)
+    bi = solver.get_block_info(cons)
+    assert bi.n_y == 244 and max(max(r) for r in bi.Y_blocksizes) == 82                  # SURVEY §8(d), cfg2
+    try:
+        og, rg = solver.solverank1sdp(cons, b, bi, verbose=False, return_info=True, omega_p=100, omega_d=100,
+                                      maxiterations=60)
+        assert rg[-1].terminate != 3
+    except ClrsdpError as e:
+        assert "higher precision" in str(e)
+
+
+CFG4_SPEC = [dict(m=2, K=91, blocks=[dict(delta=56, ranks=[2] * 91), dict(delta=42, ranks=[2] * 91)])] * 4
+
+
+def test_config4_structure_384bit_matches_oracle():
+    """BASELINE config 4 by its structure: 4 clusters of 2 x 2 polynomial-matrix constraints, K = 91 sample
+    points, every (l, k) of rank 2, vector lengths 56 and 42 (blocks 112 and 84), dim_S = 273, n_y = 60, 384 bits.
+    The constraint vectors are random instead of Padua-point evaluations of a bivariate basis (manufactured strictly
+    feasible): what the hot path sees - m > 1, L > 1, rank > 1 at these sizes - is the same. Two iterations against the
+    oracle to 2^-(p-16) (p + 64-bit arbiter where the conditioning exceeds 2^16), then the GPU solve converges."""
+    prec = 384
+    cons, b = instances.random_structured_sdp(CFG4_SPEC, n_y=60, prec=prec, seed=20261020)
+    bi = solver.get_block_info(cons)
+    assert list(bi.dim_S) == [273] * 4 and [list(r) for r in bi.Y_blocksizes] == [[112, 84]] * 4
+    hg, ho = pair(cons, b, bi, prec)
+    wc, wb = widen_problem(cons, b, 2)
+    ht = oracle_handle(prec + 64, 8)
+    solver.load_problem(ht, wc, wb, bi)
+    ht.set_params(solver.real_params(ht.nlimb))
+    ht.init_point()
+    ht.prepare()
+    for it in range(2):
+        rg, ro, rt = hg.iterate(), ho.iterate(), ht.iterate()
+        assert rg.status == 0 and ro.status == 0 and rt.status == 0
+        compare_iteration(hg, ho, bi, prec, prec - 16, ht)
+    solver.set_precision(prec)
+    try:
+        og, rows = solver.solverank1sdp(cons, b, bi, verbose=False, return_info=True)
+        assert rows[-1].terminate == 3
+        with mpmath.workprec(prec):
+            assert og[7] < mpmath.mpf(10) ** -15
+    finally:
+        solver.set_precision(256)
