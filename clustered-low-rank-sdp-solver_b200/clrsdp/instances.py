@@ -292,3 +292,84 @@ def random_structured_sdp(spec, n_y=5, prec=256, seed=7, positive_H=True):
                                       c=MpArray.from_ints(list(c_int), -3 * FRAC_BITS, nlimb)))
     b = MpArray.from_ints(list(b_int), -2 * FRAC_BITS, nlimb)
     return constraints, b
+
+
+def bivariate_matrix_program(D=6, n_y=60, clusters=4, prec=384, seed=20261021, ball_radius2=3):
+    """BASELINE config 4: `clusters` constraints, each a 2 x 2 polynomial matrix inequality in two
+    variables of degree 2D on {G_l >= 0}, G = {1, ball_radius2 - x1^2 - x2^2}, sampled at the Padua points of degree 2D
+    (K = C(2D+2, 2)) in the product-Chebyshev basis T_a(x1) T_b(x2), a + b <= D, with a fixed positive definite 2 x 2
+    matrix Pi_l per weight, through `frontend.prepareabc` (the `Pi` path, all_of_Pi = true): every (l, k) has rank 2,
+    vectors of length 2 C(D+2, 2) and 2 C(D+1, 2). D = 6: K = 91, blocks 112 and 84, dim_S = 273.
+
+    ball_radius2 = 3 keeps G_2 positive at every sample, corners of the square included (H > 0, rank 2 everywhere),
+    and the instance is manufactured strictly feasible like `random_structured_sdp` (so a full solve converges);
+    ball_radius2 = 2 vanishes at the two corner Padua points (rank 0 there, pruned by the threshold); ball_radius2 = 1
+    is SURVEY's G = 1 - x1^2 - x2^2, negative at the Padua points outside the disc (mixed-sign H: single iterations
+    from omega*I only).
+    The M_i are random symmetric polynomial matrices of degree D (seeded); M_0 enters only through c, which is set so
+    that (y0, Y0 = I) is dual feasible; b = B^T x0.
+    """
+    import mpmath
+    from . import frontend as fe
+    nlimb = prec // 32
+    mp = mpmath.mp.clone()
+    mp.prec = prec + 64
+    rng = np.random.default_rng(seed)
+    x1, x2 = fe.Poly.var(2, 0), fe.Poly.var(2, 1)
+    def cheb(k, x):
+        t = [x * 0 + 1, x * 1]
+        for i in range(2, k + 1):
+            t.append(2 * x * t[i - 1] - t[i - 2])
+        return t[:k + 1]
+    c1, c2 = cheb(D, x1), cheb(D, x2)
+    q = [c1[a] * c2[e - a] for e in range(D + 1) for a in range(e, -1, -1)]       # degree-monotone
+    G = [fe.Poly.const(2, 1), ball_radius2 - x1 * x1 - x2 * x2]
+    Pi = [[[fe.Poly.const(2, 2), fe.Poly.const(2, 1)], [fe.Poly.const(2, 1), fe.Poly.const(2, 2)]],
+          [[fe.Poly.const(2, 3), fe.Poly.const(2, -1)], [fe.Poly.const(2, -1), fe.Poly.const(2, 2)]]]
+    xs = fe.create_sample_points_2d(2 * D, prec)
+    K = len(xs)
+    mono = [e for k in range(D + 1) for e in fe.multiexponents(2, k)]
+    monovals = [[xk[0] ** e[0] * xk[1] ** e[1] for e in mono] for xk in xs]          # [K][n_mono]
+    qvals = [[fe.evaluate(p, xk) for p in q] for xk in xs]
+    y0 = [mp.mpf(int(v)) / (1 << FRAC_BITS) for v in _rand_scaled(rng, n_y, -1.0, 1.0)]
+    constraints = []
+    b_acc = [mp.mpf(0)] * n_y
+    m = 2
+    for _ in range(clusters):
+        # M_i[r][s](x_k) for i = 1..n_y: random coefficients on the monomials of degree <= D, evaluated by dot products
+        coef = _rand_scaled(rng, (n_y, 3, len(mono)), -1.0, 1.0).astype(object)
+        zero = fe.Sampled([mp.mpf(0)] * K)
+        Ms = [[[zero] * m for _ in range(m)]]
+        for i in range(n_y):
+            ent = {}
+            for pr, (r, s) in enumerate(((0, 0), (1, 0), (1, 1))):
+                cf = [mp.mpf(int(v)) / (1 << FRAC_BITS) for v in coef[i, pr]]
+                ent[(r, s)] = fe.Sampled([mp.fdot(cf, monovals[k]) for k in range(K)])
+            Ms.append([[ent[(max(r, s), min(r, s))] for s in range(m)] for r in range(m)])
+        con = fe.prepareabc(Ms, G, q, xs, 2 * D, Pi, prec=prec, qp_precomp=qvals)
+        # c = Tr(A_* Y0) + B y0 with Y0 = I; b += B^T x0 with x0 diagonally dominant per sample
+        dimS = 3 * K
+        Bm = [[con.B.to_mpf(r * n_y + i) for i in range(n_y)] for r in range(dimS)]
+        cvals = [mp.fdot(Bm[r], y0) for r in range(dimS)]
+        for l in range(con.L):
+            Vl, Hl, rk = con.V[l], con.H[l], con.ranks[l]
+            width = Vl.shape[1]
+            pos = 0
+            for k in range(K):
+                for _r in range(int(rk[k])):
+                    vv = mp.fsum(Vl.to_mpf(pos * width + t) ** 2 for t in range(width))
+                    for r in range(m):  # Tr(A_(r,r,k) Y0) = sum H |v|^2 for Y0 = I; the (r, s != r) blocks of I vanish
+                        cvals[(r + r * (r + 1) // 2) * K + k] += Hl.to_mpf(pos) * vv
+                    pos += 1
+        x0 = [mp.mpf(0)] * dimS
+        for r in range(m):
+            for s in range(r + 1):
+                pr = s + r * (r + 1) // 2
+                draw = _rand_scaled(rng, K, 1.0, 2.0) if r == s else _rand_scaled(rng, K, -0.2, 0.2)
+                for k in range(K):
+                    x0[pr * K + k] = mp.mpf(int(draw[k])) / (1 << FRAC_BITS)
+        for i in range(n_y):
+            b_acc[i] += mp.fsum(Bm[r][i] * x0[r] for r in range(dimS))
+        con.c = MpArray.from_mpf(cvals, nlimb)
+        constraints.append(con)
+    return constraints, MpArray.from_mpf(b_acc, nlimb)

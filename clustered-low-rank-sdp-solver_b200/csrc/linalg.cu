@@ -270,9 +270,10 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
       __syncwarp();
       if (lane == 0) {
         Num<NL> a = smem_get<NL>(Us, pk_u(w, r, r));
-        if (relaxed) {  // the unpivoted rows carry the scale tau_{k+1} = mu_k tau_k
-          Num<NL> thr = mp::mul_2exp(nmul(mu, smem_get<NL>(Gs, pk_g(k, k))), -(32 * NL - 16));
-          if (mp::is_zero(a) || a.neg || ncmp(a, thr) < 0) smem_put<NL>(Us, pk_u(w, r, r), thr);
+        if (relaxed) {  // the unpivoted rows carry the scale tau_{k+1} = mu_k tau_k: threshold by exponents only (no
+                        // multiplication on the pivot chain): a < 2^te  <=>  a.e <= te
+          const int te = smem_get<NL>(Gs, pk_g(k, k)).e - (32 * NL - 16);
+          if (mp::is_zero(a) || a.neg || a.e <= te) smem_put<NL>(Us, pk_u(w, r, r), mp::from_pow2<NL>(te));
         } else if (mp::is_zero(a) || a.neg) {
           bad = 1;
         }

@@ -376,3 +376,49 @@ def test_config4_structure_384bit_matches_oracle():
             assert og[7] < mpmath.mpf(10) ** -15
     finally:
         solver.set_precision(256)
+
+
+def test_config4_bivariate_polynomial_program_384bit():
+    """BASELINE config 4 with real polynomial data (`instances.bivariate_matrix_program`: 2 x 2 polynomial-matrix
+    constraints in two variables sampled at the 91 Padua points of degree 12 through the `Pi` path of `prepareabc`,
+    product-Chebyshev basis; sizes exactly SURVEY §8d's: dim_S = 273, blocks 112 and 84, Nv = 182, n_y = 60, 384 bits).
+    Two iterations against the oracle: every field agrees to 2^-(p-16), or - where the conditioning of the sampled
+    polynomial data exceeds 2^16 - the GPU result is as close (within 2 bits) to the same iteration at p + 64 bits as
+    the oracle's is. Then the GPU solve converges to the oracle-independent optimality conditions."""
+    prec = 384
+    cons, b = instances.bivariate_matrix_program(prec=prec)
+    bi = solver.get_block_info(cons)
+    assert list(bi.dim_S) == [273] * 4 and [list(r) for r in bi.Y_blocksizes] == [[112, 84]] * 4 and bi.n_y == 60
+    hg, ho = pair(cons, b, bi, prec)
+    wc, wb = widen_problem(cons, b, 2)
+    ht = oracle_handle(prec + 64, 8)
+    solver.load_problem(ht, wc, wb, bi)
+    ht.set_params(solver.real_params(ht.nlimb))
+    ht.init_point()
+    ht.prepare()
+
+    def check(name, *idx):
+        a, o, t = hg.fetch(name, *idx), ho.fetch(name, *idx), ht.fetch(name, *idx)
+        if rel_err_bits(a, o) >= prec - 16:
+            return
+        eg, eo = rel_err_bits(a, t), rel_err_bits(o, t)
+        assert eg >= eo - 2, (name, idx, eg, eo)
+
+    for it in range(2):
+        rg, ro, rt = hg.iterate(), ho.iterate(), ht.iterate()
+        assert rg.status == 0 and ro.status == 0 and rt.status == 0
+        assert rg.alpha_p == pytest.approx(ro.alpha_p, rel=1e-12) and rg.alpha_d == pytest.approx(ro.alpha_d, rel=1e-12)
+        for name in ("d", "dx", "dy", "x", "y"):
+            check(name)
+        for j in range(bi.J):
+            for l in range(bi.L[j]):
+                for name in ("Xinv", "Px", "Py", "Z", "dX", "dY", "X", "Y"):
+                    check(name, j, l)
+    solver.set_precision(prec)
+    try:
+        og, rows = solver.solverank1sdp(cons, b, bi, verbose=False, return_info=True)
+        assert rows[-1].terminate == 3
+        with mpmath.workprec(prec):
+            assert og[7] < mpmath.mpf(10) ** -15
+    finally:
+        solver.set_precision(256)
