@@ -269,3 +269,35 @@ def _print_timings(rows, time_total):
     print("Time inside search directions (both predictor & corrector step)")
     print("%11s %11s %11s %11s %11s" % ("calc Z", "calc rhs x", "solve system", "calc dX", "calc dY"))
     print(("%11.5e " * 5) % tuple(t[12:17]))
+
+
+# ---- check-pointing the iterate (the reference's warm start: initial_solutions, MPMP.jl:613, :689) ----
+def save_checkpoint(path, h: capi.Handle, blockinfo: BlockInfo, iteration=0):
+    """Write the current iterate (x, X, y, Y) of handle `h` to `path` (.npz of the wire arrays: bit-exact, any
+    precision). X and Y are stored flat in block order, as `clrsdp_download_point` delivers them."""
+    sizes = [bs for j in range(blockinfo.J) for bs in blockinfo.Y_blocksizes[j]]
+    n_X = int(sum(s * s for s in sizes))
+    x, X, y, Y = h.download_point(int(sum(blockinfo.dim_S)), n_X, blockinfo.n_y)
+    arrs = {}
+    for name, a in (("x", x), ("X", X), ("y", y), ("Y", Y)):
+        arrs[name + "_sign"], arrs[name + "_exp"], arrs[name + "_limb"] = a.sign, a.exp, a.limb
+    np.savez_compressed(path, nlimb=h.nlimb, iteration=iteration, dim_S=np.asarray(blockinfo.dim_S),
+                        blocks=np.asarray(sizes), n_y=blockinfo.n_y, **arrs)
+
+
+def load_checkpoint(path, h: capi.Handle, blockinfo: BlockInfo):
+    """Upload a saved iterate into `h` (the problem must already be loaded) and return the stored iteration number.
+    The structure is checked; the precision must be the handle's (no silent re-rounding)."""
+    z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+    sizes = [bs for j in range(blockinfo.J) for bs in blockinfo.Y_blocksizes[j]]
+    if int(z["nlimb"]) != h.nlimb:
+        raise ValueError(f"checkpoint is at {32 * int(z['nlimb'])} bits, the handle at {h.prec}")
+    if list(z["dim_S"]) != list(blockinfo.dim_S) or list(z["blocks"]) != sizes or int(z["n_y"]) != blockinfo.n_y:
+        raise ValueError("checkpoint does not match the block structure of this problem")
+    pt = []
+    for name in ("x", "X", "y", "Y"):
+        a = MpArray(z[name + "_sign"].shape[0], h.nlimb)
+        a.sign[:], a.exp[:], a.limb[:] = z[name + "_sign"], z[name + "_exp"], z[name + "_limb"]
+        pt.append(a)
+    h.upload_point(*pt)
+    return int(z["iteration"])

@@ -31,17 +31,18 @@ __device__ __forceinline__ int64_t item_off(const GatherArgs& g, int b) {
 
 // Fixed-point conversion of one entry relative to its row exponent and balanced radix-256 digits:
 //   F = trunc( x * 2^(8S-2-rexp) ),  |F| < 2^(8S-2);   F = sum_a d_a 256^(S-1-a),  d_a in [-128,127]
+// The balanced digits need no digit-serial carry loop: with M = 0x80 in each of the S byte positions,
+//   byte_i(F + M) = (b_i + c_i + 128) mod 256,   c_{i+1} = [b_i + c_i >= 128]   (the carry of the addition IS the
+// balancing carry), so d_i = byte_i(F + M) - 128 = byte_i((F + M) xor M) read as int8: one multiword add and one xor.
 template <int NL, int S>
-__device__ __forceinline__ void slice_entry(const GatherArgs& g, int row, int k, int32_t rexp, int8_t* __restrict__ digits) {
+__device__ __forceinline__ void fixed_point_digits(const GatherArgs& g, int b, int64_t at, int k, bool in_range, int32_t rexp,
+                                                   uint32_t (&W)[NL + 2]) {
   constexpr int NLW = NL + 2;
   static_assert(8 * S + 2 <= 32 * NLW, "digit window too small");
-  uint32_t W[NLW];
 #pragma unroll
   for (int i = 0; i < NLW; i++) W[i] = 0;
   bool negf = false;
-  if (k < g.K) {
-    int b = row / g.rows, r = row % g.rows;
-    int64_t at = item_off(g, b) + (int64_t)r * g.rs + (int64_t)k * g.ks;
+  if (in_range) {
     mp::Num<NL> x = mp::load<NL>(g.w, g.n, (size_t)at);
     if (!mp::is_zero(x)) {
       if (g.kshift) x.e -= g.kshift[b * g.K + k];
@@ -50,82 +51,60 @@ __device__ __forceinline__ void slice_entry(const GatherArgs& g, int row, int k,
       if (sr < 32u * NLW) {
 #pragma unroll
         for (int i = 0; i < NL; i++) W[i + 2] = x.m[i];
-        mp::shr_limbs<NLW>(W, sr >> 5);
-        mp::shr_bits<NLW>(W, sr & 31u);
+        if (sr >> 5) mp::shr_limbs<NLW>(W, sr >> 5);
+        if (sr & 31u) mp::shr_bits<NLW>(W, sr & 31u);
         negf = x.neg != 0;
       }
     }
   }
-  if (negf) {  // two's complement
-    uint32_t c = 1;
+  if (negf) mp::neg_n<NLW>(W);  // two's complement
+  uint32_t M[NLW];
 #pragma unroll
-    for (int i = 0; i < NLW; i++) {
-      uint64_t s = (uint64_t)(~W[i]) + c;
-      W[i] = (uint32_t)s;
-      c = (uint32_t)(s >> 32);
-    }
-  }
-  int carry = 0;
+  for (int i = 0; i < NLW; i++) M[i] = (4 * i + 4 <= S) ? 0x80808080u : ((4 * i < S) ? (0x80808080u >> (8 * (4 - (S - 4 * i)))) : 0u);
+  mp::add_n<NLW>(W, M);
+#pragma unroll
+  for (int i = 0; i < NLW; i++) W[i] ^= M[i];
+}
+
+template <int NL, int S>
+__device__ __forceinline__ void slice_entry(const GatherArgs& g, int row, int k, int32_t rexp, int8_t* __restrict__ digits) {
+  constexpr int NLW = NL + 2;
+  uint32_t W[NLW];
+  const int b = row / g.rows, r = row % g.rows;
+  fixed_point_digits<NL, S>(g, b, item_off(g, b) + (int64_t)r * g.rs + (int64_t)k * g.ks, k, k < g.K, rexp, W);
   int8_t* out = digits + ((size_t)(S - 1) * g.rows_total + row) * g.Kp + k;
   const size_t pstride = (size_t)g.rows_total * g.Kp;
 #pragma unroll
   for (int i = 0; i < S; i++) {
-    int v = (int)((W[i >> 2] >> (8 * (i & 3))) & 0xFFu) + carry;
-    carry = v >= 128 ? 1 : 0;
-    v -= carry << 8;
-    *out = (int8_t)v;
+    *out = (int8_t)((W[i >> 2] >> (8 * (i & 3))) & 0xFFu);
     out -= pstride;
   }
 }
 
-// Four consecutive entries k4 .. k4+3 of one row: their digits are packed into one 32-bit word per digit plane, so a
-// warp writes 128 contiguous bytes per plane and store instruction instead of 32.
+// Four consecutive entries k4 .. k4+3 of one row: their digits are packed into one 32-bit word per digit plane (a 4 x 4
+// byte transpose of the four entries' words by PRMT), so a warp writes 128 contiguous bytes per plane and store
+// instruction instead of 32.
 template <int NL, int S>
 __device__ __forceinline__ void slice_entry4(const GatherArgs& g, int row, int k4, int32_t rexp, int8_t* __restrict__ digits) {
   constexpr int NLW = NL + 2;
-  static_assert(8 * S + 2 <= 32 * NLW, "digit window too small");
-  uint32_t out[S];
-#pragma unroll
-  for (int i = 0; i < S; i++) out[i] = 0;
+  uint32_t W0[NLW], W1[NLW], W2[NLW], W3[NLW];
   const int b = row / g.rows, r = row % g.rows;
   const int64_t base = item_off(g, b) + (int64_t)r * g.rs;
-#pragma unroll
-  for (int e = 0; e < 4; e++) {
-    const int k = k4 + e;
-    uint32_t W[NLW];
-#pragma unroll
-    for (int i = 0; i < NLW; i++) W[i] = 0;
-    bool negf = false;
-    if (k < g.K) {
-      mp::Num<NL> x = mp::load<NL>(g.w, g.n, (size_t)(base + (int64_t)k * g.ks));
-      if (!mp::is_zero(x)) {
-        if (g.kshift) x.e -= g.kshift[b * g.K + k];
-        uint32_t d = (uint32_t)(rexp - x.e);
-        uint32_t sr = 32u * NLW - 8u * S + 2u + d;
-        if (sr < 32u * NLW) {
-#pragma unroll
-          for (int i = 0; i < NL; i++) W[i + 2] = x.m[i];
-          if (sr >> 5) mp::shr_limbs<NLW>(W, sr >> 5);
-          if (sr & 31u) mp::shr_bits<NLW>(W, sr & 31u);
-          negf = x.neg != 0;
-        }
-      }
-    }
-    if (negf) mp::neg_n<NLW>(W);
-    int carry = 0;
-#pragma unroll
-    for (int i = 0; i < S; i++) {
-      int v = (int)((W[i >> 2] >> (8 * (i & 3))) & 0xFFu) + carry;
-      carry = v >= 128 ? 1 : 0;
-      out[i] |= (uint32_t)(v & 0xFF) << (8 * e);
-    }
-  }
+  fixed_point_digits<NL, S>(g, b, base + (int64_t)(k4 + 0) * g.ks, k4 + 0, k4 + 0 < g.K, rexp, W0);
+  fixed_point_digits<NL, S>(g, b, base + (int64_t)(k4 + 1) * g.ks, k4 + 1, k4 + 1 < g.K, rexp, W1);
+  fixed_point_digits<NL, S>(g, b, base + (int64_t)(k4 + 2) * g.ks, k4 + 2, k4 + 2 < g.K, rexp, W2);
+  fixed_point_digits<NL, S>(g, b, base + (int64_t)(k4 + 3) * g.ks, k4 + 3, k4 + 3 < g.K, rexp, W3);
   uint32_t* o = reinterpret_cast<uint32_t*>(digits + ((size_t)(S - 1) * g.rows_total + row) * g.Kp + k4);
   const size_t pstride4 = ((size_t)g.rows_total * g.Kp) >> 2;
 #pragma unroll
-  for (int i = 0; i < S; i++) {
-    *o = out[i];
+  for (int wi = 0; 4 * wi < S; wi++) {
+    const uint32_t lo01 = __byte_perm(W0[wi], W1[wi], 0x5140), hi01 = __byte_perm(W0[wi], W1[wi], 0x7362);
+    const uint32_t lo23 = __byte_perm(W2[wi], W3[wi], 0x5140), hi23 = __byte_perm(W2[wi], W3[wi], 0x7362);
+    *o = __byte_perm(lo01, lo23, 0x5410);
     o -= pstride4;
+    if (4 * wi + 1 < S) { *o = __byte_perm(lo01, lo23, 0x7632); o -= pstride4; }
+    if (4 * wi + 2 < S) { *o = __byte_perm(hi01, hi23, 0x5410); o -= pstride4; }
+    if (4 * wi + 3 < S) { *o = __byte_perm(hi01, hi23, 0x7632); o -= pstride4; }
   }
 }
 
@@ -134,7 +113,7 @@ __device__ __forceinline__ void slice_entry4(const GatherArgs& g, int row, int k
 // The second read of the row hits L1/L2.
 constexpr int SLICE_THREADS = 256;
 template <int NL, int S>
-__global__ void __launch_bounds__(SLICE_THREADS, 3) slice_rows_kernel(GatherArgs g, int wpr, int32_t* __restrict__ exps,
+__global__ void __launch_bounds__(SLICE_THREADS, (NL <= 8 ? 4 : 2)) slice_rows_kernel(GatherArgs g, int wpr, int32_t* __restrict__ exps,
                                                                     int8_t* __restrict__ digits) {
   __shared__ int32_t smx[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -100,3 +100,38 @@ def test_precision_setter():
     with pytest.raises(ValueError):
         solver.set_precision(100)
     solver.set_precision(256)
+
+
+def test_checkpoint_roundtrip_resumes_the_same_trajectory(tmp_path):
+    """save_checkpoint / load_checkpoint (row f4): a solve interrupted after 3 iterations and resumed from the file
+    produces exactly the iterations the uninterrupted solve does (oracle handle; the product handle uses the same
+    calls)."""
+    from oracle.ref import oracle_handle
+    prec = 128
+    cons, b, _ = instances.synthetic_clustered_sdp(J=2, delta=3, K=4, n_y=2, prec=prec)
+    bi = solver.get_block_info(cons)
+
+    def fresh():
+        h = oracle_handle(prec, 1)
+        solver.load_problem(h, cons, b, bi)
+        h.set_params(solver.real_params(h.nlimb))
+        return h
+
+    h1 = fresh()
+    h1.init_point(); h1.prepare()
+    for _ in range(3):
+        h1.iterate()
+    solver.save_checkpoint(tmp_path / "it3", h1, bi, iteration=3)
+    want = [h1.iterate() for _ in range(2)]
+    h2 = fresh()
+    assert solver.load_checkpoint(tmp_path / "it3", h2, bi) == 3
+    h2.prepare()
+    got = [h2.iterate() for _ in range(2)]
+    for a, o in zip(got, want):
+        assert (a.mu, a.alpha_p, a.alpha_d, a.p_obj_new, a.d_obj_new) == (o.mu, o.alpha_p, o.alpha_d, o.p_obj_new, o.d_obj_new)
+    n_x, n_X = int(sum(bi.dim_S)), int(sum(s * s for row in bi.Y_blocksizes for s in row))
+    for a, o in zip(h2.download_point(n_x, n_X, bi.n_y), h1.download_point(n_x, n_X, bi.n_y)):
+        assert np.array_equal(a.sign, o.sign) and np.array_equal(a.exp, o.exp) and np.array_equal(a.limb, o.limb)
+    h3 = oracle_handle(256, 1)
+    with pytest.raises(ValueError):
+        solver.load_checkpoint(tmp_path / "it3", h3, bi)
