@@ -606,8 +606,11 @@ struct CarryArgs {
   int epi;
 };
 
-template <int NL, int T, int STACK>
-__global__ void carry_kernel(CarryArgs c) {
+// VAR 0: 17 planes in flight per load chunk (9 with four lane groups), registers as the compiler likes (128);
+// VAR 1 (default up to 256 bits; CLRSDP_CARRY_VAR overrides): 9 planes per chunk under __launch_bounds__(128, 5): 20 warps per
+// SM instead of 16.
+template <int NL, int T, int STACK, int VAR>
+__global__ void __launch_bounds__(128, (VAR && STACK != 4) ? 5 : 4) carry_kernel(CarryArgs c) {
   constexpr int NW = (T + 3) / 4 + 2;
   // a warp owns a 4 x 8 patch of one item: its plane reads are two runs of 4 rows x 16 bytes in the chunk-major block
   // layout, its result stores 4 runs of 8 consecutive entries
@@ -637,7 +640,7 @@ __global__ void carry_kernel(CarryArgs c) {
     int64_t carry = 0;
     // planes from the least significant (t = T-1) upwards, CH at a time: the CH (x nsplit) loads of a chunk are
     // independent and all in flight before the carry chain consumes them
-    constexpr int CH = 17;
+    constexpr int CH = (STACK == 4 || VAR) ? 9 : 17;  // (STACK = 4 with 17: 254 registers, 8 warps per SM)
 #pragma unroll
     for (int c0 = T - 1; c0 >= 0; c0 -= CH) {
       int64_t acc[CH];
@@ -884,12 +887,23 @@ static void carry_impl(Ctx& ctx, const CarryArgs& c) {
   int grid = (int)std::min<int64_t>(ceil_div(threads, 128), (int64_t)ctx.sm_count * 32);
   // algorithmic bytes: read T int32 planes (x nsplit), write (p/8+4)
   int tk = ctx.begin("carry", (double)total * (4.0 * T * c.nsplit + 4.0 * (NL + 1)));
-  if (c.stack == 1)
-    carry_kernel<NL, T, 1><<<grid, 128, 0, ctx.stream>>>(c);
+  // measured (r1g): VAR 1 is 5 % faster at 256 bits (cfg3: 1.52 -> 1.44 ms per iteration), 9 % slower at 512 bits (cfg5shard)
+  static int var_env = -2;
+  if (var_env == -2) var_env = getenv("CLRSDP_CARRY_VAR") ? atoi(getenv("CLRSDP_CARRY_VAR")) : -1;
+  const int var = var_env >= 0 ? var_env : (NL <= 8 ? 1 : 0);
+  if (var) {
+    if (c.stack == 1)
+      carry_kernel<NL, T, 1, 1><<<grid, 128, 0, ctx.stream>>>(c);
+    else if (c.stack == 2)
+      carry_kernel<NL, T, 2, 1><<<grid, 128, 0, ctx.stream>>>(c);
+    else
+      carry_kernel<NL, T, 4, 1><<<grid, 128, 0, ctx.stream>>>(c);
+  } else if (c.stack == 1)
+    carry_kernel<NL, T, 1, 0><<<grid, 128, 0, ctx.stream>>>(c);
   else if (c.stack == 2)
-    carry_kernel<NL, T, 2><<<grid, 128, 0, ctx.stream>>>(c);
+    carry_kernel<NL, T, 2, 0><<<grid, 128, 0, ctx.stream>>>(c);
   else
-    carry_kernel<NL, T, 4><<<grid, 128, 0, ctx.stream>>>(c);
+    carry_kernel<NL, T, 4, 0><<<grid, 128, 0, ctx.stream>>>(c);
   ctx.end(tk);
 }
 
