@@ -801,6 +801,19 @@ static int bk_cap() {
 }
 static int stack_of(int M) { return M <= 32 ? 4 : (M <= 64 ? 2 : 1); }
 static int bn_of(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : 64); }
+// Tile width of a product. A batch of small items that fills at most half of the SMs with 64-wide tiles is cut into
+// 32-wide ones: the time of such a CTA is the drain of its T accumulator blocks (TMEM -> registers -> global), which
+// halves with the tile width, and twice as many SMs work (cfg3: 64 items of 64 x 64 x 64 -> 128 CTAs on 148 SMs).
+static int bn_for(const GemmPlan& plan, int sm_count, bool symmetric) {
+  int bn = bn_of(plan.N);
+  static int split = -1;
+  if (split < 0) split = getenv("CLRSDP_BN_SPLIT") ? atoi(getenv("CLRSDP_BN_SPLIT")) : 1;
+  if (split && bn == 64 && !symmetric) {
+    int64_t tiles = (int64_t)plan.batch * ceil_div(plan.M, 128) * ceil_div(plan.N, 64);
+    if (2 * tiles <= sm_count) bn = 32;
+  }
+  return bn;
+}
 
 void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, int item0, int nitems, int nsplit,
                          int Kc, bool symmetric) {
@@ -814,7 +827,7 @@ void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, i
   p.Kp = A.Kp;
   p.Kc = Kc;
   p.BK = std::min(A.Kp, bk_cap());
-  p.BN = bn_of(plan.N);
+  p.BN = bn_for(plan, ctx_.sm_count, symmetric);
   p.stack = stack_of(plan.M);
   p.m_tiles = ceil_div(plan.M, 128);
   p.Mpad = p.m_tiles * 128;
@@ -925,7 +938,7 @@ void GemmEngine::multiply(const Slice& A, const Slice& B, const GemmPlan& plan, 
   if (symmetric && (&A != &B || plan.M != plan.N || plan.d_rowA || plan.d_rowB)) symmetric = false;
   if (A.Kp != B.Kp || A.S != S_ || B.S != S_) throw SolverError(-1, "gemm: operand mismatch");
   const int T = S_;
-  const int BK = std::min(A.Kp, bk_cap()), BN = bn_of(plan.N), stack = stack_of(plan.M);
+  const int BK = std::min(A.Kp, bk_cap()), BN = bn_for(plan, ctx_.sm_count, symmetric), stack = stack_of(plan.M);
   const int m_tiles = ceil_div(plan.M, 128), Mpad = m_tiles * 128;
   int64_t tiles = (int64_t)plan.batch * m_tiles * ceil_div(plan.N, BN);
   if (symmetric) {  // only the tiles that touch the upper triangle
