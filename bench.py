@@ -338,8 +338,8 @@ def main():
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant shape (64 x 64x64x64 at
                     # 256 bit: 9.0 + 11.1 MB) from the committed ncu --set full capture; its algorithmic bytes are
                     # 17.8 MB of digits read + 35.7 MB of int32 planes written, most of which stays in the 126 MB L2
-                    traffic=22215168 if args.workload == "cfg3" else None,
-                    traffic_source="profiles/r1d_ncu_mma_planes_full.txt (launch with grid 64: 8.98 MB read + 13.24 MB written)",
+                    traffic=20016896 if args.workload == "cfg3" else None,
+                    traffic_source="profiles/r1i_ncu_mma_planes_full.txt (the batch-64 64x64x64 launch, grid 128 / 198.7 KB smem: 8.98 MB read + 11.04 MB written)",
                     peak_source="measured in this run (tcgen05.mma kind::i8 issue loop on all SMs); MEASURED_PEAKS.json has "
                                 f"no int8 entry (its bf16 figure: {peaks['bf16_tflops']} TFLOP/s, {peaks['source']})",
                     achieved_note="ALGORITHMIC int8 ops (M*N*K*s(s+1)/2 MACs per product, s = p/8; no guard digits, no tile "

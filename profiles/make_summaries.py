@@ -1,0 +1,80 @@
+"""Turns the ncu outputs a gpurun call left in gpurun_out/ into the text summaries committed here.
+    python profiles/make_summaries.py r1i
+reads gpurun_out/<tag>_launches.csv (ncu --metrics gpu__time_duration.sum --csv), gpurun_out/<tag>_mma.ncu-rep and
+gpurun_out/<tag>_others.ncu-rep (ncu --set full) and writes profiles/<tag>_*.txt / .csv."""
+import collections
+import csv
+import io
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+# ---- launch list ----
+lines = [l for l in open(os.path.join(G, f"{tag}_launches.csv")) if not l.startswith("==")]
+agg, tot, n = collections.OrderedDict(), 0.0, 0
+for r in csv.DictReader(io.StringIO("".join(lines))):
+    if r.get("Metric Name") != "gpu__time_duration.sum":
+        continue
+    name = r["Kernel Name"].split("(")[0].split("<")[0].replace("void ", "")
+    v = float(r["Metric Value"].replace(",", ""))
+    ms = v / 1e6 if r["Metric Unit"] in ("ns", "nsecond") else (v / 1e3 if r["Metric Unit"] in ("us", "usecond") else v)
+    a = agg.setdefault(name, [0, 0.0])
+    a[0] += 1
+    a[1] += ms
+    tot += ms
+    n += 1
+out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c {n}  (CLRSDP_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline)",
+       f"# {tag}: {n} consecutive launches = about two IPM iterations of BASELINE config 3, launched directly (the default bench replays",
+       "# the same kernels from a CUDA graph; two streams are serialised by ncu).",
+       "# Times under ncu are cold-cache and serialised: compare SHARES with bench.py's CUDA-event shares (roofline.kernel_ms_per_step), not absolutes.",
+       f"# total {tot:.3f} ms over {n} launches", f"{'kernel':<34}{'launches':>9}{'ms':>10}{'share':>8}"]
+for k, (c, ms) in sorted(agg.items(), key=lambda x: -x[1][1]):
+    out.append(f"{k:<34}{c:>9}{ms:>10.3f}{100 * ms / tot:>7.1f}%")
+open(os.path.join(P, f"{tag}_ncu_launches_cfg3_summary.txt"), "w").write("\n".join(out) + "\n")
+shutil.copy(os.path.join(G, f"{tag}_launches.csv"), os.path.join(P, f"{tag}_ncu_launches_cfg3.csv"))
+
+# ---- full captures ----
+WANT = ["Grid Size", "Block Size", "launch__shared_mem_per_block_dynamic", "launch__registers_per_thread",
+        "gpu__time_duration.sum", "sm__cycles_elapsed.max", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__average_warp_latency_issue_stalled_short_scoreboard.pct",
+        "smsp__average_warp_latency_issue_stalled_barrier.pct", "smsp__average_warp_latency_issue_stalled_wait.pct",
+        "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.pct", "smsp__average_warp_latency_issue_stalled_lg_throttle.pct",
+        "smsp__average_warp_latency_issue_stalled_mio_throttle.pct", "smsp__average_warp_latency_issue_stalled_not_selected.pct"]
+
+
+def dump(rep, header, dst):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    lines = list(header) + [""]
+    for r in data:
+        lines.append("launch  " + r[idx["Kernel Name"]].split("(")[0][:90])
+        for w in WANT:
+            if w in idx and r[idx[w]] != "":
+                lines.append(f"  {w:<82}{r[idx[w]]:>16} {units[idx[w]]}")
+    open(dst, "w").write("\n".join(lines) + "\n")
+
+
+if os.path.exists(os.path.join(G, f"{tag}_mma.ncu-rep")):
+    dump(os.path.join(G, f"{tag}_mma.ncu-rep"),
+         ["# ncu --set full --clock-control none --import-source on -k regex:mma_planes -s 90 -c 6   (CLRSDP_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline)",
+          f"# {tag}: six consecutive mma_planes_kernel launches of an IPM iteration of BASELINE config 3 (256 bit, T = 34 digit planes).",
+          f"# full report: gpurun_out/{tag}_mma.ncu-rep (scratch, not committed)"],
+         os.path.join(P, f"{tag}_ncu_mma_planes_full.txt"))
+if os.path.exists(os.path.join(G, f"{tag}_others.ncu-rep")):
+    dump(os.path.join(G, f"{tag}_others.ncu-rep"),
+         ['# ncu --set full --clock-control none --import-source on -k regex:"carry_kernel|slice_rows|panel_factor" -s 200 -c 12   (same command)',
+          f"# {tag}: the CUDA-core kernels around the sliced GEMM (BASELINE config 3): occupancy, DRAM traffic, issue-stall shares.",
+          f"# full report: gpurun_out/{tag}_others.ncu-rep (scratch, not committed)"],
+         os.path.join(P, f"{tag}_ncu_carry_slice_panel_full.txt"))

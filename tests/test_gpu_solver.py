@@ -422,3 +422,55 @@ def test_config4_bivariate_polynomial_program_384bit():
             assert og[7] < mpmath.mpf(10) ** -15
     finally:
         solver.set_precision(256)
+
+
+def test_solvempmp_front_end_on_the_gpu():
+    """The reference's user entry `solvempmp` (MPMP.jl:562-586) end to end on the product path: polynomial input ->
+    `prepareabc` -> `get_block_info` -> `solverank1sdp` on the GPU. max t s.t. x^4 - x^2 + 1 - t >= 0 on [-1, 1]: 3/4;
+    and the same call on the oracle takes the same number of iterations."""
+    from clrsdp import frontend as fe
+    prec = 256
+    solver.set_precision(prec)
+    X = fe.Poly.var(1, 0)
+    M = [[[X ** 4 - X ** 2 + 1]], [[fe.Poly.const(1, -1)]]]
+    G = [fe.Poly.const(1, 1), 1 - X * X]
+    q = fe.make_monomial_basis(1, 2)
+    xs = [[v] for v in fe.create_sample_points_chebyshev(4)]
+    args = ([M], [G], [q], [xs], [4], [mpmath.mpf(1)])
+    og, rg = fe.solvempmp(*args, verbose=False, return_info=True)
+    oo, ro = fe.solvempmp(*args, verbose=False, return_info=True, handle=oracle_handle(prec, 2))
+    assert len(rg) == len(ro) and rg[-1].terminate == ro[-1].terminate == 3
+    with mpmath.workprec(prec):
+        assert abs(og[9] - mpmath.mpf(3) / 4) < mpmath.mpf(10) ** -12 and abs(og[8] - mpmath.mpf(3) / 4) < mpmath.mpf(10) ** -12
+        assert abs(og[8] - oo[8]) <= mpmath.mpf(2) ** -(prec - 16 - 64)
+
+
+def test_checkpoint_resume_on_the_gpu(tmp_path):
+    """save_checkpoint / load_checkpoint through the product handle: the resumed solve continues bit-identically."""
+    prec = 256
+    cons, b, _ = instances.synthetic_clustered_sdp(J=3, delta=6, K=10, n_y=5, prec=prec)
+    bi = solver.get_block_info(cons)
+
+    def fresh():
+        h = solver.product_handle(prec)
+        solver.load_problem(h, cons, b, bi)
+        h.set_params(solver.real_params(h.nlimb))
+        return h
+
+    h1 = fresh()
+    h1.init_point()
+    h1.prepare()
+    for _ in range(3):
+        h1.iterate()
+    solver.save_checkpoint(tmp_path / "it3", h1, bi, iteration=3)
+    h1.prepare()                      # the resumed handle starts from a prepare(): do the same here
+    want = [h1.iterate() for _ in range(2)]
+    h2 = fresh()
+    assert solver.load_checkpoint(tmp_path / "it3", h2, bi) == 3
+    h2.prepare()
+    got = [h2.iterate() for _ in range(2)]
+    for a, o in zip(got, want):
+        assert (a.mu, a.alpha_p, a.alpha_d, a.p_obj_new, a.d_obj_new) == (o.mu, o.alpha_p, o.alpha_d, o.p_obj_new, o.d_obj_new)
+    n_x, n_X = int(sum(bi.dim_S)), int(sum(s * s for row in bi.Y_blocksizes for s in row))
+    for a, o in zip(h2.download_point(n_x, n_X, bi.n_y), h1.download_point(n_x, n_X, bi.n_y)):
+        assert np.array_equal(a.sign, o.sign) and np.array_equal(a.exp, o.exp) and np.array_equal(a.limb, o.limb)
