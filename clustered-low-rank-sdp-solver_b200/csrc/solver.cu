@@ -43,6 +43,13 @@ Solver::Solver(int prec_bits, int device) : nl(prec_bits / 32), prec(prec_bits) 
   CLR_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
   CLR_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   CLR_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+  for (auto& h : invh_) {  // the inverse-panel chains of chol_inverse (one beside the main, one beside the side stream)
+    h.gemm.reset(new GemmEngine(ctx, nl));
+    CLR_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+    CLR_CUDA(cudaEventCreateWithFlags(&h.ev_go, cudaEventDisableTiming));
+    CLR_CUDA(cudaEventCreateWithFlags(&h.ev_done, cudaEventDisableTiming));
+  }
+  if (const char* g = getenv("CLRSDP_INVH")) use_invh_ = atoi(g) != 0;
   scal.alloc(SL_COUNT, nl);
   work.alloc(4096, nl);
   d_flags.ensure(4 * sizeof(int));
@@ -68,6 +75,11 @@ Solver::~Solver() {
   if (side_stream_) cudaStreamDestroy(side_stream_);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_join_) cudaEventDestroy(ev_join_);
+  for (auto& h : invh_) {
+    if (h.stream) cudaStreamDestroy(h.stream);
+    if (h.ev_go) cudaEventDestroy(h.ev_go);
+    if (h.ev_done) cudaEventDestroy(h.ev_done);
+  }
 }
 
 // ---- multi-GPU ------------------------------------------------------------------------------------------
@@ -695,9 +707,36 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
   }
   mat_zero(ctx, nl, Linv);
   tscr.alloc(std::max<size_t>(tscr.n, (size_t)batch * PANEL * n), nl);
+  // off-diagonal panel of L^-1 for the row block at k0:  Linv[p, 0:k0] = -Linv_pp * ( L[p, 0:k0] * Linv[0:k0, 0:k0] ).
+  // It needs the factor up to and including panel k0 and the inverse panels above it - nothing of the trailing matrix -
+  // so the chain of these panels runs on a helper stream BESIDE the rest of the factorisation (own GEMM workspace and
+  // scratch), forked after panel_factor(k0) and joined at the end: the pivot chain no longer waits for it.
+  InvHelper& H = invh_[side ? 1 : 0];
+  const bool par = use_invh_ && n > 2 * PANEL;
+  if (par) H.tscr.alloc(std::max<size_t>(H.tscr.n, (size_t)batch * PANEL * n), nl);
+  auto inverse_panel = [&](int k0, GemmEngine* ge2, Slice& s1, Slice& s2, MpBuf& scr) {
+    const int wk = std::min(PANEL, n - k0);
+    // T[i][c] = sum_r U[r][k0+i] * Linv[r][c], stored transposed: Tt[c][i]
+    OutDesc ot;
+    ot.dst = scr.t(), ot.bstride = (int64_t)PANEL * n, ot.rs = 1, ot.cs = wk;
+    product(ge2, s1, s2, op_cols(Uw, 0, k0, wk, k0), op_cols(Linv, 0, 0, k0, k0), wk, k0, ot, EPI_STORE, nullptr);
+    OperandDesc tb;
+    tb.src = scr.t(), tb.batch = batch, tb.bstride = (int64_t)PANEL * n, tb.rs = wk, tb.ks = 1, tb.rows = k0, tb.K = wk;
+    product(ge2, s1, s2, op_rows(Linv, k0, k0, wk, wk), tb, wk, k0, out_sub(Linv, k0, 0), EPI_NEG, nullptr);
+  };
+  bool forked = false;
   for (int k0 = 0; k0 < n; k0 += PANEL) {
     const int wk = std::min(PANEL, n - k0), n2 = n - k0 - wk;
     panel_factor(ctx, nl, Uw.sub(k0, k0, wk), Linv.sub(k0, k0, wk), want_u, d_stat, relaxed);
+    if (par && k0 >= PANEL) {
+      cudaStream_t cur = ctx.stream;
+      CLR_CUDA(cudaEventRecord(H.ev_go, cur));
+      CLR_CUDA(cudaStreamWaitEvent(H.stream, H.ev_go, 0));
+      ctx.stream = H.stream;
+      inverse_panel(k0, H.gemm.get(), H.s1, H.s2, H.tscr);
+      ctx.stream = cur;
+      forked = true;
+    }
     if (n2 > 0) {
       // U12 = L11^-1 A12 (overwrites A12). The CUDA-core kernel reads its operands while other threads store, so
       // there the product goes to scratch first; the tensor path slices its operands before it writes.
@@ -722,17 +761,12 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
       product(gemm_loc, fs2_, fs2_, u12, u12, n2, n2, out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
     }
   }
-  // off-diagonal panels of L^-1:  Linv[p, 0:k0] = -Linv_pp * ( L[p, 0:k0] * Linv[0:k0, 0:k0] )
-  for (int k0 = PANEL; k0 < n; k0 += PANEL) {
-    const int wk = std::min(PANEL, n - k0);
-    // T[i][c] = sum_r U[r][k0+i] * Linv[r][c], stored transposed: Tt[c][i]
-    OutDesc ot;
-    ot.dst = tscr.t(), ot.bstride = (int64_t)PANEL * n, ot.rs = 1, ot.cs = wk;
-    product(gemm_loc, fs1_, fs2_, op_cols(Uw, 0, k0, wk, k0), op_cols(Linv, 0, 0, k0, k0), wk, k0, ot, EPI_STORE, nullptr);
-    OperandDesc tb;
-    tb.src = tscr.t(), tb.batch = batch, tb.bstride = (int64_t)PANEL * n, tb.rs = wk, tb.ks = 1, tb.rows = k0, tb.K = wk;
-    product(gemm_loc, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), tb, wk, k0, out_sub(Linv, k0, 0), EPI_NEG, nullptr);
+  if (forked) {
+    CLR_CUDA(cudaEventRecord(H.ev_done, H.stream));
+    CLR_CUDA(cudaStreamWaitEvent(ctx.stream, H.ev_done, 0));
   }
+  if (!par)
+    for (int k0 = PANEL; k0 < n; k0 += PANEL) inverse_panel(k0, gemm_loc, fs1_, fs2_, tscr);
   if (!d_keep_scale) col_scale(ctx, nl, Linv, -1, d_scale);
   if (want_u) col_scale(ctx, nl, Uw, +1, d_scale);
 }

@@ -133,6 +133,16 @@ class Solver {
   GemmEngine* ge() { return on_side_ ? gemm_side_.get() : gemm_.get(); }
   Slice fs1s_, fs2s_;
   MpBuf tscr_side_;
+  // helper streams for the inverse-panel chains of chol_inverse ([0] beside the main stream, [1] beside the side stream)
+  struct InvHelper {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_go = nullptr, ev_done = nullptr;
+    std::unique_ptr<GemmEngine> gemm;
+    Slice s1, s2;
+    MpBuf tscr;
+  };
+  InvHelper invh_[2];
+  bool use_invh_ = true;
   Comm comm_;
   int ntot_local = 0;
   // structure
