@@ -106,14 +106,15 @@ def algorithmic_int8_macs(bi, prec):
     return pmac * per, pmac
 
 
-def cpu_baseline(n_threads, sample_J=None, iters=1):
-    """The oracle (CPU restatement of MPMP.jl, MPFR) timed on a bounded sample: `sample_J` clusters of the
-    same shape instead of 64; per-cluster phases scale linearly with J, the factorisation of Q does not."""
+def _time_oracle(n_threads, sample_J, iters, gemm_mode):
     from clrsdp import solver
     from oracle.ref import oracle_handle
     Jfull = WORKLOAD["J_per_gpu"]
-    sample_J = sample_J or max(1, min(Jfull, n_threads // 2 if n_threads >= 4 else 2))
     cons, b, bi = build_problem(sample_J, 0, sample_J, WORKLOAD["prec"])
+    if gemm_mode:
+        os.environ["CLRSDP_REF_GEMM"] = gemm_mode      # read by the oracle when a handle is created
+    else:
+        os.environ.pop("CLRSDP_REF_GEMM", None)
     h = oracle_handle(WORKLOAD["prec"], n_threads)
     solver.load_problem(h, cons, b, bi)
     h.set_params(solver.real_params(h.nlimb))
@@ -127,10 +128,26 @@ def cpu_baseline(n_threads, sample_J=None, iters=1):
         tq = r.timings[11]  # chol_Q: independent of J
         per_iter.append((dt - tq) * (Jfull / sample_J) + tq)
     h.close()
-    return dict(value=float(np.mean(per_iter)), unit=UNIT, cores=n_threads, kind="port",
-                sample=f"{iters} iteration(s) of the MPFR restatement (oracle/) on {sample_J} of {Jfull} clusters "
-                       f"(same delta/K/n_y), per-cluster phases scaled x{Jfull / sample_J:g}, Q factorisation unscaled; "
-                       "the reference itself (Julia+Arb) cannot run in this image")
+    os.environ.pop("CLRSDP_REF_GEMM", None)
+    return float(np.mean(per_iter))
+
+
+def cpu_baseline(n_threads, sample_J=None, iters=1, both=True):
+    """The oracle (CPU restatement of MPMP.jl, MPFR) timed on a bounded sample: `sample_J` clusters of the
+    same shape instead of 64; per-cluster phases scale linearly with J, the factorisation of Q does not.
+    `value` is timed with the oracle's block fixed-point product (CLRSDP_REF_GEMM=fixed: exact integer dot products
+    over mpn limbs, one rounding per entry - the way libarb's approx_mul works); the time with classical
+    mpfr_fma triple loops (what the parity tests run) is reported beside it."""
+    Jfull = WORKLOAD["J_per_gpu"]
+    sample_J = sample_J or max(1, min(Jfull, n_threads // 2 if n_threads >= 4 else 2))
+    v_fixed = _time_oracle(n_threads, sample_J, iters, "fixed")
+    out = dict(value=v_fixed, unit=UNIT, cores=n_threads, kind="port",
+               sample=f"{iters} iteration(s) of the MPFR restatement (oracle/, block fixed-point GEMM over mpn limbs like "
+                      f"libarb's approx_mul) on {sample_J} of {Jfull} clusters (same delta/K/n_y), per-cluster phases scaled "
+                      f"x{Jfull / sample_J:g}, Q factorisation unscaled; the reference itself (Julia+Arb) cannot run in this image")
+    if both:
+        out["value_mpfr_fma_loops"] = _time_oracle(n_threads, sample_J, iters, None)
+    return out
 
 
 def run_reference(args):
@@ -143,11 +160,11 @@ def run_reference(args):
     # one repetition (a bounded sample: n_threads/2 of the 64 clusters, extrapolated) takes a few seconds; the run is
     # capped at about two minutes of CPU time whatever K is: `steps` reports the repetitions actually timed
     t_begin = time.time()
-    cpu_baseline(n_threads, iters=1)           # warm-up (library load, page faults)
+    cpu_baseline(n_threads, iters=1, both=False)           # warm-up (library load, page faults)
     t_rep = max(0.5, time.time() - t_begin)
     reps = int(max(1, min(args.steps, 120.0 / t_rep)))
     for _ in range(reps):
-        last = cpu_baseline(n_threads, iters=1)
+        last = cpu_baseline(n_threads, iters=1, both=False)
         vals.append(last["value"])
     args.steps_requested, args.steps = args.steps, reps
     v = float(np.mean(vals))

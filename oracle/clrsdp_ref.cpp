@@ -103,24 +103,121 @@ double now_s() {
 // ---------------------------------------------------------------------------------------------------
 // dense kernels (the libarb entry points of SURVEY §2.3, restated)
 // ---------------------------------------------------------------------------------------------------
-// approx_mul!: classical product, one rounding per fused multiply-add.
+// approx_mul!, two ways (selected per process by CLRSDP_REF_GEMM, read in clrsdp_ref_create):
+//  * default: classical product, one rounding per fused multiply-add (what the parity tests check against);
+//  * "fixed": block fixed point, the way libarb's approx_mul works: every row of A and every column of B is
+//    aligned to its largest exponent and converted to integers of p/64 + 1 limbs, the dot products are exact integer
+//    multiply-accumulates (mpn_mul_n / mpn_add_n, positive and negative terms apart) and each entry is rounded once.
+//    It is the faster CPU product; bench.py times the CPU baseline with it and reports the fma-loop time beside it.
+static int g_gemm_fixed = 0;
+
+struct FixedRows {  // rows[r][k]: Lw limbs, sign, and the row exponent: value = +-limbs * 2^(E - 64 Lw)
+  int Lw = 0, K = 0;
+  std::vector<mp_limb_t> limbs;  // [rows][K][Lw]
+  std::vector<signed char> sign; // [rows][K]
+  std::vector<long> E;           // [rows], LONG_MIN for an all-zero row
+};
+// get(r, k) -> const Real&
+template <class Get>
+static void to_fixed(FixedRows& F, int rows, int K, long prec, Get get) {
+  const int L = (int)((prec + 63) / 64), Lw = L + 1;
+  F.Lw = Lw, F.K = K;
+  F.limbs.assign((size_t)rows * K * Lw, 0);
+  F.sign.assign((size_t)rows * K, 0);
+  F.E.assign(rows, LONG_MIN);
+  std::vector<mp_limb_t> tmp(Lw);
+  for (int r = 0; r < rows; r++) {
+    long E = LONG_MIN;
+    for (int k = 0; k < K; k++) {
+      const Real& x = get(r, k);
+      if (!mpfr_zero_p(&x.v)) E = std::max(E, (long)x.v._mpfr_exp);
+    }
+    F.E[r] = E;
+    if (E == LONG_MIN) continue;
+    for (int k = 0; k < K; k++) {
+      const Real& x = get(r, k);
+      if (mpfr_zero_p(&x.v)) continue;
+      const long sh = E - (long)x.v._mpfr_exp;
+      if (sh >= 64L * Lw) continue;
+      mp_limb_t* dst = &F.limbs[((size_t)r * K + k) * Lw];
+      tmp[0] = 0;
+      for (int i = 0; i < L; i++) tmp[i + 1] = x.v._mpfr_d[i];
+      const int ws = (int)(sh / 64), bs = (int)(sh % 64);
+      for (int i = 0; i + ws < Lw; i++) dst[i] = tmp[i + ws];
+      if (bs) __gmpn_rshift(dst, dst, Lw, (unsigned)bs);
+      F.sign[(size_t)r * K + k] = x.v._mpfr_sign < 0 ? -1 : 1;
+    }
+  }
+}
+static void fixed_dot(Real& out, const FixedRows& A, int ra, const FixedRows& B, int rb, std::vector<mp_limb_t>& ws) {
+  const int Lw = A.Lw, K = A.K, N = 2 * Lw + 1;
+  if (A.E[ra] == LONG_MIN || B.E[rb] == LONG_MIN) {
+    r_zero(out);
+    return;
+  }
+  ws.assign((size_t)3 * N, 0);
+  mp_limb_t *pos = ws.data(), *neg = pos + N, *prod = neg + N;
+  const mp_limb_t* a = &A.limbs[(size_t)ra * K * Lw];
+  const mp_limb_t* b = &B.limbs[(size_t)rb * K * Lw];
+  for (int k = 0; k < K; k++) {
+    const int sg = A.sign[(size_t)ra * K + k] * B.sign[(size_t)rb * K + k];
+    if (!sg) continue;
+    __gmpn_mul_n(prod, a + (size_t)k * Lw, b + (size_t)k * Lw, Lw);
+    mp_limb_t* acc = sg > 0 ? pos : neg;
+    acc[2 * Lw] += __gmpn_add_n(acc, acc, prod, 2 * Lw);
+  }
+  int sign = __gmpn_cmp(pos, neg, N);
+  if (sign == 0) {
+    r_zero(out);
+    return;
+  }
+  if (sign > 0) __gmpn_sub_n(pos, pos, neg, N); else __gmpn_sub_n(pos, neg, pos, N);
+  int top = N - 1;
+  while (top >= 0 && pos[top] == 0) top--;
+  const int lz = __builtin_clzl(pos[top]);
+  const int n = top + 1;
+  if (lz) __gmpn_lshift(pos, pos, n, (unsigned)lz);
+  __mpfr_struct t;
+  t._mpfr_prec = 64L * n;
+  t._mpfr_sign = sign > 0 ? 1 : -1;
+  t._mpfr_exp = A.E[ra] + B.E[rb] - 128L * Lw + 64L * n - lz;
+  t._mpfr_d = pos;
+  mpfr_set4(&out.v, &t, MPFR_RNDN, t._mpfr_sign);
+}
+static void gemm_fixed(Mat& out, const Mat& A, int c0, int nc, const Mat& B) {
+  const long prec = A.r && A.c ? A(0, 0).v._mpfr_prec : 64;
+  FixedRows FA, FB;
+  to_fixed(FA, A.r, nc, prec, [&](int r, int k) -> const Real& { return A(r, c0 + k); });
+  to_fixed(FB, B.c, nc, prec, [&](int r, int k) -> const Real& { return B(k, r); });
+  std::vector<mp_limb_t> ws;
+  for (int i = 0; i < A.r; i++)
+    for (int j = 0; j < B.c; j++) fixed_dot(out(i, j), FA, i, FB, j, ws);
+}
 void gemm(Mat& C, const Mat& A, const Mat& B) {
   Mat out(A.r, B.c);
-  for (int i = 0; i < A.r; i++)
-    for (int j = 0; j < B.c; j++) {
-      Real& acc = out(i, j);
-      for (int k = 0; k < A.c; k++) r_fma(acc, A(i, k), B(k, j));
-    }
+  if (g_gemm_fixed && A.c > 0) {
+    gemm_fixed(out, A, 0, A.c, B);
+  } else {
+    for (int i = 0; i < A.r; i++)
+      for (int j = 0; j < B.c; j++) {
+        Real& acc = out(i, j);
+        for (int k = 0; k < A.c; k++) r_fma(acc, A(i, k), B(k, j));
+      }
+  }
   C = std::move(out);
 }
 // C = A[:, c0:c0+nc] * B      (sub-column view of A, used by the pairings, MPMP.jl:1291-1296)
 void gemm_cols(Mat& C, const Mat& A, int c0, int nc, const Mat& B) {
   Mat out(A.r, B.c);
-  for (int i = 0; i < A.r; i++)
-    for (int j = 0; j < B.c; j++) {
-      Real& acc = out(i, j);
-      for (int k = 0; k < nc; k++) r_fma(acc, A(i, c0 + k), B(k, j));
-    }
+  if (g_gemm_fixed && nc > 0) {
+    gemm_fixed(out, A, c0, nc, B);
+  } else {
+    for (int i = 0; i < A.r; i++)
+      for (int j = 0; j < B.c; j++) {
+        Real& acc = out(i, j);
+        for (int k = 0; k < nc; k++) r_fma(acc, A(i, c0 + k), B(k, j));
+      }
+  }
   C = std::move(out);
 }
 Mat transpose(const Mat& A) {
@@ -152,6 +249,38 @@ void solve_tril(Mat& X, const Mat& Lm, const Mat& B, bool unit) {
   int n = Lm.r, nc = B.c;
   Mat out(n, nc);
   Real s, t;
+  if (g_gemm_fixed && n > 48 && nc > 0) {
+    // blocked forward substitution (libarb's approx_solve_tril is recursive over block products too): the update of a
+    // row block by the rows already solved is a block fixed-point product, the 32 x 32 diagonal blocks are solved
+    // by substitution
+    const int nb = 32;
+    const long prec = B(0, 0).v._mpfr_prec;
+    std::vector<mp_limb_t> ws;
+    for (int r0 = 0; r0 < n; r0 += nb) {
+      const int r1 = std::min(n, r0 + nb);
+      FixedRows FA, FB;
+      if (r0 > 0) {
+        to_fixed(FA, r1 - r0, r0, prec, [&](int r, int k) -> const Real& { return Lm(r0 + r, k); });
+        to_fixed(FB, nc, r0, prec, [&](int c, int k) -> const Real& { return out(k, c); });
+      }
+      for (int c = 0; c < nc; c++)
+        for (int i = r0; i < r1; i++) {
+          if (r0 > 0) {
+            fixed_dot(t, FA, i - r0, FB, c, ws);
+            r_sub(s, B(i, c), t);
+          } else {
+            s = B(i, c);
+          }
+          for (int k = r0; k < i; k++) r_fnma(s, Lm(i, k), out(k, c), t);
+          if (unit)
+            out(i, c) = s;
+          else
+            r_div(out(i, c), s, Lm(i, i));
+        }
+    }
+    X = std::move(out);
+    return;
+  }
   for (int c = 0; c < nc; c++)
     for (int i = 0; i < n; i++) {
       s = B(i, c);
@@ -777,11 +906,21 @@ struct clrsdp_solver {
       for (int q = 0; q < t; q++) lo += (q < nchunk - n_min) ? min_size + 1 : min_size;
       int hi = lo + ((t < nchunk - n_min) ? min_size + 1 : min_size);
       Mat out(n_y, n_y);
-      for (int a = 0; a < n_y; a++)
-        for (int bq = 0; bq < n_y; bq++) {
-          Real& acc = out(a, bq);
-          for (int rr = lo; rr < hi; rr++) r_fma(acc, dec.BTUinv[rowj[rr]](a, rowi[rr]), dec.LinvB[rowj[rr]](rowi[rr], bq));
-        }
+      if (g_gemm_fixed && hi > lo) {
+        FixedRows FA, FB;
+        const long prec = out(0, 0).v._mpfr_prec;
+        to_fixed(FA, n_y, hi - lo, prec, [&](int a, int k) -> const Real& { return dec.BTUinv[rowj[lo + k]](a, rowi[lo + k]); });
+        to_fixed(FB, n_y, hi - lo, prec, [&](int bq, int k) -> const Real& { return dec.LinvB[rowj[lo + k]](rowi[lo + k], bq); });
+        std::vector<mp_limb_t> ws;
+        for (int a = 0; a < n_y; a++)
+          for (int bq = 0; bq < n_y; bq++) fixed_dot(out(a, bq), FA, a, FB, bq, ws);
+      } else {
+        for (int a = 0; a < n_y; a++)
+          for (int bq = 0; bq < n_y; bq++) {
+            Real& acc = out(a, bq);
+            for (int rr = lo; rr < hi; rr++) r_fma(acc, dec.BTUinv[rowj[rr]](a, rowi[rr]), dec.LinvB[rowj[rr]](rowi[rr], bq));
+          }
+      }
       Qp[t] = std::move(out);
     });
     Mat Q(n_y, n_y);
@@ -1171,6 +1310,10 @@ void to_wire(clrsdp_mp_out* o, int64_t i, const Real& x, int nlimb) {
 #define REF_API extern "C" __attribute__((visibility("default")))
 
 REF_API int clrsdp_ref_create(clrsdp_handle* h, int prec_bits, int nthreads) {
+  {
+    const char* gm = getenv("CLRSDP_REF_GEMM");
+    g_gemm_fixed = (gm && std::string(gm) == "fixed") ? 1 : 0;
+  }
   if (!h || prec_bits < 64 || prec_bits % 32) return CLRSDP_ERR_BAD_ARG;
   g_prec = prec_bits;
   clrsdp_solver* s = new clrsdp_solver();

@@ -50,4 +50,12 @@ int mpfr_div_2si(mpfr_ptr, mpfr_srcptr, long, mpfr_rnd_t);
 int mpfr_div_ui(mpfr_ptr, mpfr_srcptr, unsigned long, mpfr_rnd_t);
 int mpfr_mul_si(mpfr_ptr, mpfr_srcptr, long, mpfr_rnd_t);
 void mpfr_swap(mpfr_ptr, mpfr_ptr);
+// libgmp's mpn layer (public ABI names): used by the block fixed-point product (the way libarb's approx_mul works)
+typedef long mp_size_t;
+void __gmpn_mul_n(mp_limb_t*, const mp_limb_t*, const mp_limb_t*, mp_size_t);
+mp_limb_t __gmpn_add_n(mp_limb_t*, const mp_limb_t*, const mp_limb_t*, mp_size_t);
+mp_limb_t __gmpn_sub_n(mp_limb_t*, const mp_limb_t*, const mp_limb_t*, mp_size_t);
+mp_limb_t __gmpn_rshift(mp_limb_t*, const mp_limb_t*, mp_size_t, unsigned int);
+mp_limb_t __gmpn_lshift(mp_limb_t*, const mp_limb_t*, mp_size_t, unsigned int);
+int __gmpn_cmp(const mp_limb_t*, const mp_limb_t*, mp_size_t);
 }
