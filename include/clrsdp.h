@@ -170,6 +170,8 @@ int clrsdp_solve(clrsdp_handle h, clrsdp_iter_info* rows, int max_rows, int* n_r
 /* name: "x","y","dx","dy","p","d","b","c" (vectors), "X","Y","Xinv","R","P","Z","dX","dY","XY"
  * (block (j,l), nb x nb), "S","Sfac","Sinvfac" (cluster j, dim_S x dim_S), "W" (L_j^{-1} B_j, dim_S x n_y),
  * "Q","Qfac" (n_y x n_y), "Px","Py" (pairings of block (j,l), m*Nv x m*Nv), "scalar" (slot j).
+ * "Sfac" / "Sinvfac" are the factors of the EQUILIBRATED Schur complement S' = D^-1 S D^-1 (D a diagonal of powers
+ * of two chosen per iteration): the library never forms L^-1 of S itself; "W" is L^-1 B exactly.
  * Returns the count written (>= 0) or a negative status. out may be NULL to query the count. */
 int64_t clrsdp_fetch(clrsdp_handle h, const char* name, int j, int l, clrsdp_mp_out* out);
 
