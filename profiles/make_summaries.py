@@ -46,10 +46,16 @@ WANT = ["Grid Size", "Block Size", "launch__shared_mem_per_block_dynamic", "laun
         "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-        "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__average_warp_latency_issue_stalled_short_scoreboard.pct",
-        "smsp__average_warp_latency_issue_stalled_barrier.pct", "smsp__average_warp_latency_issue_stalled_wait.pct",
-        "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.pct", "smsp__average_warp_latency_issue_stalled_lg_throttle.pct",
-        "smsp__average_warp_latency_issue_stalled_mio_throttle.pct", "smsp__average_warp_latency_issue_stalled_not_selected.pct"]
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
 
 
 def dump(rep, header, dst):
