@@ -207,4 +207,55 @@ function solverank1sdp(constraints, b, blockinfo; C = 0, b0 = 0, maxiterations =
     end
 end
 
+# ---- problem files (clrsdp/problem_io.py: CLRSDP1) ---------------------------------------------------------------
+# Dumps the reference's own prepareabc output - and, optionally, the result of the reference's solverank1sdp - so that
+# the Python test-suite can pin the oracle and the GPU path against the real reference (tests/golden/).
+function put_arr(io::IO, a::MpArr)
+    write(io, UInt64(length(a.sign)))
+    write(io, a.sign)
+    write(io, a.exp)
+    write(io, a.limb)                 # n x nlimb column-major = limb plane k contiguous = [nlimb][n]
+end
+jstr(v::AbstractVector) = "[" * join(string.(v), ",") * "]"
+
+"""
+    write_problem(path, constraints, b, blockinfo; b0 = 0, solution = nothing)
+
+`solution`: the 11-tuple returned by `solverank1sdp` plus the iteration count, as
+`(x, X, y, Y, primal_obj, dual_obj, iterations)`, or `nothing`.
+"""
+function write_problem(path, constraints, b, bi; b0 = 0, solution = nothing)
+    clusters = String[]
+    for j in 1:bi.J
+        delta = [bi.Y_blocksizes[j][l] ÷ bi.m[j] for l in 1:bi.L[j]]
+        ranks = [jstr([bi.ranks[j][l][k] for k in 1:bi.n_samples[j]]) for l in 1:bi.L[j]]
+        push!(clusters, "{\"m\":$(bi.m[j]),\"K\":$(bi.n_samples[j]),\"L\":$(bi.L[j]),\"delta\":$(jstr(delta)),\"ranks\":[" *
+                        join(ranks, ",") * "]}")
+    end
+    sol = solution === nothing ? "null" :
+          "{\"iterations\":$(solution[7]),\"primal_obj\":\"$(solution[5])\",\"dual_obj\":\"$(solution[6])\",\"has_point\":true}"
+    hdr = "{\"prec\":$(precision(BigFloat)),\"n_y\":$(bi.n_y),\"b0\":\"$(b0)\",\"clusters\":[" * join(clusters, ",") *
+          "],\"solution\":$sol}"
+    open(path, "w") do io
+        write(io, "CLRSDP1\n")
+        write(io, UInt64(sizeof(hdr)))
+        write(io, hdr)
+        put_arr(io, MpArr(b))
+        for (j, (A, B, c, H)) in enumerate(constraints)
+            for l in 1:bi.L[j]
+                put_arr(io, MpArr(vcat(BigFloat[], [midpoints(A[l, k][r]) for k in 1:bi.n_samples[j] for r in 1:length(A[l, k])]...)))
+            end
+            for l in 1:bi.L[j]
+                put_arr(io, MpArr(BigFloat[BigFloat(Arblib.midref(H[l, k][r])) for k in 1:bi.n_samples[j] for r in 1:length(H[l, k])]))
+            end
+            put_arr(io, MpArr(B))
+            put_arr(io, MpArr(c))
+        end
+        if solution !== nothing
+            x, X, y, Y = solution[1:4]
+            put_arr(io, MpArr(x)); put_arr(io, flatten_blocks(X)); put_arr(io, MpArr(y)); put_arr(io, flatten_blocks(Y))
+        end
+    end
+end
+
 end # module

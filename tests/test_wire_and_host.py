@@ -135,3 +135,37 @@ def test_checkpoint_roundtrip_resumes_the_same_trajectory(tmp_path):
     h3 = oracle_handle(256, 1)
     with pytest.raises(ValueError):
         solver.load_checkpoint(tmp_path / "it3", h3, bi)
+
+
+def test_problem_file_roundtrip_is_bit_exact(tmp_path):
+    """clrsdp.problem_io (row f4): constraints, objective and an iterate survive the file bit for bit; a file written by
+    the reference-side shim (julia/ClrsdpB200.jl: write_problem) has the same layout."""
+    from clrsdp import problem_io
+    spec = [dict(m=2, K=3, blocks=[dict(delta=3, ranks=[2, 0, 1]), dict(delta=2, ranks=[1, 1, 1])]),
+            dict(m=1, K=4, blocks=[dict(delta=3, ranks=[1, 2, 1, 1])])]
+    cons, b = instances.random_structured_sdp(spec, n_y=4, prec=192)
+    bi = solver.get_block_info(cons)
+    n_x, n_X = int(sum(bi.dim_S)), int(sum(s * s for row in bi.Y_blocksizes for s in row))
+    rng = np.random.default_rng(3)
+    point = tuple(MpArray.from_scaled_int64(rng.integers(-2 ** 40, 2 ** 40, size=n, dtype=np.int64), -37, 6)
+                  for n in (n_x, n_X, 4, n_X))
+    path = tmp_path / "p.clrsdp"
+    problem_io.save_problem(path, cons, b, b0="3", solution=dict(iterations=17, primal_obj="-0.5", dual_obj="-0.5"),
+                            point=point)
+    cons2, b2, meta = problem_io.load_problem_file(path)
+    same = lambda a, o: np.array_equal(a.sign, o.sign) and np.array_equal(a.exp, o.exp) and np.array_equal(a.limb, o.limb)
+    assert meta["prec"] == 192 and meta["b0"] == "3" and meta["solution"]["iterations"] == 17 and same(b2, b)
+    assert len(cons2) == len(cons)
+    for a, o in zip(cons2, cons):
+        assert same(a.B, o.B) and same(a.c, o.c) and a.B.shape == o.B.shape
+        for l in range(o.L):
+            assert same(a.V[l], o.V[l]) and a.V[l].shape == o.V[l].shape and same(a.H[l], o.H[l])
+            assert list(a.ranks[l]) == list(o.ranks[l])
+    bi2 = solver.get_block_info(cons2)
+    assert (bi2.J, bi2.n_y, list(bi2.dim_S), [list(r) for r in bi2.Y_blocksizes]) == \
+           (bi.J, bi.n_y, list(bi.dim_S), [list(r) for r in bi.Y_blocksizes])
+    assert all(same(a, o) for a, o in zip(meta["point"], point))
+    with open(path, "r+b") as f:
+        f.write(b"X")
+    with pytest.raises(ValueError):
+        problem_io.load_problem_file(path)
