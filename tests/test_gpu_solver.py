@@ -474,3 +474,32 @@ def test_checkpoint_resume_on_the_gpu(tmp_path):
     n_x, n_X = int(sum(bi.dim_S)), int(sum(s * s for row in bi.Y_blocksizes for s in row))
     for a, o in zip(h2.download_point(n_x, n_X, bi.n_y), h1.download_point(n_x, n_X, bi.n_y)):
         assert np.array_equal(a.sign, o.sign) and np.array_equal(a.exp, o.exp) and np.array_equal(a.limb, o.limb)
+
+
+def _reference_files():
+    import glob
+    import os
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.clrsdp")))
+
+
+@pytest.mark.parametrize("path", _reference_files() or [None])
+def test_gpu_against_reference_problem_files(path):
+    """The GPU path against the REAL reference's result, for every CLRSDP1 file under tests/golden/ (written by
+    julia/ClrsdpB200.jl where Julia + Arblib exist; see test_oracle_pin.py). Skipped while there is none."""
+    if path is None:
+        pytest.skip("no tests/golden/*.clrsdp reference file present (needs Julia + Arblib to produce)")
+    from clrsdp import problem_io
+    cons, b, meta = problem_io.load_problem_file(path)
+    prec = meta["prec"]
+    bi = solver.get_block_info(cons)
+    solver.set_precision(prec)
+    try:
+        out, rows = solver.solverank1sdp(cons, b, bi, b0=mpmath.mpf(meta["b0"]), verbose=False, return_info=True)
+    finally:
+        solver.set_precision(256)
+    sol = meta["solution"]
+    assert sol is not None and len(rows) == sol["iterations"]
+    with mpmath.workprec(prec):
+        tol = mpmath.mpf(2) ** -(prec - 16 - 64)
+        assert abs(out[8] - mpmath.mpf(sol["primal_obj"])) <= abs(mpmath.mpf(sol["primal_obj"])) * tol
+        assert abs(out[9] - mpmath.mpf(sol["dual_obj"])) <= abs(mpmath.mpf(sol["dual_obj"])) * tol
