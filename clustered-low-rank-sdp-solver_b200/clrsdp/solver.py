@@ -269,6 +269,10 @@ def _print_timings(rows, time_total):
     print("Time inside search directions (both predictor & corrector step)")
     print("%11s %11s %11s %11s %11s" % ("calc Z", "calc rhs x", "solve system", "calc dX", "calc dY"))
     print(("%11.5e " * 5) % tuple(t[12:17]))
+    if len(rows) > 2 and not t.any():
+        print("(per-phase times are only collected when the iteration is launched kernel by kernel: CLRSDP_GRAPH=0; "
+              "the default replays it from a CUDA graph and reports the total per iteration, `seconds`, only: "
+              "%.5e s over the same iterations)" % sum(r.seconds for r in rows[2:]))
 
 
 # ---- check-pointing the iterate (the reference's warm start: initial_solutions, MPMP.jl:613, :689) ----
