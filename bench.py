@@ -49,32 +49,55 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md): NVML when the binding is importable (a
+    sample every ~5 ms), else nvidia-smi (one sample per ~60 ms process start)."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.rows, self.stop_flag, self.index = [], False, index
+        self.rows, self.stop_flag, self.index = [], False, index   # rows: (sm_mhz, sm_max_mhz, set of reasons)
+        self.how = "nvidia-smi"
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        hd = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(hd, nv.NVML_CLOCK_SM))
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        self.how = "nvml"
+        while not self.stop_flag:
+            sm = float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(hd))
+            self.rows.append((sm, mx, {n for b, n in bits if r & b}))
+            time.sleep(0.005)
 
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            self.how = "nvidia-smi"
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                c = [v.strip() for v in out.split(",")]
+                if len(c) >= 6:
+                    self.rows.append((float(c[0]), float(c[1]), {self.NAMES[i] for i in range(4) if c[2 + i].lower().startswith("active")}))
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = sorted(set().union(*[r[2] for r in self.rows])) if self.rows else []
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(self.rows))
+                    samples=len(self.rows), how=self.how)
 
 
 def build_problem(J, j_offset, j_total, nl_prec):
@@ -106,74 +129,97 @@ def algorithmic_int8_macs(bi, prec):
     return pmac * per, pmac
 
 
-def _time_oracle(n_threads, sample_J, iters, gemm_mode):
+def config_dict(workload_name, world):
+    """The `config` object of the JSON line: identical for the GPU arm and for `--impl reference`."""
+    Jloc = WORKLOAD["J_per_gpu"]
+    return dict(workload=("synthetic clustered low-rank SDP, BASELINE config 3 per GPU " if workload_name == "cfg3" else
+                          "synthetic clustered low-rank SDP, one GPU's share (64 clusters) of BASELINE config 5 ") +
+                         "(manufactured strictly feasible; iterations from omega*I)",
+                clusters_total=world * Jloc, l2="working set > L2 (several hundred MB of arenas touched per "
+                "iteration); no explicit flush", **WORKLOAD)
+
+
+def _time_oracle(n_threads, J, iters, gemm_mode, discard=1):
+    """Wall-clock seconds of `iters` FULL interior-point iterations of the oracle on J clusters (no sub-sampling, no
+    extrapolation), after `discard` untimed ones: the first iteration starts from omega*I, whose zero off-diagonal
+    entries make MPFR products cheaper than in any later iteration (the reference drops its first two, MPMP.jl:889)."""
     from clrsdp import solver
     from oracle.ref import oracle_handle
-    Jfull = WORKLOAD["J_per_gpu"]
-    cons, b, bi = build_problem(sample_J, 0, sample_J, WORKLOAD["prec"])
+    cons, b, bi = build_problem(J, 0, J, WORKLOAD["prec"])
     if gemm_mode:
         os.environ["CLRSDP_REF_GEMM"] = gemm_mode      # read by the oracle when a handle is created
     else:
         os.environ.pop("CLRSDP_REF_GEMM", None)
     h = oracle_handle(WORKLOAD["prec"], n_threads)
+    os.environ.pop("CLRSDP_REF_GEMM", None)
     solver.load_problem(h, cons, b, bi)
     h.set_params(solver.real_params(h.nlimb))
     h.init_point()
     h.prepare()
     per_iter = []
-    for _ in range(iters):
+    for i in range(discard + iters):
         t0 = time.time()
-        r = h.iterate()
-        dt = time.time() - t0
-        tq = r.timings[11]  # chol_Q: independent of J
-        per_iter.append((dt - tq) * (Jfull / sample_J) + tq)
+        h.iterate()
+        if i >= discard:
+            per_iter.append(time.time() - t0)
     h.close()
-    os.environ.pop("CLRSDP_REF_GEMM", None)
-    return float(np.mean(per_iter))
+    return per_iter
 
 
-def cpu_baseline(n_threads, sample_J=None, iters=1, both=True):
-    """The oracle (CPU restatement of MPMP.jl, MPFR) timed on a bounded sample: `sample_J` clusters of the
-    same shape instead of 64; per-cluster phases scale linearly with J, the factorisation of Q does not.
+def cpu_baseline(n_threads, J=None, iters=1, both=False):
+    """The oracle (CPU restatement of MPMP.jl, MPFR; the reference itself - Julia + Arb - cannot run in this image) timed
+    on the host cores on the SAME instance as the GPU arm: all J clusters, whole iterations, nothing extrapolated.
     `value` is timed with the oracle's block fixed-point product (CLRSDP_REF_GEMM=fixed: exact integer dot products
     over mpn limbs, one rounding per entry - the way libarb's approx_mul works); the time with classical
     mpfr_fma triple loops (what the parity tests run) is reported beside it."""
-    Jfull = WORKLOAD["J_per_gpu"]
-    sample_J = sample_J or max(1, min(Jfull, n_threads // 2 if n_threads >= 4 else 2))
-    v_fixed = _time_oracle(n_threads, sample_J, iters, "fixed")
-    out = dict(value=v_fixed, unit=UNIT, cores=n_threads, kind="port",
-               sample=f"{iters} iteration(s) of the MPFR restatement (oracle/, block fixed-point GEMM over mpn limbs like "
-                      f"libarb's approx_mul) on {sample_J} of {Jfull} clusters (same delta/K/n_y), per-cluster phases scaled "
-                      f"x{Jfull / sample_J:g}, Q factorisation unscaled; the reference itself (Julia+Arb) cannot run in this image")
+    J = J or WORKLOAD["J_per_gpu"]
+    t_fixed = _time_oracle(n_threads, J, iters, "fixed")
+    out = dict(value=float(np.mean(t_fixed)), unit=UNIT, cores=n_threads, kind="port", clusters=J, iterations_timed=len(t_fixed),
+               per_iteration_s=[round(t, 3) for t in t_fixed],
+               sample=f"{len(t_fixed)} whole iteration(s) (after 1 untimed from omega*I) of the MPFR restatement (oracle/, block "
+                      f"fixed-point GEMM over mpn limbs like libarb's approx_mul) on all {J} clusters of the workload, "
+                      f"{n_threads} threads over the clusters / blocks / Q chunks like the reference's Threads.@threads; "
+                      "the reference itself (Julia+Arb) cannot run in this image")
     if both:
-        out["value_mpfr_fma_loops"] = _time_oracle(n_threads, sample_J, iters, None)
+        out["value_mpfr_fma_loops"] = float(np.mean(_time_oracle(n_threads, J, 1, None)))
     return out
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU path for the same metric and config. Every timed step is one WHOLE
+    iteration on the GPU arm's instance (64 clusters per GPU x N GPUs) on all host cores; `steps` is the number of
+    iterations actually timed (the run is capped at a few minutes whatever K is). Should the N-GPU instance not fit that
+    cap on this host, fewer clusters are timed and `work_ratio` (GPU-arm work / timed work) says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_threads = os.cpu_count() or 1
-    vals = []
-    last = None
-    # one repetition (a bounded sample: n_threads/2 of the 64 clusters, extrapolated) takes a few seconds; the run is
-    # capped at about two minutes of CPU time whatever K is: `steps` reports the repetitions actually timed
+    Jloc, world = WORKLOAD["J_per_gpu"], max(1, args.gpus)
+    budget = 200.0
     t_begin = time.time()
-    cpu_baseline(n_threads, iters=1, both=False)           # warm-up (library load, page faults)
-    t_rep = max(0.5, time.time() - t_begin)
-    reps = int(max(1, min(args.steps, 120.0 / t_rep)))
-    for _ in range(reps):
-        last = cpu_baseline(n_threads, iters=1, both=False)
-        vals.append(last["value"])
-    args.steps_requested, args.steps = args.steps, reps
+    t64 = _time_oracle(n_threads, Jloc, 1, "fixed", discard=1)[0]      # also the warm-up (library load, page faults)
+    J = Jloc * world
+    if world > 1 and 2.5 * t64 * world > budget:                       # (1 discarded + >= 1 timed iteration must fit)
+        J = Jloc * max(1, min(world, int(budget / (2.5 * t64))))
+    if J == Jloc:
+        reps = int(max(1, min(args.steps, (budget - (time.time() - t_begin)) / max(t64, 1e-3))))
+        vals = [t64] + (_time_oracle(n_threads, J, reps - 1, "fixed") if reps > 1 else [])
+    else:
+        est = t64 * J / Jloc
+        reps = int(max(1, min(args.steps, (budget - (time.time() - t_begin)) / est - 1)))
+        vals = _time_oracle(n_threads, J, reps, "fixed")
     v = float(np.mean(vals))
-    last["value"] = v
-    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=v * 1e3, higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f256 (MPFR)",
-                data="synthetic", impl="reference", steps_requested=args.steps_requested,
-                config=dict(workload="synthetic clustered low-rank SDP, BASELINE config 3 per GPU", **WORKLOAD),
-                cpu_baseline=last, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    cb = dict(value=v, unit=UNIT, cores=n_threads, kind="port", clusters=J, iterations_timed=len(vals),
+              per_iteration_s=[round(t, 3) for t in vals],
+              sample=f"{len(vals)} whole iteration(s) of the MPFR restatement (oracle/, block fixed-point GEMM over mpn limbs like "
+                     f"libarb's approx_mul) on {J} clusters, {n_threads} threads; nothing extrapolated")
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=len(vals), warmup=1,
+                ms_per_step=v * 1e3, higher_is_better=False, scaling="weak", vs_baseline=None,
+                dtype=f"u{WORKLOAD['prec']} fixed-limb float (int8 slices, int32 accumulate)", data="synthetic",
+                impl="reference", steps_requested=args.steps, warmup_requested=args.warmup,
+                config=config_dict(args.workload, world), work_ratio=(Jloc * world) / J,
+                reference_dtype=f"f{WORKLOAD['prec']} (MPFR round-to-nearest; block fixed-point products)",
+                cpu_baseline=cb, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
 
@@ -184,6 +230,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-fma", action="store_true", help="also time the oracle with classical mpfr_fma product loops")
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table here")
     args = ap.parse_args()
@@ -367,11 +414,7 @@ def main():
     line = dict(metric=METRIC, value=sec_per_iter, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec_per_iter * 1e3, higher_is_better=False, scaling="weak", vs_baseline=None,
                 dtype=f"u{prec} fixed-limb float (int8 slices, int32 accumulate)", data="synthetic",
-                config=dict(workload=("synthetic clustered low-rank SDP, BASELINE config 3 per GPU " if args.workload == "cfg3" else
-                                      "synthetic clustered low-rank SDP, one GPU's share (64 clusters) of BASELINE config 5 ") +
-                                     "(manufactured strictly feasible; iterations from omega*I)",
-                            clusters_total=world * Jloc, l2="working set > L2 (several hundred MB of arenas touched per "
-                            "iteration); no explicit flush", **WORKLOAD),
+                config=config_dict(args.workload, world),
                 wall_ms_per_step=wall / args.steps * 1e3,
                 e2e=dict(value=e2e_wall / args.steps, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          parts_ms=dict(zip(["upload_point", "prepare", "iterate", "download_point"],
@@ -381,7 +424,7 @@ def main():
                 algorithmic=dict(pmac_per_iter=pmac, int8_mac_per_iter=macs))
     if not args.no_cpu_baseline and world == 1:
         try:
-            line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1, both=args.cpu_fma)
         except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
             line["cpu_baseline"] = dict(error=str(e))
     if args.profile_out:

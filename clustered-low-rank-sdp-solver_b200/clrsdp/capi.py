@@ -27,6 +27,7 @@ STATUS = {
     -10: "X block not positive definite", -11: "Y block not positive definite",
     -12: "S could not be factorised", -13: "Q could not be factorised",
     -14: "step-length eigenvalue failed", -15: "call order violated",
+    -16: "the iterate was lost (mu, a step length or an objective is zero, negative or not finite)",
 }
 TERMINATE = {0: "running", 1: "Primal feasible solution found", 2: "Dual feasible solution found",
              3: "Optimal solution found", 4: "maximum iterations reached"}
@@ -61,7 +62,7 @@ class ClrsdpError(RuntimeError):
     def __init__(self, code, where, detail=""):
         self.code = code
         msg = f"{where}: {STATUS.get(code, code)}"
-        if code in (-10, -11, -12, -13, -14):
+        if code in (-10, -11, -12, -13, -14, -16):
             # the reference's error strings (MPMP.jl:793,1439,1503,1882)
             msg += " — try again with higher precision"
         if detail:
@@ -264,6 +265,18 @@ class Handle:
         sa, sl, si = A.c_struct(), L.c_struct(), Li.c_struct()
         self._check(f(self._h, batch, n, ctypes.byref(sa), ctypes.byref(sl), ctypes.byref(si)), "op_cholesky")
         return L.reshape(batch, n, n), Li.reshape(batch, n, n)
+
+    def op_signed_factor(self, batch, n, A: MpArray):
+        """(M, signs) with A^-1 = M^T diag(signs) M per matrix of the batch (include/clrsdp.h)."""
+        M = MpArray(batch * n * n, self.nlimb)
+        signs = np.zeros(batch * n, dtype=np.int32)
+        f = self._fn("op_signed_factor")
+        mp = ctypes.POINTER(clrsdp_mp)
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, mp, mp, ctypes.POINTER(ctypes.c_int32)]
+        sa, sm = A.c_struct(), M.c_struct()
+        self._check(f(self._h, batch, n, ctypes.byref(sa), ctypes.byref(sm),
+                      signs.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))), "op_signed_factor")
+        return M.reshape(batch, n, n), signs.reshape(batch, n)
 
     def op_lambda_min(self, batch, n, A: MpArray) -> MpArray:
         lam = MpArray(batch, self.nlimb)

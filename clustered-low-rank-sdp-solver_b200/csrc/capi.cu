@@ -151,6 +151,14 @@ CAPI int clrsdp_op_cholesky(clrsdp_handle h, int batch, int n, const clrsdp_mp* 
     return s.op_cholesky(batch, n, A, L, Linv);
   });
 }
+CAPI int clrsdp_op_signed_factor(clrsdp_handle h, int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* Minv,
+                                 int32_t* signs) {
+  return guard(h, [&](clr::Solver& s) {
+    if (!A || !Minv || !signs || batch <= 0 || n <= 0) return (int)CLRSDP_ERR_BAD_ARG;
+    s.op_signed_factor(batch, n, A, Minv, signs);
+    return 0;
+  });
+}
 CAPI int clrsdp_op_lambda_min(clrsdp_handle h, int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lam) {
   return guard(h, [&](clr::Solver& s) {
     if (!A || !lam) return (int)CLRSDP_ERR_BAD_ARG;

@@ -23,6 +23,8 @@ struct GatherArgs {
   int64_t off0, bstride, rs, ks;
   int batch, rows, K, Kp, rows_total;
   const int* kshift;  // optional [batch][K]: entry (b, r, k) is taken as x * 2^-kshift[b*K + k] (exact)
+  const int* ksign;   // optional [batch][ksign_ld]: entry (b, r, k) is negated where ksign[b*ksign_ld + k] != 0
+  int ksign_ld;
 };
 
 __device__ __forceinline__ int64_t item_off(const GatherArgs& g, int b) {
@@ -53,7 +55,7 @@ __device__ __forceinline__ void fixed_point_digits(const GatherArgs& g, int b, i
         for (int i = 0; i < NL; i++) W[i + 2] = x.m[i];
         if (sr >> 5) mp::shr_limbs<NLW>(W, sr >> 5);
         if (sr & 31u) mp::shr_bits<NLW>(W, sr & 31u);
-        negf = x.neg != 0;
+        negf = (x.neg != 0) != (g.ksign != nullptr && g.ksign[(int64_t)b * g.ksign_ld + k] != 0);
       }
     }
   }
@@ -771,7 +773,7 @@ static void slice_impl(Ctx& ctx, const OperandDesc& op, Slice& out) {
   size_t bytes = (size_t)S * out.rows_total * Kp;
   out.digits.ensure(bytes);
   out.exps.ensure(sizeof(int32_t) * (size_t)std::max(out.rows_total, 1));
-  GatherArgs g{op.src.w, op.src.n, op.d_off, op.off0, op.bstride, op.rs, op.ks, op.batch, op.rows, K, Kp, out.rows_total, op.d_kshift};
+  GatherArgs g{op.src.w, op.src.n, op.d_off, op.off0, op.bstride, op.rs, op.ks, op.batch, op.rows, K, Kp, out.rows_total, op.d_kshift, op.d_ksign, op.ksign_ld};
   int64_t total = (int64_t)out.rows_total * Kp;
   // long rows (or few of them) get a whole block per row, short rows one warp
   int wpr = (Kp > 256 || (int64_t)out.rows_total * 32 < (int64_t)ctx.sm_count * 256) ? 8 : 1;
@@ -935,7 +937,7 @@ static void split_k(int sm_count, int T, int Kp, int BK, int64_t tiles, int& Kc,
 
 void GemmEngine::multiply(const Slice& A, const Slice& B, const GemmPlan& plan, const OutDesc& C, int epi,
                           const mp::Tensor* extra, bool symmetric) {
-  if (symmetric && (&A != &B || plan.M != plan.N || plan.d_rowA || plan.d_rowB)) symmetric = false;
+  if (symmetric && (A.rows_total != B.rows_total || plan.M != plan.N || plan.d_rowA || plan.d_rowB)) symmetric = false;
   if (A.Kp != B.Kp || A.S != S_ || B.S != S_) throw SolverError(-1, "gemm: operand mismatch");
   const int T = S_;
   const int BK = std::min(A.Kp, bk_cap()), BN = bn_for(plan, ctx_.sm_count, symmetric), stack = stack_of(plan.M);

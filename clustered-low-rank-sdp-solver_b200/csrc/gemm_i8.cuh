@@ -27,6 +27,10 @@ struct OperandDesc {
   // optional [batch][K] exponents: the operand is sliced as x(b, r, k) * 2^-d_kshift[b*K + k] (exact scaling of the
   // contraction index, e.g. D^-1 B with the equilibration D of the matrix that B is multiplied into)
   const int* d_kshift = nullptr;
+  // optional [batch][ksign_ld] flags: entry (b, r, k) is negated where d_ksign[b*ksign_ld + k] != 0 (the Sigma of a
+  // signed factorisation A = U^T Sigma U applied to the contraction index)
+  const int* d_ksign = nullptr;
+  int ksign_ld = 0;
 };
 // destination of a product: element (b, i, j) at off(b) + i*rs + j*cs, off(b) as above
 struct OutDesc {
@@ -61,8 +65,9 @@ class GemmEngine {
   GemmEngine(Ctx& c, int nl);
   void slice(const OperandDesc& op, Slice& out);
   // C = A * B (row-operand form) with optional epilogue; E uses C's addressing on tensor `extra`
-  // `symmetric` (same slice on both sides, C = A A^T): only the tiles touching the upper triangle are computed, the
-  // carry kernel mirrors them
+  // `symmetric`: the caller guarantees C = C^T and that row i of A and row i of B have the same exponent (the same
+  // slice on both sides, or two slices of one operand that differ by signs only): only the tiles touching the upper
+  // triangle are computed, the carry kernel mirrors them
   void multiply(const Slice& A, const Slice& B, const GemmPlan& plan, const OutDesc& C, int epi = EPI_STORE,
                 const mp::Tensor* extra = nullptr, bool symmetric = false);
   // exact integer planes for tests: planes [T][batch][M][N] (splits already summed must be 1)

@@ -229,7 +229,7 @@ template <int NL>
 __global__ void __launch_bounds__(PANEL_THREADS)
 panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shiftA, int ldA, mp::Tensor Lm,
                     const int64_t* __restrict__ offL, int64_t shiftL, int ldL, int w, int write_u,
-                    int* __restrict__ status, int relaxed) {
+                    int* __restrict__ status, int* __restrict__ sig, int sig_ld) {
   extern __shared__ uint32_t sm[];
   const int ntri = w * (w + 1) / 2;
   uint32_t* Us = sm;                                  // packed upper triangle of the scaled work matrix R'
@@ -245,15 +245,23 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
     if (c <= r) smem_put<NL>(Gs, pk_g(r, c), (r == 0 && c == 0) ? mp::one<NL>() : mp::zero<NL>());
   }
   __syncthreads();
-  // `relaxed` (Schur complement and Q, which the reference factors by LU and never tests for definiteness,
-  // MPMP.jl:1436,1501): a pivot that is not above the rounding level of the equilibrated matrix, 2^-(p-16), is replaced
-  // by that level instead of ending the factorisation - a backward perturbation of the size of the rounding errors
-  // already in the matrix (what a pivoted LU does implicitly when the matrix is singular to working precision).
+  // SIGNED mode (sig != nullptr: the Schur complements S_j and Q, which the reference factors by pivoted LU and never
+  // tests for definiteness, MPMP.jl:1436,1501): the factorisation is A = U^T Sigma U with Sigma = diag(+-1), i.e. an
+  // LDL^T whose pivots keep their sign. Near the optimum S_j is singular to working precision and its computed trailing
+  // pivots come out with either sign; a Cholesky factorisation has to perturb them (by far more than their rounding
+  // error) to go on, which destroys the search direction, whereas the signed factorisation is backward stable at the
+  // rounding level like the LU. The elimination below never divides, so a negative pivot costs nothing: the common row
+  // scale tau just carries its sign. Only a pivot that is exactly zero or below 2^-(p+8) times the scale of its row is
+  // replaced (by that bound, sign kept) - a perturbation below the rounding errors already in the matrix.
+  constexpr int FLOOR_BITS = 32 * NL + 8;
   if (tid == 0) {
     Num<NL> a = smem_get<NL>(Us, pk_u(w, 0, 0));
-    if (relaxed) {
-      Num<NL> thr = mp::from_pow2<NL>(-(32 * NL - 16));
-      if (mp::is_zero(a) || a.neg || ncmp(a, thr) < 0) smem_put<NL>(Us, pk_u(w, 0, 0), thr);
+    if (sig) {
+      if (mp::is_zero(a) || a.e <= -FLOOR_BITS) {
+        Num<NL> f = mp::from_pow2<NL>(-FLOOR_BITS);
+        f.neg = mp::is_zero(a) ? 0u : a.neg;
+        smem_put<NL>(Us, pk_u(w, 0, 0), f);
+      }
     } else if (mp::is_zero(a) || a.neg) {
       bad = 1;
     }
@@ -270,10 +278,14 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
       __syncwarp();
       if (lane == 0) {
         Num<NL> a = smem_get<NL>(Us, pk_u(w, r, r));
-        if (relaxed) {  // the unpivoted rows carry the scale tau_{k+1} = mu_k tau_k: threshold by exponents only (no
-                        // multiplication on the pivot chain): a < 2^te  <=>  a.e <= te
-          const int te = smem_get<NL>(Gs, pk_g(k, k)).e - (32 * NL - 16);
-          if (mp::is_zero(a) || a.neg || a.e <= te) smem_put<NL>(Us, pk_u(w, r, r), mp::from_pow2<NL>(te));
+        if (sig) {  // the unpivoted rows carry the scale tau_{k+1} = mu_k tau_k: threshold by exponents only (no
+                    // multiplication on the pivot chain): |a| < 2^te  <=>  a.e <= te
+          const int te = smem_get<NL>(Gs, pk_g(k, k)).e - FLOOR_BITS;
+          if (mp::is_zero(a) || a.e <= te) {
+            Num<NL> f = mp::from_pow2<NL>(te);
+            f.neg = mp::is_zero(a) ? 0u : a.neg;
+            smem_put<NL>(Us, pk_u(w, r, r), f);
+          }
         } else if (mp::is_zero(a) || a.neg) {
           bad = 1;
         }
@@ -300,9 +312,19 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
     }
     __syncthreads();
   }
-  // f_k = rsqrt(tau_k d'_k), one row per lane
+  // f_k = rsqrt(|tau_k d'_k|), one row per lane. Signed mode: the true pivot d_k = d'_k / tau_k has the sign
+  // sigma_k = sign(tau_k d'_k); row k of L^-1 (L = U^T) is G'_k * sign(tau_k) f_k, row k of U is R'_k * sign(d'_k) f_k.
+  __shared__ uint32_t sgn_tau[PANEL_W], sgn_d[PANEL_W];
   if (warp == 0 && !bad && lane < w) {
-    Num<NL> f, root = nsqrt_rsqrt(nmul(smem_get<NL>(Gs, pk_g(lane, lane)), smem_get<NL>(Us, pk_u(w, lane, lane))), f);
+    Num<NL> tau = smem_get<NL>(Gs, pk_g(lane, lane)), dk = smem_get<NL>(Us, pk_u(w, lane, lane));
+    sgn_tau[lane] = sig ? tau.neg : 0u;
+    sgn_d[lane] = sig ? dk.neg : 0u;
+    Num<NL> prod = nmul(tau, dk);
+    if (sig) {
+      sig[(int64_t)b * sig_ld + lane] = (int)prod.neg;
+      prod.neg = 0u;
+    }
+    Num<NL> f, root = nsqrt_rsqrt(prod, f);
     (void)root;
     smem_put<NL>(Fs, lane, f);
   }
@@ -311,14 +333,21 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
     for (int idx = tid; idx < w * w; idx += nthr) {
       int r = idx / w, c = idx % w;
       Num<NL> f = smem_get<NL>(Fs, r);
-      if (write_u) stm<NL>(A, oa + (int64_t)r * ldA + c, r <= c ? nmul(smem_get<NL>(Us, pk_u(w, r, c)), f) : mp::zero<NL>());
-      stm<NL>(Lm, ol + (int64_t)r * ldL + c, c <= r ? nmul(smem_get<NL>(Gs, pk_g(r, c)), f) : mp::zero<NL>());
+      if (write_u) {
+        Num<NL> u = r <= c ? nmul(smem_get<NL>(Us, pk_u(w, r, c)), f) : mp::zero<NL>();
+        if (sgn_d[r] && !mp::is_zero(u)) u.neg ^= 1u;
+        stm<NL>(A, oa + (int64_t)r * ldA + c, u);
+      }
+      Num<NL> g = c <= r ? nmul(smem_get<NL>(Gs, pk_g(r, c)), f) : mp::zero<NL>();
+      if (sgn_tau[r] && !mp::is_zero(g)) g.neg ^= 1u;
+      stm<NL>(Lm, ol + (int64_t)r * ldL + c, g);
     }
   }
   if (tid == 0) status[b] = bad;
 }
 int panel_width(int nl) { (void)nl; return PANEL_W; }
-void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status, bool relaxed) {
+void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status, int* d_sig,
+                  int sig_ld) {
   if (A.n > panel_width(nl)) throw SolverError(-1, "panel_factor: block larger than the panel width");
   DISPATCH_NL(nl, {
     size_t words = ((size_t)A.n * (A.n + 1) + A.n) * (NL + 2);
@@ -331,7 +360,7 @@ void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, boo
     int tk = ctx.begin(nm.c_str());
     panel_factor_kernel<NL><<<A.batch, PANEL_THREADS, words * sizeof(uint32_t), ctx.stream>>>(
         A.t, A.d_off, A.shift, A.stride(), Linv.t, Linv.d_off, Linv.shift, Linv.stride(), A.n, write_u ? 1 : 0,
-        d_status, relaxed ? 1 : 0);
+        d_status, d_sig, sig_ld);
     ctx.end(tk);
   });
 }
@@ -1358,6 +1387,19 @@ __global__ void scatter_scale_kernel(const int* __restrict__ src, int batch, int
   int b = idx / n, i = idx - b * n;
   dst[off[b] + i] = src[idx];
 }
+// v[off + i] = -v[off + i] where sg[i] != 0 (headers only)
+__global__ void vec_flip_kernel(uint32_t* __restrict__ hdr, int64_t n, const int* __restrict__ sg) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t h = hdr[i];
+    if (sg[i] && (((int32_t)h) >> 1) != mp::EXP_ZERO) hdr[i] = h ^ 1u;
+  }
+}
+void vec_flip(Ctx& ctx, int nl, mp::Tensor v, int64_t off, int64_t n, const int* d_sig) {
+  if (n <= 0) return;
+  int tk = ctx.begin("vec_flip", (double)n * 12.0);
+  vec_flip_kernel<<<ew_grid(ctx, n), 128, 0, ctx.stream>>>(v.w + (size_t)nl * v.n + off, n, d_sig);
+  ctx.end(tk);
+}
 void vec_scale(Ctx& ctx, int nl, mp::Tensor v, int64_t off, int64_t n, int sign, const int* d_scale) {
   if (n <= 0) return;
   int tk = ctx.begin("vec_scale", (double)n * 12.0);
@@ -1619,6 +1661,8 @@ struct SmallGemmDev {
   const int64_t* offC;
   int64_t a0, abs_, ars, aks, b0, bbs, brs, bks, c0, cbs, crs, ccs;
   int batch, M, N, K, ks_log, epi;
+  const int* ksign;  // optional [batch][ksign_ld]: term k of item b enters with a minus sign where ksign != 0
+  int ksign_ld;
 };
 template <int NL>
 __global__ void __launch_bounds__(256) small_gemm_kernel(SmallGemmDev g) {
@@ -1636,8 +1680,12 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(SmallGemmDev g) {
     b = (int)(out / ((int64_t)g.N * g.M));
     const int64_t ab = g.a0 + (g.offA ? g.offA[b] : (int64_t)b * g.abs_) + (int64_t)i * g.ars;
     const int64_t bb = g.b0 + (g.offB ? g.offB[b] : (int64_t)b * g.bbs) + (int64_t)j * g.brs;
-    for (int k = part; k < g.K; k += KS)
-      acc = mp::add(acc, mp::mul(ldm<NL>(g.A, ab + (int64_t)k * g.aks), ldm<NL>(g.B, bb + (int64_t)k * g.bks)));
+    const int* ksg = g.ksign ? g.ksign + (int64_t)b * g.ksign_ld : nullptr;
+    for (int k = part; k < g.K; k += KS) {
+      Num<NL> t = mp::mul(ldm<NL>(g.A, ab + (int64_t)k * g.aks), ldm<NL>(g.B, bb + (int64_t)k * g.bks));
+      if (ksg && ksg[k] && !mp::is_zero(t)) t.neg ^= 1u;
+      acc = mp::add(acc, t);
+    }
   }
 #pragma unroll 1
   for (int o = KS >> 1; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
@@ -1692,6 +1740,7 @@ void small_gemm(Ctx& ctx, int nl, const SmallGemmArgs& a) {
   g.b0 = a.b0, g.bbs = a.bbs, g.brs = a.brs, g.bks = a.bks;
   g.c0 = a.c0, g.cbs = a.cbs, g.crs = a.crs, g.ccs = a.ccs;
   g.batch = a.batch, g.M = a.M, g.N = a.N, g.K = a.K, g.epi = a.epi;
+  g.ksign = a.ksign, g.ksign_ld = a.ksign_ld;
   const int64_t outs = (int64_t)a.batch * a.M * a.N;
   if (outs <= 0) return;
   // split K over adjacent lanes until the grid fills the machine (about 4 x 256 threads per SM)
@@ -1923,7 +1972,16 @@ void combine_ranks(Ctx& ctx, int nl, const uint32_t* gathered, int nranks, int64
 // driver scalars (single thread; the reference does these in Arb on the host, MPMP.jl:755-756 etc.)
 // =========================================================================================================
 template <int NL>
-__global__ void scalar_kernel(int prog, mp::Tensor sc, int* flags, double* dout) {
+__global__ void scalar_kernel(int prog, mp::Tensor sc, int* flags, double* dout, const int* __restrict__ status,
+                              int n_status) {
+  // a failed factorisation (X or Y not positive definite) must not reach the update: the step lengths become zero, so
+  // the iterate of the last good iteration stays on the device for a resume at higher precision (the reference raises
+  // before its update, MPMP.jl:793 precedes :877)
+  int failed = 0;
+  if (status) {
+    for (int i = threadIdx.x; i < n_status; i += 32) failed |= status[i];
+    failed = __any_sync(0xffffffffu, failed != 0);
+  }
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   auto G = [&](int s) { return ldm<NL>(sc, s); };
   auto Pp = [&](int s, const Num<NL>& v) { stm<NL>(sc, s, v); };
@@ -1952,6 +2010,7 @@ __global__ void scalar_kernel(int prog, mp::Tensor sc, int* flags, double* dout)
       if (ncmp(ad, ap) < 0) ap = ad;
       ad = ap;
     }
+    if (failed) ap = ad = mp::zero<NL>();
     Pp(SL_ALPHA_P, ap);
     Pp(SL_ALPHA_D, ad);
   } else if (prog == SP_OBJECTIVES || prog == SP_OBJECTIVES_INIT) {  // objectives and gap (:1027-1034, :1067-1078)
@@ -1981,10 +2040,11 @@ __global__ void scalar_kernel(int prog, mp::Tensor sc, int* flags, double* dout)
   if (dout)
     for (int s = 0; s < SL_COUNT; s++) dout[s] = mp::to_double(G(s));
 }
-void scalar_program(Ctx& ctx, int nl, int prog, mp::Tensor scal, int* d_flags, double* d_out) {
+void scalar_program(Ctx& ctx, int nl, int prog, mp::Tensor scal, int* d_flags, double* d_out, const int* d_status,
+                    int n_status) {
   DISPATCH_NL(nl, {
     int tk = ctx.begin("scalar_program");
-    scalar_kernel<NL><<<1, 32, 0, ctx.stream>>>(prog, scal, d_flags, d_out);
+    scalar_kernel<NL><<<1, 32, 0, ctx.stream>>>(prog, scal, d_flags, d_out, d_status, n_status);
     ctx.end(tk);
   });
 }

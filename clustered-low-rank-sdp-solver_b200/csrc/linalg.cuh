@@ -35,10 +35,11 @@ void tri_inverse(Ctx& ctx, int nl, const MatBatch& U, mp::Tensor rdiag, const Ma
 // Fused panel factorisation of w x w SPD blocks (w <= panel_width(nl)): A is overwritten by its upper Cholesky
 // factor U (if write_u) and Linv receives L^-1 = U^-T (lower); both may be sub-blocks of larger matrices.
 int panel_width(int nl);
-// `relaxed`: pivots at or below the rounding level 2^-(p-16) of the (equilibrated) block are raised to it instead of
-// reporting the matrix as not positive definite.
+// With d_sig the factorisation is SIGNED, A = U^T Sigma U with Sigma = diag(+-1) (an LDL^T whose pivots keep their sign;
+// what stands in for the reference's pivoted LU of S_j and Q, MPMP.jl:1436,1501): d_sig[b*sig_ld + k] = 1 where the
+// pivot of row k is negative, nothing is reported as "not positive definite", and Linv = L^-1 with L = U^T.
 void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status,
-                  bool relaxed = false);
+                  int* d_sig = nullptr, int sig_ld = 0);
 // smallest eigenvalue of each symmetric matrix (destroys W): out[out_off + b].
 // Replaces approx_eig_qr! + min over real parts (MPMP.jl:1857-1870) by Householder tridiagonalisation
 // + multisection with Sturm counts.
@@ -73,6 +74,8 @@ void col_scale(Ctx& ctx, int nl, const MatBatch& M, int sign, const int* d_scale
 // v[off + i] *= 2^(sign * d_scale[i]); d_dst[d_off[b] + i] = d_src[b*n + i]
 void vec_scale(Ctx& ctx, int nl, mp::Tensor v, int64_t off, int64_t n, int sign, const int* d_scale);
 void scatter_scale(Ctx& ctx, const int* d_src, int batch, int n, const int64_t* d_off, int* d_dst);
+// v[off + i] = -v[off + i] where d_sig[i] != 0 (the Sigma of a signed factorisation applied to a vector)
+void vec_flip(Ctx& ctx, int nl, mp::Tensor v, int64_t off, int64_t n, const int* d_sig);
 // c[i] = a[i] (op) b[i], op in '+','-','*','/','s' (sqrt of a): the scalar arithmetic of mpf.cuh on the device
 void ew_binary(Ctx& ctx, int nl, int op, mp::Tensor c, mp::Tensor a, mp::Tensor b, int64_t n);
 
@@ -123,6 +126,8 @@ struct SmallGemmArgs {
   const int64_t* offC = nullptr;
   int64_t a0 = 0, abs_ = 0, ars = 0, aks = 1, b0 = 0, bbs = 0, brs = 0, bks = 1, c0 = 0, cbs = 0, crs = 0, ccs = 1;
   int batch = 1, M = 0, N = 0, K = 0, epi = 0;
+  const int* ksign = nullptr;  // optional [batch][ksign_ld]: term k of item b is subtracted where ksign != 0
+  int ksign_ld = 0;
 };
 void small_gemm(Ctx& ctx, int nl, const SmallGemmArgs& a);
 // C(b,i,j) = A(b,i,j): strided rectangular copy (A element (b,i,j) at offA(b) + i*ars + j*aks)
@@ -182,6 +187,8 @@ enum ScalarSlots : int {
 };
 enum ScalarProgram : int { SP_MU = 0, SP_BETA, SP_ALPHA, SP_OBJECTIVES, SP_ERRORS, SP_OBJECTIVES_INIT };
 // flags[0] = pd_feas (in/out), flags[1] = terminate reason, flags[2..3] = need_primal/need_dual
-void scalar_program(Ctx& ctx, int nl, int prog, mp::Tensor scal, int* d_flags, double* d_out);
+// SP_ALPHA with d_status: the step lengths are set to zero when any of the n_status factorisation flags is raised
+void scalar_program(Ctx& ctx, int nl, int prog, mp::Tensor scal, int* d_flags, double* d_out,
+                    const int* d_status = nullptr, int n_status = 0);
 
 }  // namespace clr

@@ -4,6 +4,7 @@
 // of the log row.
 #include "solver.cuh"
 
+#include <cmath>
 #include <cstdlib>
 
 #include <algorithm>
@@ -371,6 +372,8 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
   for (MpBuf* t : {&x, &dx, &d, &c, &rhs, &tvec, &tmpx, &trx, &dx_pred}) t->alloc(sumS, nl);
   for (MpBuf* t : {&y, &dy, &p, &b, &tmpy, &zvec, &dyr, &dy_pred}) t->alloc(n_y, nl);
   xscale.ensure(sizeof(int) * (size_t)std::max(sumS, 1));
+  xsign.ensure(sizeof(int) * (size_t)std::max(sumS, 1));
+  qsign.ensure(sizeof(int) * (size_t)std::max(n_y, 1));
   int64_t maxrd = n_y;
   for (auto& g : bgroups_) maxrd = std::max<int64_t>(maxrd, (int64_t)g.blocks.size() * g.nb);
   for (auto& g : cgroups_) maxrd = std::max<int64_t>(maxrd, (int64_t)g.clusters.size() * g.dimS);
@@ -662,8 +665,10 @@ static constexpr int64_t SMALL_GEMM_PMAC = 1500000;
 void Solver::product(GemmEngine* ge, Slice& sa, Slice& sb, const OperandDesc& a, const OperandDesc& b, int M, int N,
                      const OutDesc& c, int epi, const mp::Tensor* extra) {
   const int64_t pmac = (int64_t)a.batch * M * N * a.K;
+  if (a.d_ksign || a.d_kshift || b.d_kshift) throw SolverError(-1, "product: scaled / signed operands go on the B side");
   if (pmac <= SMALL_GEMM_PMAC) {
     SmallGemmArgs g;
+    g.ksign = b.d_ksign, g.ksign_ld = b.ksign_ld;
     g.A = a.src, g.B = b.src, g.C = c.dst;
     if (extra) g.E = *extra;
     g.offA = a.d_off, g.offB = b.d_off, g.offC = c.d_off;
@@ -680,7 +685,7 @@ void Solver::product(GemmEngine* ge, Slice& sa, Slice& sb, const OperandDesc& a,
 }
 
 void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv,
-                          int* d_stat, bool want_u, bool side, bool relaxed, int* d_keep_scale) {
+                          int* d_stat, bool want_u, bool side, int* d_sig, int* d_keep_scale) {
   const int n = A.n, batch = A.batch;
   GemmEngine* gemm_loc = side ? this->gemm_side_.get() : this->gemm_.get();
   Slice& fs1_ = side ? this->fs1s_ : this->fs1_;
@@ -699,8 +704,13 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
   int* d_scale = d_keep_scale ? d_keep_scale : scb.as<int>();
   equil_exponents(ctx, nl, A, d_scale);
   mat_copy_scaled(ctx, nl, Uw, A, true, d_scale);  // work on the upper triangle of the equilibrated matrix
+  // Signed mode (d_sig: [batch][n] flags, see panel_factor): A' = U^T Sigma U. With Y = Sigma U (what the row products
+  // G11 * A12 below deliver, stored in the off-diagonal part of Uw) the trailing update is A22 -= Y12^T Sigma1 Y12 and
+  // L[p, 0:k0] = (Sigma Y)[0:k0, p]^T in the inverse panels: Sigma only ever sits on a contraction index, where the
+  // slicer (OperandDesc::d_ksign) or the CUDA-core product applies it exactly. Linv = L^-1 with L = U^T, unsigned.
+  if (d_sig && want_u) throw SolverError(-1, "chol_inverse: the signed factorisation does not deliver U");
   if (n <= PANEL) {
-    panel_factor(ctx, nl, Uw, Linv, want_u, d_stat, relaxed);
+    panel_factor(ctx, nl, Uw, Linv, want_u, d_stat, d_sig, n);
     if (!d_keep_scale) col_scale(ctx, nl, Linv, -1, d_scale);
     if (want_u) col_scale(ctx, nl, Uw, +1, d_scale);
     return;
@@ -719,7 +729,9 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
     // T[i][c] = sum_r U[r][k0+i] * Linv[r][c], stored transposed: Tt[c][i]
     OutDesc ot;
     ot.dst = scr.t(), ot.bstride = (int64_t)PANEL * n, ot.rs = 1, ot.cs = wk;
-    product(ge2, s1, s2, op_cols(Uw, 0, k0, wk, k0), op_cols(Linv, 0, 0, k0, k0), wk, k0, ot, EPI_STORE, nullptr);
+    OperandDesc lin = op_cols(Linv, 0, 0, k0, k0);
+    if (d_sig) lin.d_ksign = d_sig, lin.ksign_ld = n;  // L[k0+i][r] = sigma_r Y[r][k0+i]
+    product(ge2, s1, s2, op_cols(Uw, 0, k0, wk, k0), lin, wk, k0, ot, EPI_STORE, nullptr);
     OperandDesc tb;
     tb.src = scr.t(), tb.batch = batch, tb.bstride = (int64_t)PANEL * n, tb.rs = wk, tb.ks = 1, tb.rows = k0, tb.K = wk;
     product(ge2, s1, s2, op_rows(Linv, k0, k0, wk, wk), tb, wk, k0, out_sub(Linv, k0, 0), EPI_NEG, nullptr);
@@ -727,7 +739,7 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
   bool forked = false;
   for (int k0 = 0; k0 < n; k0 += PANEL) {
     const int wk = std::min(PANEL, n - k0), n2 = n - k0 - wk;
-    panel_factor(ctx, nl, Uw.sub(k0, k0, wk), Linv.sub(k0, k0, wk), want_u, d_stat, relaxed);
+    panel_factor(ctx, nl, Uw.sub(k0, k0, wk), Linv.sub(k0, k0, wk), want_u, d_stat, d_sig ? d_sig + k0 : nullptr, n);
     if (par && k0 >= PANEL) {
       cudaStream_t cur = ctx.stream;
       CLR_CUDA(cudaEventRecord(H.ev_go, cur));
@@ -755,10 +767,16 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
         product(gemm_loc, fs1_, fs2_, op_rows(Linv, k0, k0, wk, wk), op_cols(Uw, k0, k0 + wk, n2, wk), wk, n2,
                 out_sub(Uw, k0, k0 + wk), EPI_STORE, nullptr);
       }
-      // A22 -= U12^T U12
+      // A22 -= U12^T U12   (signed: Y12^T Sigma1 Y12)
       mp::Tensor ut = Uw.t;
       OperandDesc u12 = op_cols(Uw, k0, k0 + wk, n2, wk);
-      product(gemm_loc, fs2_, fs2_, u12, u12, n2, n2, out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
+      if (d_sig) {
+        OperandDesc u12s = u12;
+        u12s.d_ksign = d_sig + k0, u12s.ksign_ld = n;
+        product(gemm_loc, fs2_, fs1_, u12, u12s, n2, n2, out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
+      } else {
+        product(gemm_loc, fs2_, fs2_, u12, u12, n2, n2, out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
+      }
     }
   }
   if (forked) {
@@ -913,9 +931,13 @@ void Solver::decomposition() {
     // Linvs holds L'^-1 of the equilibrated S' = D^-1 S D^-1; D (exponents in g.equil, and in xscale indexed like x)
     // goes onto the other operand wherever the constraint index is contracted: L^-1 B = L'^-1 (D^-1 B) below,
     // L^-1 rhs = L'^-1 (D^-1 rhs) and L^-T u = D^-1 (L'^-T u) in search_direction().
+    // The factorisation is signed, S'_j = U^T Sigma_j U (see panel_factor): Sigma_j (flags in g.sig, and in xsign indexed
+    // like x) enters as S_j^-1 = D^-1 L'^-T Sigma L'^-1 D^-1, i.e. Q = W^T Sigma W and Sigma on t_j, W_j dy below.
     g.equil.ensure(sizeof(int) * g.clusters.size() * (size_t)g.dimS);
-    chol_inverse(A, U, V, Li, d_status.as<int>() + sbase, false, false, true, g.equil.as<int>());
+    g.sig.ensure(sizeof(int) * g.clusters.size() * (size_t)g.dimS);
+    chol_inverse(A, U, V, Li, d_status.as<int>() + sbase, false, false, g.sig.as<int>(), g.equil.as<int>());
     scatter_scale(ctx, g.equil.as<int>(), (int)g.clusters.size(), g.dimS, g.offW.as<int64_t>(), xscale.as<int>());
+    scatter_scale(ctx, g.sig.as<int>(), (int)g.clusters.size(), g.dimS, g.offW.as<int64_t>(), xsign.as<int>());
     sbase += (int)g.clusters.size();
   }
   mark(-1 - CLRSDP_T_CHOL_S);
@@ -943,16 +965,18 @@ void Solver::decomposition() {
   }
   mark(-1 - CLRSDP_T_CINVB);
   mark(CLRSDP_T_Q);
-  {  // Q = sum_j W_j^T W_j = Wt Wt^T  (the reference forms B^T U^-1 * L^-1 B, :1467-1495)
+  {  // Q = sum_j W_j^T Sigma_j W_j = Wt Sigma Wt^T  (the reference forms B^T U^-1 * L^-1 B, :1467-1495)
     Slice& sW = sW_;
     OperandDesc a;
     a.src = Wt.t();
     a.batch = 1, a.rows = n_y, a.K = sumS, a.rs = sumS, a.ks = 1;
     ge()->slice(a, sW);
+    a.d_ksign = xsign.as<int>(), a.ksign_ld = sumS;
+    ge()->slice(a, sWs_);
     OutDesc o;
     o.dst = Q.t();
     o.rs = n_y, o.cs = 1;
-    ge()->multiply(sW, sW, plan_of(1, n_y, n_y), o, EPI_STORE, nullptr, true);  // symmetric: upper tiles only
+    ge()->multiply(sW, sWs_, plan_of(1, n_y, n_y), o, EPI_STORE, nullptr, true);  // symmetric: upper tiles only
     allreduce(Q, 0, (int64_t)n_y * n_y, COMB_SUM);  // the cross-cluster reduction (sum(Q), :1494)
   }
   mark(-1 - CLRSDP_T_Q);
@@ -964,7 +988,7 @@ void Solver::decomposition() {
   {
     MatBatch A{Q.t(), d_qoff.as<int64_t>(), 1, n_y}, U{Uq.t(), d_qoff.as<int64_t>(), 1, n_y};
     MatBatch V{Vq.t(), d_qoff.as<int64_t>(), 1, n_y}, Li{Linvq.t(), d_qoff.as<int64_t>(), 1, n_y};
-    chol_inverse(A, U, V, Li, d_status.as<int>() + 2 * (int)blocks_.size() + J, false, true, true);
+    chol_inverse(A, U, V, Li, d_status.as<int>() + 2 * (int)blocks_.size() + J, false, true, qsign.as<int>());
   }
   mark(-1 - CLRSDP_T_CHOL_Q);
   end_side();
@@ -990,7 +1014,7 @@ void Solver::search_direction() {
   mark(-1 - CLRSDP_T_RHS_X);
   mark(CLRSDP_T_SYS);
   {
-    // t_j = L_j^-1 rhs_j = L'_j^-1 (D_j^-1 rhs_j)
+    // S_j^-1 = D^-1 L'^-T Sigma L'^-1 D^-1:  t_j = Sigma L'_j^-1 (D_j^-1 rhs_j)
     vec_scale(ctx, nl, rhs.t(), 0, sumS, -1, xscale.as<int>());
     GemvArgs a;
     a.A = Linvs.t(), a.x = rhs.t(), a.out = tvec.t();
@@ -999,7 +1023,8 @@ void Solver::search_direction() {
     a.d_row0 = d_row0.as<int>(), a.d_K = d_itemK.as<int>();
     a.item_trans = 0;  // A_item[r][k], leading dimension = K_item
     gemv(ctx, nl, a, work.t());
-    // tmpy = sum_j W_j^T t_j = Wt t
+    vec_flip(ctx, nl, tvec.t(), 0, sumS, xsign.as<int>());  // t <- Sigma t
+    // tmpy = sum_j W_j^T Sigma_j t_j = Wt t
     GemvArgs w;
     w.A = Wt.t(), w.x = tvec.t(), w.out = tmpy.t();
     w.rs = sumS, w.ks = 1, w.rows = n_y, w.K = sumS;
@@ -1012,15 +1037,17 @@ void Solver::search_direction() {
     q1.A = Linvq.t(), q1.x = dyr.t(), q1.out = zvec.t();
     q1.rs = n_y, q1.ks = 1, q1.rows = n_y, q1.K = n_y;
     gemv(ctx, nl, q1, work.t());
+    vec_flip(ctx, nl, zvec.t(), 0, n_y, qsign.as<int>());  // Q^-1 = Lq^-T Sigma_q Lq^-1
     GemvArgs q2 = q1;
     q2.x = zvec.t(), q2.out = dy.t();
     q2.rs = 1, q2.ks = n_y;
     gemv(ctx, nl, q2, work.t());
-    // u = t + W dy ; dx_j = L_j^-T u_j
+    // u = t + Sigma W dy ; dx_j = D^-1 L'_j^-T u_j
     GemvArgs wd;
     wd.A = Wt.t(), wd.x = dy.t(), wd.out = tmpx.t();
     wd.rs = 1, wd.ks = sumS, wd.rows = sumS, wd.K = n_y;
     gemv(ctx, nl, wd, work.t());
+    vec_flip(ctx, nl, tmpx.t(), 0, sumS, xsign.as<int>());  // u = Sigma (t + W dy)
     ew_lincomb(ctx, nl, tmpx.t(), 0, tvec.t(), 0, 1, tmpx.t(), 0, 1, sumS);
     GemvArgs bt = a;
     bt.x = tmpx.t(), bt.out = dx.t();
@@ -1251,7 +1278,7 @@ void Solver::iteration_body() {
   // step 7
   mark(CLRSDP_T_ALPHA);
   step_lengths();
-  scalar_program(ctx, nl, SP_ALPHA, scal.t(), d_flags.as<int>(), nullptr);
+  scalar_program(ctx, nl, SP_ALPHA, scal.t(), d_flags.as<int>(), nullptr, d_status.as<int>(), n_status);
   mark(-1 - CLRSDP_T_ALPHA);
   // step 8
   ew_axpy(ctx, nl, x.t(), 0, dx.t(), 0, scal.t(), SL_ALPHA_P, sumS);
@@ -1372,6 +1399,15 @@ int Solver::iterate(clrsdp_iter_info* info) {
     row.seconds = total;  // device time of the iteration (CUDA events on the launching stream)
   }
   (void)t0;
+  // A lost iterate must be loud: once mu or a step length is zero, negative or not finite the run cannot recover (the
+  // reference would walk on to maxiterations with garbage); report it instead of a row that looks like progress.
+  if (st == 0 && !(std::isfinite(row.mu) && row.mu > 0 && std::isfinite(row.alpha_p) && row.alpha_p > 0 &&
+                   std::isfinite(row.alpha_d) && row.alpha_d > 0 && std::isfinite(row.beta_c) &&
+                   std::isfinite(row.p_obj_new) && std::isfinite(row.d_obj_new))) {
+    st = CLRSDP_ERR_DIVERGED;
+    row.status = st;
+    err = "the iterate was lost (mu, a step length or an objective is zero, negative or not finite): the working precision is too low for this instance — try again with higher precision";
+  }
   if (st) prepared = false;
   if (info) *info = row;
   return st;
@@ -1520,6 +1556,31 @@ int Solver::op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, 
   }
   if (Linv) to_host(li, 0, tot, Linv, 0);
   return 0;
+}
+// the factorisation of S_j and Q as a stand-alone op: equilibrated A' = D^-1 A D^-1 = U^T Sigma U (signed, panel_factor);
+// delivers M = L^-1 D^-1 (L = U^T) and the signs, so that A^-1 = M^T Sigma M
+void Solver::op_signed_factor(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* Minv, int32_t* signs) {
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  int64_t tot = (int64_t)batch * n * n;
+  if (A->n != tot || Minv->n < tot) throw SolverError(CLRSDP_ERR_BAD_ARG, "op_signed_factor: sizes");
+  MpBuf a, u, li;
+  a.alloc(tot, nl), u.alloc(tot, nl), li.alloc(tot, nl);
+  to_device(A, 0, tot, a, 0);
+  std::vector<int64_t> off(batch);
+  for (int i = 0; i < batch; i++) off[i] = (int64_t)i * n * n;
+  DevBuf doff, dst, dsig;
+  upload(doff, off, ctx.stream);
+  dst.ensure(sizeof(int) * batch);
+  dsig.ensure(sizeof(int) * (size_t)batch * n);
+  MatBatch Ab{a.t(), doff.as<int64_t>(), batch, n}, Ub{u.t(), doff.as<int64_t>(), batch, n};
+  MatBatch Lb{li.t(), doff.as<int64_t>(), batch, n};
+  CLR_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(int) * batch, ctx.stream));
+  chol_inverse(Ab, Ub, Ub, Lb, dst.as<int>(), false, false, dsig.as<int>());
+  std::vector<int> hs((size_t)batch * n);
+  CLR_CUDA(cudaMemcpyAsync(hs.data(), dsig.p, sizeof(int) * hs.size(), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  for (size_t i = 0; i < hs.size(); i++) signs[i] = hs[i] ? -1 : 1;
+  to_host(li, 0, tot, Minv, 0);
 }
 void Solver::op_elementwise(int op, const clrsdp_mp* a, const clrsdp_mp* b2, clrsdp_mp_out* cc) {
   CLR_CUDA(cudaSetDevice(ctx.device));

@@ -42,6 +42,7 @@ struct ClusterGroup {
   Slice sBt;    // per iteration: rows a (n_y) of (D_j^-1 B_j)^T, K = dimS
   Slice sLinv;  // per iteration: rows of L'_j^-1
   DevBuf equil; // per iteration: [clusters][dimS] equilibration exponents of S_j (D_j = diag 2^s)
+  DevBuf sig;   // per iteration: [clusters][dimS] signs of the pivots of S'_j = U^T Sigma U (1 = negative)
 };
 
 class Solver {
@@ -71,6 +72,7 @@ class Solver {
   void op_gemm_planes(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, int32_t* planes,
                       int* n_planes, int32_t* row_exp, int32_t* col_exp);
   int op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, clrsdp_mp_out* Linv);
+  void op_signed_factor(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* Minv, int32_t* signs);
   void op_lambda_min(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lam);
   void op_elementwise(int op, const clrsdp_mp* a, const clrsdp_mp* b, clrsdp_mp_out* c);
 
@@ -106,7 +108,7 @@ class Solver {
   // Linv = (chol A)^-1 for a batch of SPD matrices: blocked right-looking Cholesky, panels on the CUDA cores,
   // trailing updates and the off-diagonal inverse panels through the sliced tensor-core GEMM
   void chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv, int* d_status,
-                    bool want_u = false, bool side = false, bool relaxed = false, int* d_keep_scale = nullptr);
+                    bool want_u = false, bool side = false, int* d_sig = nullptr, int* d_keep_scale = nullptr);
   void product(GemmEngine* ge, Slice& sa, Slice& sb, const OperandDesc& a, const OperandDesc& b, int M, int N,
                const OutDesc& c, int epi, const mp::Tensor* extra);
   // a second stream for work that is off the critical path (see decomposition())
@@ -125,6 +127,8 @@ class Solver {
   std::vector<std::pair<const char*, size_t>> pinned_;  // host ranges registered through pin_host
   DevBuf equil_, equil_side_;                          // equilibration exponents of chol_inverse
   DevBuf xscale;                                       // [sumS] the exponents of the S_j, indexed like x
+  DevBuf xsign, qsign;                                 // pivot signs of the S_j (indexed like x) and of Q ([n_y])
+  Slice sWs_;                                          // Sigma W: the rows of Wt sliced with the signs on the contraction index
   DevBuf wire_se_;                                     // sign / exponent scratch of the pinned transfer path
   std::unique_ptr<GemmEngine> gemm_, gemm_side_;
   cudaStream_t side_stream_ = nullptr, main_stream_ = nullptr;

@@ -63,7 +63,10 @@ enum {
   CLRSDP_ERR_SINGULAR_S= -12, /* factorisation of S_j failed    (MPMP.jl:1438-1440)                     */
   CLRSDP_ERR_SINGULAR_Q= -13, /* factorisation of Q failed      (MPMP.jl:1502-1504)                     */
   CLRSDP_ERR_EIG       = -14, /* step-length eigen solve failed (MPMP.jl:1861-1862,1881-1884)           */
-  CLRSDP_ERR_STATE     = -15  /* call order violated (e.g. iterate before a point exists)               */
+  CLRSDP_ERR_STATE     = -15, /* call order violated (e.g. iterate before a point exists)               */
+  CLRSDP_ERR_DIVERGED  = -16  /* the iterate was lost: mu, a step length or an objective came out zero, negative or
+                                 not finite. No reference counterpart (the reference walks on to maxiterations);
+                                 the shim maps it to the same "higher precision" error as NOT_PD_X/Y. */
 };
 
 /* termination reasons reported in clrsdp_iter_info.terminate (MPMP.jl:1147-1173) */
@@ -187,6 +190,12 @@ int clrsdp_op_gemm_planes(clrsdp_handle h, int batch, int M, int N, int K, const
 /* lower Cholesky factor / inverse factor of a batch of SPD n x n matrices (cho!, spd_inv!) */
 int clrsdp_op_cholesky(clrsdp_handle h, int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L,
                        clrsdp_mp_out* Linv);
+/* The factorisation that stands in for the reference's pivoted LU of S_j and Q (approx_lu!, MPMP.jl:1436,1501): for
+ * each symmetric (not necessarily definite) n x n matrix A of the batch, the signed factorisation of the equilibrated
+ * matrix, A = D U^T Sigma U D with Sigma = diag(+-1) and D a diagonal of powers of two. Delivers M = U^-T D^-1
+ * (n x n, lower triangular, row-major) and signs[b*n + k] = Sigma_kk in {-1,+1}, so that A^-1 = M^T Sigma M. */
+int clrsdp_op_signed_factor(clrsdp_handle h, int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* Minv,
+                            int32_t* signs);
 /* smallest eigenvalue of each symmetric n x n matrix of a batch (approx_eig_qr! + min, :1857-1870) */
 int clrsdp_op_lambda_min(clrsdp_handle h, int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lam);
 /* elementwise c = a (op) b, op in {'+','-','*','/'} and c = sqrt(a) with op 's' (scalar kernels' arithmetic) */

@@ -110,6 +110,14 @@ double now_s() {
 //    multiply-accumulates (mpn_mul_n / mpn_add_n, positive and negative terms apart) and each entry is rounded once.
 //    It is the faster CPU product; bench.py times the CPU baseline with it and reports the fma-loop time beside it.
 static int g_gemm_fixed = 0;
+// ALGORITHM SWITCH (the default, "lu", is the reference's algorithm and what "the oracle" means everywhere):
+// CLRSDP_REF_FACTOR (read per handle at create) replaces the reference's pivoted LU of S_j and Q (MPMP.jl:1436,:1501) by
+// the factorisation of the GPU path so that its numerical behaviour can be studied on the CPU beside the LU, in MPFR
+// arithmetic: "ldl" = equilibrated signed Cholesky S' = U^T Sigma U (pivots keep their sign), explicit inverse factors,
+// W = L^-1 B, Q = W^T Sigma W (what csrc/ does since round 2); "chol" = the round-1 algorithm (pivots below
+// 2^-(p-CLRSDP_REF_CLAMP) raised to that floor), kept because it reproduces round 1's loss of the iterate on sphere packing
+// d = 8 at 256 bits. CLRSDP_REF_REFINE=<n> adds n steps of iterative refinement of the Schur solve (measured: no help).
+static int g_clamp_bits = 16, g_refine = 0;
 
 struct FixedRows {  // rows[r][k]: Lw limbs, sign, and the row exponent: value = +-limbs * 2^(E - 64 Lw)
   int Lw = 0, K = 0;
@@ -352,6 +360,56 @@ bool spd_inverse(Mat& Inv, const Mat& A) {
   Inv = std::move(out);
   return true;
 }
+// EXPERIMENT (CLRSDP_REF_FACTOR=chol): what the GPU path's chol_inverse computes. A' = D^-1 A D^-1 with
+// D = diag(2^ceil(e_ii/2)); Cholesky of A' with pivots below 2^-(p-clamp) raised to that floor; Linv = L'^-1.
+static int chol_inverse_equil(Mat& Linv, std::vector<long>& sc, std::vector<int>& sg, const Mat& A, long prec, int mode) {
+  const int n = A.r;
+  sc.assign(n, 0);
+  for (int i = 0; i < n; i++)
+    if (!mpfr_zero_p(&A(i, i).v)) {
+      long e = (long)A(i, i).v._mpfr_exp;
+      sc[i] = (e >= 0) ? (e + 1) / 2 : -((-e) / 2);
+    }
+  Mat Ap(n, n), L(n, n);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) mpfr_mul_2si(&Ap(i, j).v, &A(i, j).v, -(sc[i] + sc[j]), MPFR_RNDN);
+  Real thr, s, t;
+  mpfr_set_ui_2exp(&thr.v, 1, -(prec - g_clamp_bits), MPFR_RNDN);
+  int clamped = 0;
+  sg.assign(n, 1);
+  for (int j = 0; j < n; j++) {
+    s = Ap(j, j);
+    for (int k = 0; k < j; k++) {
+      r_mul(t, L(j, k), L(j, k));
+      if (sg[k] > 0) r_sub(s, s, t); else r_add(s, s, t);
+    }
+    if (mode == 2) {  // signed (LDL^T-like): keep the sign of the pivot, floor its magnitude
+      if (mpfr_sgn(&s.v) < 0) {
+        sg[j] = -1;
+        r_neg(s, s);
+        clamped++;
+      }
+      if (r_cmp(s, thr) < 0) s = thr;
+    } else if (r_cmp(s, thr) < 0) {
+      s = thr;
+      clamped++;
+    }
+    mpfr_sqrt(&L(j, j).v, &s.v, MPFR_RNDN);
+    for (int i = j + 1; i < n; i++) {
+      s = Ap(i, j);
+      for (int k = 0; k < j; k++) {
+        r_mul(t, L(i, k), L(j, k));
+        if (sg[k] > 0) r_sub(s, s, t); else r_add(s, s, t);
+      }
+      r_div(L(i, j), s, L(j, j));
+      if (sg[j] < 0) r_neg(L(i, j), L(i, j));
+    }
+  }
+  Mat I(n, n);
+  for (int i = 0; i < n; i++) r_set_si(I(i, i), 1);
+  solve_tril(Linv, L, I, false);
+  return clamped;
+}
 // Smallest eigenvalue of a symmetric matrix: Householder tridiagonalisation + Sturm bisection.
 // Stands in for approx_eig_qr! + min over real parts (MPMP.jl:1857-1870).
 bool lambda_min_sym(Real& lam, Mat A) {
@@ -493,12 +551,19 @@ struct Decomp {  // (S, perms, LinvB, BTUinv, perm, Q) of MPMP.jl:1507
   std::vector<Mat> LinvB, BTUinv;
   std::vector<int> permQ;
   Mat QLU;
+  // CLRSDP_REF_FACTOR=chol (experiment): L'_j^-1 of the equilibrated S_j, its scaling exponents, W_j = L_j^-1 B_j, Lq^-1
+  std::vector<Mat> Linv, W;
+  std::vector<std::vector<long>> sc;
+  std::vector<std::vector<int>> sg;
+  std::vector<int> sgQ;
+  Mat LinvQ;
 };
 typedef std::vector<std::vector<Mat>> BlockDiag;  // [j][l]
 
 }  // namespace
 
 struct clrsdp_solver {
+  int factor_mode = 0;  // experiment switch CLRSDP_REF_FACTOR, read at create: 0 = lu (the reference), 1 = chol, 2 = ldl
   long prec = 256;
   int nthreads = 1;
   int nlimb = 8;
@@ -872,6 +937,7 @@ struct clrsdp_solver {
     S_keep = S;
     t_schur = now_s() - t0;
     t0 = now_s();
+    if (factor_mode) return T_decomposition_chol();
     dec.LU = std::move(S);
     dec.perms.assign(J, {});
     std::vector<int> ok(J, 1);
@@ -935,6 +1001,111 @@ struct clrsdp_solver {
     return 0;
   }
 
+  // EXPERIMENT (CLRSDP_REF_FACTOR=chol): the GPU path's decomposition, see the switch at the top of the file
+  int n_clamped_S = 0, n_clamped_Q = 0;
+  int T_decomposition_chol() {
+    dec.Linv.assign(J, Mat());
+    dec.W.assign(J, Mat());
+    dec.sc.assign(J, {});
+    dec.sg.assign(J, {});
+    std::vector<int> cl_(J, 0);
+    parallel_for(J, [&](int j) {
+      cl_[j] = chol_inverse_equil(dec.Linv[j], dec.sc[j], dec.sg[j], S_keep[j], prec, factor_mode);
+      Mat DB(cl[j].dimS, n_y);
+      for (int i = 0; i < cl[j].dimS; i++)
+        for (int k = 0; k < n_y; k++) mpfr_mul_2si(&DB(i, k).v, &cl[j].B(i, k).v, -dec.sc[j][i], MPFR_RNDN);
+      gemm(dec.W[j], dec.Linv[j], DB);
+    });
+    n_clamped_S = 0;
+    for (int j = 0; j < J; j++) n_clamped_S += cl_[j];
+    Mat Q(n_y, n_y);
+    for (int j = 0; j < J; j++) {
+      Mat Wt = transpose(dec.W[j]), Qj;
+      for (int i = 0; i < cl[j].dimS; i++)
+        if (dec.sg[j][i] < 0)
+          for (int k = 0; k < n_y; k++) r_neg(Wt(k, i), Wt(k, i));
+      gemm(Qj, Wt, dec.W[j]);
+      for (size_t i = 0; i < Q.a.size(); i++) r_add(Q.a[i], Q.a[i], Qj.a[i]);
+    }
+    Q_keep = Q;
+    std::vector<long> scq;
+    n_clamped_Q = chol_inverse_equil(dec.LinvQ, scq, dec.sgQ, Q, prec, factor_mode);
+    for (int i = 0; i < n_y; i++)
+      for (int k = 0; k < n_y; k++) mpfr_mul_2si(&dec.LinvQ(i, k).v, &dec.LinvQ(i, k).v, -scq[k], MPFR_RNDN);
+    if (getenv("CLRSDP_REF_VERBOSE")) fprintf(stderr, "[chol] iter %d clamped S %d Q %d\n", iter, n_clamped_S, n_clamped_Q);
+    return 0;
+  }
+  // one solve of the Schur system with the factors above: S dx - B dy = rx, B^T dx = ry
+  void schur_solve_chol(std::vector<Real>& sdx, std::vector<Real>& sdy, const std::vector<Real>& rx, const std::vector<Real>& ry) {
+    std::vector<Mat> tv(J);
+    std::vector<Mat> ty(J);
+    parallel_for(J, [&](int j) {
+      int n = cl[j].dimS;
+      Mat rhs(n, 1);
+      for (int i = 0; i < n; i++) mpfr_mul_2si(&rhs(i, 0).v, &rx[x_idx[j] + i].v, -dec.sc[j][i], MPFR_RNDN);
+      gemm(tv[j], dec.Linv[j], rhs);
+      for (int i = 0; i < n; i++)
+        if (dec.sg[j][i] < 0) r_neg(tv[j](i, 0), tv[j](i, 0));  // tv = Sigma L^-1 D^-1 rx
+      Mat Wt = transpose(dec.W[j]);
+      gemm(ty[j], Wt, tv[j]);
+    });
+    Mat dyr(n_y, 1), z, dyv;
+    for (int k = 0; k < n_y; k++) {
+      Real sum;
+      for (int j = 0; j < J; j++) r_add(sum, sum, ty[j](k, 0));
+      r_sub(dyr(k, 0), ry[k], sum);
+    }
+    gemm(z, dec.LinvQ, dyr);
+    for (int k = 0; k < n_y; k++)
+      if (dec.sgQ[k] < 0) r_neg(z(k, 0), z(k, 0));
+    Mat LqT = transpose(dec.LinvQ);
+    gemm(dyv, LqT, z);
+    sdy.assign(n_y, Real());
+    for (int k = 0; k < n_y; k++) sdy[k] = dyv(k, 0);
+    sdx.assign(sumS, Real());
+    parallel_for(J, [&](int j) {
+      Mat u, sol;
+      gemm(u, dec.W[j], dyv);
+      for (int i = 0; i < cl[j].dimS; i++) {
+        if (dec.sg[j][i] < 0) r_neg(u(i, 0), u(i, 0));  // Sigma (W dy) + Sigma t
+        r_add(u(i, 0), u(i, 0), tv[j](i, 0));
+      }
+      Mat LiT = transpose(dec.Linv[j]);
+      gemm(sol, LiT, u);
+      for (int i = 0; i < cl[j].dimS; i++) mpfr_mul_2si(&sdx[x_idx[j] + i].v, &sol(i, 0).v, -dec.sc[j][i], MPFR_RNDN);
+    });
+  }
+  void search_system_chol(const std::vector<Real>& rhs_x) {
+    schur_solve_chol(dx, dy, rhs_x, p);
+    for (int it = 0; it < g_refine; it++) {
+      // r1 = rhs_x - (S dx - B dy), r2 = p - B^T dx
+      std::vector<Real> r1(sumS), r2(n_y), cx, cy;
+      Real t;
+      for (int j = 0; j < J; j++) {
+        int n = cl[j].dimS;
+        for (int i = 0; i < n; i++) {
+          Real acc = rhs_x[x_idx[j] + i];
+          for (int k = 0; k < n; k++) r_fnma(acc, S_keep[j](i, k), dx[x_idx[j] + k], t);
+          for (int k = 0; k < n_y; k++) r_fma(acc, cl[j].B(i, k), dy[k]);
+          r1[x_idx[j] + i] = acc;
+        }
+      }
+      for (int k = 0; k < n_y; k++) {
+        Real acc = p[k];
+        for (int j = 0; j < J; j++)
+          for (int i = 0; i < cl[j].dimS; i++) r_fnma(acc, cl[j].B(i, k), dx[x_idx[j] + i], t);
+        r2[k] = acc;
+      }
+      if (getenv("CLRSDP_REF_VERBOSE")) {
+        Real m1 = max_abs(r1), m2 = max_abs(r2), mx = max_abs(dx), my = max_abs(dy);
+        fprintf(stderr, "[chol] iter %d refine %d: |r1| %.2e |r2| %.2e |dx| %.2e |dy| %.2e\n", iter, it, m1.d(), m2.d(), mx.d(), my.d());
+      }
+      schur_solve_chol(cx, cy, r1, r2);
+      for (int i = 0; i < sumS; i++) r_add(dx[i], dx[i], cx[i]);
+      for (int k = 0; k < n_y; k++) r_add(dy[k], dy[k], cy[k]);
+    }
+  }
+
   // compute_search_direction (MPMP.jl:1682-1824)
   void search_direction() {
     double t0 = now_s();
@@ -960,6 +1131,11 @@ struct clrsdp_solver {
     }
     t_dir[1] += now_s() - t0;
     t0 = now_s();
+    if (factor_mode) {
+      search_system_chol(rhs_x);
+      goto system_done;
+    }
+    {
     std::vector<Mat> temp_x(J), temp_y(J);
     parallel_for(J, [&](int j) {  // (:1751-1759)
       int n = cl[j].dimS;
@@ -991,6 +1167,8 @@ struct clrsdp_solver {
       solve_triu(sol, dec.LU[j], t2, false);
       for (int i = 0; i < cl[j].dimS; i++) dx[x_idx[j] + i] = sol(i, 0);
     });
+    }
+  system_done:
     t_dir[2] += now_s() - t0;
     t0 = now_s();
     weighted_A(dX, dx);  // dX = sum dx_i A_i + P (:1780-1786)
@@ -1313,10 +1491,16 @@ REF_API int clrsdp_ref_create(clrsdp_handle* h, int prec_bits, int nthreads) {
   {
     const char* gm = getenv("CLRSDP_REF_GEMM");
     g_gemm_fixed = (gm && std::string(gm) == "fixed") ? 1 : 0;
+    if (const char* cb = getenv("CLRSDP_REF_CLAMP")) g_clamp_bits = atoi(cb);
+    if (const char* rf = getenv("CLRSDP_REF_REFINE")) g_refine = atoi(rf);
   }
   if (!h || prec_bits < 64 || prec_bits % 32) return CLRSDP_ERR_BAD_ARG;
   g_prec = prec_bits;
   clrsdp_solver* s = new clrsdp_solver();
+  {
+    const char* fm = getenv("CLRSDP_REF_FACTOR");
+    s->factor_mode = (fm && std::string(fm) == "chol") ? 1 : ((fm && std::string(fm) == "ldl") ? 2 : 0);
+  }
   s->prec = prec_bits;
   s->nlimb = prec_bits / 32;
   s->nthreads = nthreads > 0 ? nthreads : (int)std::max(1u, std::thread::hardware_concurrency());

@@ -159,3 +159,41 @@ def test_lambda_min_degenerate_spectra(handles):
     assert got[1] == pytest.approx(-2.0, abs=1e-12)
     assert got[2] == pytest.approx(0.5, abs=1e-12)
     assert got[3] == pytest.approx(1e-30, rel=1e-9)
+
+
+@pytest.mark.parametrize("shape", [(2, 7), (2, 33), (1, 70), (1, 130)])
+def test_signed_factor_inverts_indefinite_matrices(handles, shape):
+    """The factorisation of S_j and Q (stand-in for the reference's pivoted LU, MPMP.jl:1436,1501): symmetric INDEFINITE
+    matrices - what a Schur complement that is singular to working precision looks like - are factored as
+    A = D U^T Sigma U D without any pivot being reported or perturbed; M^T Sigma M is the inverse, checked against the
+    identity in exact rational arithmetic relative to cond(A): |M^T Sigma M A - I| <= cond * 2^-(p-16)."""
+    prec, h, _ = handles
+    batch, n = shape
+    rng = np.random.default_rng(n)
+    mats = []
+    for _ in range(batch):
+        Qm, _ = np.linalg.qr(rng.normal(size=(n, n)))
+        ev = rng.uniform(0.5, 2.0, size=n) * np.where(np.arange(n) % 3 == 1, -1.0, 1.0)   # a third of the spectrum is negative
+        mats.append((Qm * ev) @ Qm.T)
+        mats[-1] = (mats[-1] + mats[-1].T) / 2
+    A = MpArray.from_double(np.array(mats).reshape(-1), h.nlimb)
+    M, sg = h.op_signed_factor(batch, n, A)
+    assert set(np.unique(sg)) <= {-1, 1}
+    import mpmath
+    with mpmath.workprec(prec + 64):
+        for b in range(batch):
+            # inertia (Sylvester): the number of negative pivots equals the number of negative eigenvalues
+            assert int((sg[b] < 0).sum()) == int((np.linalg.eigvalsh(mats[b]) < 0).sum())
+            Mm = mpmath.matrix(n, n)
+            vals = M.take(np.arange(b * n * n, (b + 1) * n * n)).to_mpfs()
+            for i in range(n):
+                for j in range(n):
+                    Mm[i, j] = vals[i * n + j]
+                    if j > i:
+                        assert vals[i * n + j] == 0          # lower triangular
+            Am = mpmath.matrix(mats[b].tolist())
+            Sg = mpmath.diag([int(s) for s in sg[b]])
+            R = Mm.T * Sg * Mm * Am - mpmath.eye(n)
+            err = max(abs(R[i, j]) for i in range(n) for j in range(n))
+            # unpivoted LDL^T of an indefinite matrix: element growth enters the bound (measured < 2^30 on these seeds)
+            assert err <= mpmath.mpf(2) ** -(prec - 16 - 40), (b, mpmath.nstr(err, 5))
