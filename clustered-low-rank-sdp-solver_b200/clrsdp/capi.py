@@ -145,6 +145,18 @@ class Handle:
         s = [a.c_struct() for a in (V, H, B, c)]
         self._check(f(self._h, int(j), *[ctypes.byref(x) for x in s]), "upload_cluster")
 
+    def upload_C(self, C: MpArray | None):
+        """Objective matrix C (kwarg of solverank1sdp, MPMP.jl:599): blocks in (j,l) order, each nb x nb row-major,
+        concatenated; None restores C = 0."""
+        f = self._fn("upload_C")
+        mp = ctypes.POINTER(clrsdp_mp)
+        f.argtypes = [ctypes.c_void_p, mp]
+        if C is None:
+            self._check(f(self._h, None), "upload_C")
+        else:
+            sc = C.c_struct()
+            self._check(f(self._h, ctypes.byref(sc)), "upload_C")
+
     def upload_objective(self, b: MpArray, b0: MpArray):
         f = self._fn("upload_objective")
         mp = ctypes.POINTER(clrsdp_mp)

@@ -143,8 +143,16 @@ def real_params(nlimb, **kw) -> MpArray:
     return MpArray.concat([_to_mp_scalar(p[k], nlimb) for k in order])
 
 
-def load_problem(h: capi.Handle, constraints, b: MpArray, blockinfo: BlockInfo, b0=0):
-    """set_structure + upload_cluster for every constraint + upload_objective."""
+def flatten_blocks(M) -> MpArray:
+    """A block-diagonal matrix given as list over j of lists over l of MpArray (nb, nb) -> the flat (j,l)-ordered,
+    row-major layout the C ABI takes for X, Y and C."""
+    if isinstance(M, MpArray):
+        return M
+    return MpArray.concat([blk.reshape(blk.n) for row in M for blk in row])
+
+
+def load_problem(h: capi.Handle, constraints, b: MpArray, blockinfo: BlockInfo, b0=0, C=None):
+    """set_structure + upload_cluster for every constraint + upload_objective (+ upload_C for C != 0)."""
     bi = blockinfo
     delta = [d for j in range(bi.J) for d in bi.delta[j]]
     ranks = [r for j in range(bi.J) for l in range(bi.L[j]) for r in bi.ranks[j][l]]
@@ -154,6 +162,8 @@ def load_problem(h: capi.Handle, constraints, b: MpArray, blockinfo: BlockInfo, 
         H = MpArray.concat(c.H) if len(c.H) > 1 else c.H[0]
         h.upload_cluster(j, V, H, c.B, c.c)
     h.upload_objective(b, _to_mp_scalar(b0, h.nlimb))
+    if C is not None:
+        h.upload_C(flatten_blocks(C))
 
 
 def product_handle(prec=None, device=0) -> capi.Handle:
@@ -185,13 +195,15 @@ def solverank1sdp(constraints, b, blockinfo: BlockInfo, *, C=0, b0=0, maxiterati
     (:1014-1024); X, Y, P are lists over j of lists over l of MpArray (nb, nb); the three scalars are
     mpmath mpf at working precision. `handle` lets tests pass a handle on the CPU oracle.
     """
-    if C != 0:
-        raise NotImplementedError("only C = 0 (the reference's default, MPMP.jl:599,691-695) is supported")
+    if isinstance(C, (int, float)) and C == 0:
+        C = None                                     # the reference's AbsoluteZero (MPMP.jl:691-695)
+    elif isinstance(C, (int, float)):
+        raise ValueError("C must be 0 or a block-diagonal matrix with the structure of X (MPMP.jl:599)")
     own = handle is None
     h = handle or product_handle()
     nl = h.nlimb
     b = b if isinstance(b, MpArray) else MpArray.from_mpf(b, nl)
-    load_problem(h, constraints, b, blockinfo, b0)
+    load_problem(h, constraints, b, blockinfo, b0, C)
     h.set_params(real_params(nl, beta_infeasible=beta_infeasible, beta_feasible=beta_feasible, gamma=gamma,
                              omega_p=omega_p, omega_d=omega_d, duality_gap_threshold=duality_gap_threshold,
                              primal_error_threshold=primal_error_threshold,
@@ -201,8 +213,7 @@ def solverank1sdp(constraints, b, blockinfo: BlockInfo, *, C=0, b0=0, maxiterati
     n_X = int(sum(s * s for s in sizes))
     if len(initial_solutions) == 4:  # warm start (:689)
         x0, X0, y0, Y0 = initial_solutions
-        flat = lambda M: MpArray.concat([blk.reshape(blk.n) for row in M for blk in row])
-        h.upload_point(x0, flat(X0), y0, flat(Y0))
+        h.upload_point(x0, flatten_blocks(X0), y0, flatten_blocks(Y0))
     else:
         h.init_point()
     if verbose:
@@ -238,7 +249,7 @@ def solverank1sdp(constraints, b, blockinfo: BlockInfo, *, C=0, b0=0, maxiterati
             P[j].append(h.fetch("P", j, l).reshape(s, s))
             off += s * s
     p, d = h.fetch("p"), h.fetch("d")
-    # return values (:1021-1023): gap WITHOUT b0 (:1067-1074), objectives with b0
+    # return values (:1021-1023): gap WITHOUT b0 (:1067-1074; <C,Y> is inside dual_obj), objectives with b0
     primal_obj, dual_obj = h.scalar("p_obj"), h.scalar("d_obj")
     import mpmath
     with mpmath.workprec(h.prec):

@@ -80,6 +80,12 @@ CAPI int clrsdp_upload_objective(clrsdp_handle h, const clrsdp_mp* b, const clrs
     return 0;
   });
 }
+CAPI int clrsdp_upload_C(clrsdp_handle h, const clrsdp_mp* C) {
+  return guard(h, [&](clr::Solver& s) {
+    s.upload_C(C);
+    return 0;
+  });
+}
 CAPI int clrsdp_set_params(clrsdp_handle h, const clrsdp_mp* rp, const clrsdp_int_params* ip) {
   return guard(h, [&](clr::Solver& s) {
     s.set_params(rp, ip);

@@ -212,6 +212,40 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
+// TMEM <-> registers for CPS = 4, 8 or 16 consecutive columns of this thread's lane
+template <int CPS>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CPS]);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
+template <int CPS>
+__device__ __forceinline__ void tmem_st_zero(uint32_t taddr);
+template <>
+__device__ __forceinline__ void tmem_st_zero<16>(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st_zero<8>(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st_zero<4>(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%1,%1,%1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+
 // one lane of a converged warp; everything around the elected instruction stays warp-uniform, so descriptors and
 // barrier addresses live in uniform registers (issuing from `if (lane == 0)` makes the compiler wrap every tcgen05/TMA
 // instruction in a lane-serialising R2UR loop, ~250 cycles per MMA)
@@ -241,8 +275,21 @@ struct MmaParams {
   int n_tile_pairs;
   int32_t* blocks;  // [T][nsplit][batch][ceil(N/4)][Mpad][4]: block q, lane group r holds the partial plane q + r
   uint32_t idesc, sbo16, layout_type;
+  uint32_t idesc2;  // instruction descriptor of the N = 2 BN MMA over a pair of adjacent B digit tiles (0 = do not pair)
   int debug;  // CLRSDP_MMA_DEBUG (measuring aid): 1 = skip the block stores, 2 = skip the TMEM loads, 32 = cycle counters
   long long* dbg;
+  // FUSED epilogue (single K-split): the epilogue warps propagate the carries themselves while the planes arrive (least
+  // significant first) and finish the numbers (normalise, round, epilogue operation, store): no int32 planes in HBM, no
+  // carry launch. `blocks` then holds the raw two's-complement words [NW][batch][ceil(N/4)][Mpad][4] of every lane group.
+  const int32_t* expA;  // per row of A / B (global row index)
+  const int32_t* expB;
+  uint32_t* cw;         // destination tensor (planar mp) and the extra operand of the epilogue operation
+  size_t cn;
+  const uint32_t* ew;
+  size_t en;
+  const int64_t* c_off;
+  int64_t c_off0, c_bstride, c_rs, c_cs;
+  int epi;
 };
 
 constexpr int EPI_SETS = 4;       // epilogue warp sets: block q is drained by set q % EPI_SETS
@@ -313,7 +360,34 @@ __device__ __forceinline__ void mma_issue(const MmaParams& p, uint64_t* bars, ui
           const uint64_t adesc0 = make_smem_desc(sa, p.sbo16, p.layout_type);
           const uint64_t bdesc0 = make_smem_desc(sa + a_bytes, p.sbo16, p.layout_type);
           const bool full = na == DG / STACK && nb == DG && cmax >= QSPAN && !need_wait;
-          if (full) {  // interior stage (the common case): no predicates
+          if (full && p.idesc2) {
+            // interior stage, B digits taken in PAIRS along N: the tiles of digits jb and jb + 1 are adjacent in shared
+            // memory (one TMA box, digit-major) and their blocks c, c + 1 adjacent in TMEM, so one MMA of N = 2 BN does
+            // both. An SS-mode kind::i8 MMA reads 128 x 32 bytes of A and N x 32 bytes of B from shared memory at 128 B/clk:
+            // at N = 64 that is 48 cycles for 32 cycles of arithmetic, at N = 128 the two are balanced (64 / 64). Only
+            // the pair that would straddle the end of the accumulator ring (slot 7 | slot 0) is issued as two halves.
+            if (elect_one()) {
+#pragma unroll
+              for (int ia = 0; ia < DG / STACK; ia++) {
+#pragma unroll
+                for (int jb = 0; jb < DG; jb += 2) {
+                  const int s0 = (sb + ia * STACK + jb) & (ACC_SLOTS - 1);
+                  const uint32_t d_tmem = tmem_base + (uint32_t)(s0 * p.BN);
+                  const uint64_t ad = adesc0 + (uint64_t)(ia * a_step), bd = bdesc0 + (uint64_t)(jb * b_step);
+                  if (s0 != ACC_SLOTS - 1) {
+                    umma_i8(d_tmem, ad, bd, p.idesc2, 1u);
+                    if (two_k) umma_i8(d_tmem, ad + 2, bd + 2, p.idesc2, 1u);
+                  } else {
+                    umma_i8(d_tmem, ad, bd, p.idesc, 1u);
+                    if (two_k) umma_i8(d_tmem, ad + 2, bd + 2, p.idesc, 1u);
+                    umma_i8(tmem_base, ad, bd + b_step, p.idesc, 1u);
+                    if (two_k) umma_i8(tmem_base, ad + 2, bd + b_step + 2, p.idesc, 1u);
+                  }
+                }
+              }
+              umma_commit(smem_u32(&bars[8 + stage]));
+            }
+          } else if (full) {  // interior stage (the common case): no predicates
             if (elect_one()) {
 #pragma unroll
               for (int ia = 0; ia < DG / STACK; ia++) {
@@ -395,6 +469,210 @@ __device__ __forceinline__ void mma_issue(const MmaParams& p, uint64_t* bars, ui
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Epilogue of one warp: columns [eset*CPS, (eset+1)*CPS) of the tile, TMEM lanes [32*q4, 32*q4 + 32), all blocks.
+//
+// !FUSED: the int32 blocks go to HBM as they are (chunk-major [N/4][Mpad][4]); carry_kernel finishes them (K-splits,
+//         symmetric products, the exact-plane test entry).
+// FUSED:  per entry a running 64-bit carry and the 32-bit word under construction stay in registers: plane t (byte
+//         position T-1-t from the least significant end) contributes byte (carry + v) & 0xFF, carry <- (carry + v) >> 8.
+//         A word is final as soon as its four bytes are (carries only travel upwards) and is streamed to the raw-word
+//         buffer (L2-resident: 4*NW bytes per entry and lane group instead of 4*T). After the last plane the carry is
+//         spelled out into the words above (sign extension). Then the same threads finish the tile: sum of the lane groups
+//         of an entry (M-stacking: group r holds the planes of digit a + r, processed one byte position later), two's
+//         complement sign, normalisation, rounding to p bits, exponent, epilogue operation, store - what carry_kernel does,
+//         without the round trip of the planes through HBM and without the extra launch.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NL, int CPS, bool FUSED>
+__device__ __forceinline__ void epilogue_warp(const MmaParams& p, uint64_t* bars, uint32_t tmem_base, int q4, int eset, int lane,
+                                              int mt, int nt, int item, int split) {
+  constexpr int TT = 4 * NL + GUARD_DIGITS;     // digit planes of this precision (= p.T)
+  constexpr int NW = (TT + 3) / 4 + 2;          // words of the raw two's-complement result
+  const int T = p.T, stack = p.stack;
+  const int qspan = (DG - stack) + (DG - 1);
+  const int Dmax = (T - 1) / DG;
+  const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+  {  // hand every accumulator to the issuers zeroed: each warp clears its own columns of all slots
+    for (int sl = 0; sl < ACC_SLOTS; sl++) tmem_st_zero<CPS>(tmem_base + lane_addr + (uint32_t)(sl * p.BN + eset * CPS));
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bars[32]));
+  }
+  const int lrow = q4 * 32 + lane;
+  const int mip = 128 / stack;
+  const int grp = lrow / mip;           // lane group: plane q + grp
+  const bool row_ok = (stack == 1) ? (mt * 128 + lrow < p.M) : ((lrow - grp * mip) < p.M);
+  const int row = mt * 128 + lrow;
+  const int n4 = (p.N + 3) >> 2;
+  const int chunk0 = (nt * p.BN + eset * CPS) >> 2;   // first 4-column chunk of this thread
+  // acc[c] = carry + sum of the planes of the word under construction, plane at byte k weighted 2^(8k): one IMAD.WIDE per
+  // plane and entry (|v| < 2^31, so |acc| < 2^56); when the word's four bytes are in, its low half is final
+  int64_t acc[CPS];
+#pragma unroll
+  for (int c = 0; c < CPS; c++) acc[c] = 0;
+  // raw words of (word w, this item): int4 index ((w * batch + item) * n4 + chunk) * Mpad + row
+  int4* const wbase = reinterpret_cast<int4*>(p.blocks) + (size_t)item * n4 * p.Mpad + row;
+  const size_t wstride = (size_t)p.batch * n4 * p.Mpad;
+  auto flush = [&](int w) {
+    if (row_ok && !(p.debug & 1)) {
+#pragma unroll
+      for (int i = 0; i < CPS / 4; i++)
+        if (chunk0 + i < n4)
+          wbase[(size_t)w * wstride + (size_t)(chunk0 + i) * p.Mpad] =
+              make_int4((int)(uint32_t)acc[4 * i], (int)(uint32_t)acc[4 * i + 1], (int)(uint32_t)acc[4 * i + 2], (int)(uint32_t)acc[4 * i + 3]);
+    }
+#pragma unroll
+    for (int c = 0; c < CPS; c++) acc[c] >>= 32;  // arithmetic: the carry into the next word
+  };
+  long long dbg_wait = 0;
+  const long long dbg_t0 = p.dbg ? clock64() : 0;
+  for (int D = Dmax; D >= 0; D--) {
+    const int q_hi = min(T - 1, DG * D + qspan);
+    const int q_lo = (D == 0) ? 0 : DG * D + qspan - (DG - 1);
+    for (int q = q_hi; q >= q_lo; q--) {
+      const int slot = q & (ACC_SLOTS - 1);
+      const uint32_t u = (uint32_t)(T - 1 - q) >> 3;
+      const long long cw0 = p.dbg ? clock64() : 0;
+      mbar_wait(smem_u32(&bars[16 + slot]), u & 1u);
+      if (p.dbg) dbg_wait += clock64() - cw0;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(slot * p.BN + eset * CPS);
+      uint32_t v[CPS];
+      if (!(p.debug & 2)) {
+        tmem_ld<CPS>(taddr, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int c = 0; c < CPS; c++) v[c] = 0;
+      }
+      // the accumulator slot goes back as soon as it has been read and cleared
+      tmem_st_zero<CPS>(taddr);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[24 + slot]));
+      if (!FUSED) {
+        // chunk-major block layout [N/4][Mpad][4]: the 32 rows of a warp are 512 contiguous bytes per 4-column chunk
+        if (row_ok && (q + grp < T) && !(p.debug & 1)) {
+          int4* out = reinterpret_cast<int4*>(p.blocks) + (((size_t)q * p.nsplit + split) * p.batch + item) * (size_t)n4 * p.Mpad + row;
+#pragma unroll
+          for (int i = 0; i < CPS / 4; i++)
+            if (chunk0 + i < n4)
+              out[(size_t)(chunk0 + i) * p.Mpad] = make_int4((int)v[4 * i], (int)v[4 * i + 1], (int)v[4 * i + 2], (int)v[4 * i + 3]);
+        }
+      } else {
+        const int t = q + grp;  // the plane these rows of block q belong to
+        if (t < T) {
+          const int pos = T - 1 - t;
+          const int32_t weight = 1 << (8 * (pos & 3));
+#pragma unroll
+          for (int c = 0; c < CPS; c++)  // one IMAD.WIDE each (nvcc turns the C++ product into a six-instruction 64-bit shift-add)
+            asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"((int32_t)v[c]), "r"(weight));
+          if ((pos & 3) == 3) flush(pos >> 2);
+        }
+      }
+    }
+  }
+  if (p.dbg && blockIdx.x == 0 && eset == 0 && q4 == 0 && lane == 0) {
+    p.dbg[8] = clock64() - dbg_t0;  // epilogue: all blocks drained
+    p.dbg[9] = dbg_wait;            // of which waiting for complete blocks
+  }
+  if (!FUSED) return;
+  // the remaining carry (signed) is spelled out in the words above the last plane (sign extension up to word NW - 1)
+  // (the next byte position of this lane group is T - grp: the words below (T - grp) >> 2 are complete and flushed)
+  for (int w = (T - grp) >> 2; w < NW; w++) flush(w);
+  // every lane group's words of this tile are in memory: epilogue warps only (named barrier 1)
+  asm volatile("bar.sync 1, %0;" ::"r"(32 * 4 * EPI_SETS) : "memory");
+  if (p.debug & 1) return;
+  // Finish: a warp takes 4 x 8 patches of the tile (its reads of the raw words are runs of 4 rows x 16 bytes in the
+  // chunk-major layout, its result stores 4 runs of 8 consecutive entries per limb plane), one entry per lane.
+  const int ewarp = 4 * eset + q4;                       // 0 .. 15
+  const int rows_tile = (stack == 1) ? 128 : mip;        // output rows of this tile
+  const int npc = p.BN >> 3, npatch = (rows_tile >> 2) * npc;
+  const int gitem = p.item0 + item;
+  const int rowA0 = (p.rowA ? p.rowA[gitem] : gitem * p.M), rowB0 = (p.rowB ? p.rowB[gitem] : gitem * p.N);
+  const int64_t cbase = p.c_off0 + (p.c_off ? p.c_off[gitem] : (int64_t)gitem * p.c_bstride);
+  const uint32_t* const raw = reinterpret_cast<const uint32_t*>(p.blocks) + (size_t)item * n4 * p.Mpad * 4;
+  const size_t wstride4 = wstride * 4;
+  // The raw words of the NEXT patch are requested before the current one is normalised and stored (two L2 round trips
+  // in flight per thread: with 16 warps per SM the finish is bound by that latency, not by the arithmetic).
+  auto entry_of = [&](int pt, int& il, int& i, int& j) {
+    il = 4 * (pt / npc) + (lane >> 3);  // row inside the tile
+    i = mt * 128 + il;
+    j = nt * p.BN + 8 * (pt % npc) + (lane & 7);
+    return pt < npatch && i < p.M && j < p.N;
+  };
+  auto request = [&](int pt, uint32_t (&R0)[NW], uint32_t (&R1)[NW]) {
+    int il, i, j;
+    if (!entry_of(pt, il, i, j)) return;
+    const uint32_t* e0 = raw + ((size_t)(j >> 2) * p.Mpad + (mt * 128 + il)) * 4 + (j & 3);
+#pragma unroll
+    for (int w = 0; w < NW; w++) R0[w] = __ldcg(e0 + (size_t)w * wstride4);
+    if (stack > 1) {
+#pragma unroll
+      for (int w = 0; w < NW; w++) R1[w] = __ldcg(e0 + (size_t)w * wstride4 + (size_t)mip * 4);
+    }
+  };
+  uint32_t N0[NW], N1[NW];
+  request(ewarp, N0, N1);
+  for (int pt = ewarp; pt < npatch; pt += 4 * EPI_SETS) {
+    int il, i, j;
+    const bool live = entry_of(pt, il, i, j);
+    uint32_t W[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) W[w] = N0[w];
+    if (live && stack > 1) {  // lane groups are numbers on the same scale: multiword sum mod 2^(32 NW)
+      mp::add_n<NW>(W, N1);
+      const uint32_t* e0 = raw + ((size_t)(j >> 2) * p.Mpad + (mt * 128 + il)) * 4 + (j & 3);
+      for (int r = 2; r < stack; r++) {
+        uint32_t V[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) V[w] = __ldcg(e0 + (size_t)w * wstride4 + (size_t)r * mip * 4);
+        mp::add_n<NW>(W, V);
+      }
+    }
+    request(pt + 4 * EPI_SETS, N0, N1);
+    if (!live) continue;
+    const bool negf = (W[NW - 1] >> 31) != 0;
+    if (negf) {
+      uint32_t cc = 1;
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        const uint64_t sm = (uint64_t)(~W[w]) + cc;
+        W[w] = (uint32_t)sm;
+        cc = (uint32_t)(sm >> 32);
+      }
+    }
+    const int32_t ea = p.expA[rowA0 + i], eb = p.expB[rowB0 + j];
+    mp::Num<NL> r;
+    const int shn = mp::normalize_n<NW>(W);
+    if (shn < 0 || ea == mp::EXP_ZERO || eb == mp::EXP_ZERO) {
+      r = mp::zero<NL>();
+    } else {
+      uint32_t X[NL + 1];
+#pragma unroll
+      for (int w = 0; w <= NL; w++) X[w] = W[NW - NL - 1 + w];
+      // value = N_int * 2^(ea + eb - 4 - 8T), N_int = (W / 2^(32 NW)) * 2^(32 NW - sh)
+      mp::round_guard<NL>(r, X, 32 * NW - shn + ea + eb - 4 - 8 * T, negf ? 1u : 0u);
+    }
+    const int64_t at = cbase + (int64_t)i * p.c_rs + (int64_t)j * p.c_cs;
+    if (p.epi == EPI_NEG) {
+      r = mp::neg(r);
+    } else if (p.epi != EPI_STORE) {
+      mp::Num<NL> e = mp::load<NL>(p.ew, p.en, (size_t)at);
+      if (p.epi == EPI_SUB_FROM)
+        r = mp::sub(e, r);
+      else if (p.epi == EPI_MINUS_SUB)
+        r = mp::sub(r, e);
+      else
+        r = mp::add(r, e);
+    }
+    mp::store<NL>(p.cw, p.cn, (size_t)at, r);
+  }
+  if (p.dbg && blockIdx.x == 0 && eset == 0 && q4 == 0 && lane == 0) p.dbg[10] = clock64() - dbg_t0;  // epilogue incl. finish
+}
+
 // One CTA = one 128 x BN output tile of one batch item (x one K-split) and ALL its digit planes.
 //
 // The digit pairs (a, b), a + b < T, are visited in DG x DG squares: a pipeline stage holds the tiles of DG digits of A
@@ -408,6 +686,7 @@ __device__ __forceinline__ void mma_issue(const MmaParams& p, uint64_t* bars, ui
 // Items with at most 64 (32) rows stack 2 (4) consecutive digits of A along the 128 rows of the MMA: rows
 // [r*128/stack, (r+1)*128/stack) of block q then hold the contribution of digit a + r, i.e. of plane q + r, and the
 // carry kernel adds the `stack` lane groups. This keeps all 128 rows of the tensor core busy on the 64 x 64 blocks.
+template <int NL, bool FUSED>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, MmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -459,7 +738,7 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < ACC_SLOTS; s++) {
       mbar_init(smem_u32(&bars[16 + s]), NISSUE);
-      mbar_init(smem_u32(&bars[24 + s]), 4);
+      mbar_init(smem_u32(&bars[24 + s]), 4 * EPI_SETS);
     }
     mbar_init(smem_u32(&bars[32]), 4 * EPI_SETS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -510,69 +789,17 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     else
       mma_issue<4>(p, bars, smem, stage_bytes, a_tile, b_tile, a_bytes, tmem_base, kblocks, warp - 1);
   } else {
-    // ------------------------------ epilogue: TMEM -> registers -> HBM blocks --------------------
-    // EPI_SETS sets of four warps (one warp per TMEM lane quarter) drain the blocks round-robin, so several drains
-    // (barrier wake-up, TMEM load, stores) are in flight;
-    // all TMEM loads of a block are issued before the single wait.
+    // ------------------------------ epilogue: TMEM -> registers -> HBM --------------------------------
+    // Four warp sets (one warp per TMEM lane quarter in each); set e owns the columns [e*BN/4, (e+1)*BN/4) of EVERY block,
+    // so a thread sees all planes of its entries in the order they complete (least significant first).
     const int q4 = warp & 3;                      // TMEM lane quarter this warp may access
-    const int eset = (warp - FIRST_EPI) >> 2;     // handles the blocks with q % EPI_SETS == eset
-    {  // hand every accumulator to the issuers zeroed: set e clears the slots e, e + EPI_SETS, ...
-      for (int sl = eset; sl < ACC_SLOTS; sl += EPI_SETS)
-        for (int c0 = 0; c0 < p.BN; c0 += 16) tmem_st16_zero(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sl * p.BN + c0));
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars[32]));
-    }
-    const int lrow = q4 * 32 + lane;
-    const int mip = 128 / stack;
-    const int grp = lrow / mip;           // lane group: plane q + grp
-    const bool row_ok = (stack == 1) ? (mt * 128 + lrow < p.M) : ((lrow - grp * mip) < p.M);
-    const int row = mt * 128 + lrow;
-    for (int D = Dmax; D >= 0; D--) {
-      const int q_hi = min(T - 1, DG * D + qspan);
-      const int q_lo = (D == 0) ? 0 : DG * D + qspan - (DG - 1);
-      for (int q = q_hi; q >= q_lo; q--) {
-        if ((q % EPI_SETS) != eset) continue;
-        const int slot = q & (ACC_SLOTS - 1);
-        const uint32_t u = (uint32_t)(T - 1 - q) >> 3;
-        mbar_wait(smem_u32(&bars[16 + slot]), u & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // chunk-major block layout [N/4][Mpad][4]: the 32 rows of a warp are 512 contiguous bytes per 4-column chunk
-        const int n4 = (p.N + 3) >> 2;
-        int4* out = reinterpret_cast<int4*>(p.blocks) + (((size_t)q * p.nsplit + split) * p.batch + item) * (size_t)n4 * p.Mpad + row;
-        const bool live = row_ok && (q + grp < T) && !(p.debug & 1);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(slot * p.BN);
-        uint32_t v[4][16];
-        if (!(p.debug & 2)) {
-#pragma unroll
-          for (int cc = 0; cc < 4; cc++)
-            if (cc * 16 < p.BN) tmem_ld16(taddr + cc * 16, v[cc]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
-        // the accumulator slot goes back as soon as it has been read and cleared
-#pragma unroll
-        for (int cc = 0; cc < 4; cc++)
-          if (cc * 16 < p.BN) tmem_st16_zero(taddr + cc * 16);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars[24 + slot]));
-        if (live) {
-#pragma unroll
-          for (int cc = 0; cc < 4; cc++) {
-            if (cc * 16 < p.BN) {
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                const int chunk = ((nt * p.BN + cc * 16) >> 2) + i;
-                if (chunk < n4)
-                  out[(size_t)chunk * p.Mpad] = make_int4((int)v[cc][4 * i], (int)v[cc][4 * i + 1], (int)v[cc][4 * i + 2], (int)v[cc][4 * i + 3]);
-              }
-            }
-          }
-        }
-      }
-    }
+    const int eset = (warp - FIRST_EPI) >> 2;     // column group
+    if (p.BN == 64)
+      epilogue_warp<NL, 16, FUSED>(p, bars, tmem_base, q4, eset, lane, mt, nt, item, split);
+    else if (p.BN == 32)
+      epilogue_warp<NL, 8, FUSED>(p, bars, tmem_base, q4, eset, lane, mt, nt, item, split);
+    else
+      epilogue_warp<NL, 4, FUSED>(p, bars, tmem_base, q4, eset, lane, mt, nt, item, split);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -755,8 +982,20 @@ static CUtensorMap make_map(const Slice& s, int box_rows, int BK, int box_digits
   return tm;
 }
 
+typedef void (*MmaKernel)(const CUtensorMap, const CUtensorMap, MmaParams);
+static MmaKernel mma_kernel_of(int nl, bool fused) {
+  switch (nl) {
+    case 4: return fused ? mma_planes_kernel<4, true> : mma_planes_kernel<4, false>;
+    case 8: return fused ? mma_planes_kernel<8, true> : mma_planes_kernel<8, false>;
+    case 12: return fused ? mma_planes_kernel<12, true> : mma_planes_kernel<12, false>;
+    case 16: return fused ? mma_planes_kernel<16, true> : mma_planes_kernel<16, false>;
+    default: throw SolverError(-1, "unsupported precision");
+  }
+}
 GemmEngine::GemmEngine(Ctx& c, int nl) : ctx_(c), nl_(nl), S_(num_digits(nl)) {
-  CLR_CUDA(cudaFuncSetAttribute(mma_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  for (int f = 0; f < 2; f++)
+    CLR_CUDA(cudaFuncSetAttribute(mma_kernel_of(nl, f != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (const char* e = getenv("CLRSDP_FUSED_CARRY")) fused_ok_ = atoi(e) != 0;
 }
 
 template <int NL>
@@ -818,9 +1057,17 @@ static int bn_for(const GemmPlan& plan, int sm_count, bool symmetric) {
 }
 
 void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, int item0, int nitems, int nsplit,
-                         int Kc, bool symmetric) {
+                         int Kc, bool symmetric, const FusedOut* fo) {
   MmaParams p;
   memset(&p, 0, sizeof(p));
+  if (fo) {
+    if (nsplit != 1 || symmetric) throw SolverError(-1, "fused epilogue: single K-split, all tiles");
+    p.expA = A.exps.as<int32_t>(), p.expB = B.exps.as<int32_t>();
+    p.cw = fo->C.dst.w, p.cn = fo->C.dst.n;
+    p.ew = fo->extra ? fo->extra->w : fo->C.dst.w, p.en = fo->extra ? fo->extra->n : fo->C.dst.n;
+    p.c_off = fo->C.d_off, p.c_off0 = fo->C.off0, p.c_bstride = fo->C.bstride, p.c_rs = fo->C.rs, p.c_cs = fo->C.cs;
+    p.epi = fo->epi;
+  }
   p.T = S_;
   p.M = plan.M;
   p.N = plan.N;
@@ -846,6 +1093,11 @@ void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, i
   // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 (2) at [4,6), a/b format INT8 (1) at
   // [7,10)/[10,13), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
   p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  {
+    static int pair = -1;
+    if (pair < 0) pair = getenv("CLRSDP_PAIR_N") ? atoi(getenv("CLRSDP_PAIR_N")) : 0;  // (off until measured on the GPU)
+    p.idesc2 = pair ? ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) : 0u;
+  }
   p.sbo16 = (8u * p.BK) >> 4;
   p.layout_type = p.BK == 128 ? 2u : (p.BK == 64 ? 4u : 6u);
   size_t a_bytes = (size_t)128 * p.BK * (DG / p.stack), b_bytes = (size_t)p.BN * p.BK * DG;
@@ -876,19 +1128,22 @@ void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, i
   // algorithmic MACs: M*N*K * s(s+1)/2 with s = p/8, no guard digits, no tile padding
   double s_alg = 4.0 * nl_;
   double alg = (double)nitems * (symmetric ? 0.5 * plan.M * (plan.M + 1.0) : (double)plan.M * plan.N) * (double)A.K * (s_alg * (s_alg + 1) / 2.0);
-  std::string nm = "mma_planes_M" + std::to_string(plan.M) + "_N" + std::to_string(plan.N) + "_K" + std::to_string(A.K) + "_b" + std::to_string(nitems);
+  std::string nm = std::string(fo ? "mma_planes_fused_M" : "mma_planes_M") + std::to_string(plan.M) + "_N" + std::to_string(plan.N) + "_K" + std::to_string(A.K) + "_b" + std::to_string(nitems);
   int tk = ctx_.begin(nm.c_str(), alg);
   static long long* d_dbg = nullptr;
   if (p.debug & 32) {
-    if (!d_dbg) CLR_CUDA(cudaMalloc(&d_dbg, 64));
+    if (!d_dbg) CLR_CUDA(cudaMalloc(&d_dbg, 128));
+    CLR_CUDA(cudaMemsetAsync(d_dbg, 0, 128, ctx_.stream));
     p.dbg = d_dbg;
   }
-  mma_planes_kernel<<<(unsigned)grid, MMA_THREADS, smem, ctx_.stream>>>(tmA, tmB, p);
+  mma_kernel_of(nl_, fo != nullptr)<<<(unsigned)grid, MMA_THREADS, smem, ctx_.stream>>>(tmA, tmB, p);
   ctx_.end(tk);
   if (p.debug & 32) {
-    long long h[8];
+    long long h[16];
     CLR_CUDA(cudaStreamSynchronize(ctx_.stream));
-    CLR_CUDA(cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost));
+    CLR_CUDA(cudaMemcpy(h, d_dbg, 128, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[mma dbg] epilogue warp 0 of CTA 0: %lld cycles to drain all blocks (%lld waiting for complete blocks), %lld incl. the finish\n",
+            h[8], h[9], h[10]);
     fprintf(stderr, "[mma dbg] %s grid=%lld stages=%d stack=%d BN=%d BK=%d: issuer cycles %lld, waiting for TMA %lld, for accumulator slots %lld; CTA0 life %lld ns, last CTA starts %+lld ns after CTA0 and lives %lld ns\n", nm.c_str(),
             (long long)grid, p.stages, p.stack, p.BN, p.BK, h[0], h[1], h[6], h[3] - h[2], h[4] - h[2], h[5] - h[4]);
   }
@@ -956,8 +1211,15 @@ void GemmEngine::multiply(const Slice& A, const Slice& B, const GemmPlan& plan, 
   size_t cap = (size_t)1536 << 20;
   int chunk = (int)std::max<size_t>(1, std::min<size_t>(plan.batch, cap / std::max<size_t>(per_item, 1)));
   planes_.ensure(per_item * chunk);
+  // one K-split and no mirrored tiles: the epilogue of the tensor-core kernel finishes the numbers itself
+  const bool fused = fused_ok_ && nsplit == 1 && !symmetric;
   for (int item0 = 0; item0 < plan.batch; item0 += chunk) {
     int n = std::min(chunk, plan.batch - item0);
+    if (fused) {
+      FusedOut fo{C, epi, extra};
+      run_mma(A, B, plan, item0, n, nsplit, Kc, symmetric, &fo);
+      continue;
+    }
     run_mma(A, B, plan, item0, n, nsplit, Kc, symmetric);
     CarryArgs c;
     memset(&c, 0, sizeof(c));

@@ -78,7 +78,14 @@ class GemmEngine {
   double last_int8_macs = 0;  // executed digit-product MACs of the last multiply (incl. guard digits)
 
  private:
-  void run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, int item0, int nitems, int nsplit, int Kc, bool symmetric);
+  struct FusedOut {  // destination + epilogue operation when the tensor-core kernel finishes the numbers itself
+    OutDesc C;
+    int epi;
+    const mp::Tensor* extra;
+  };
+  void run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, int item0, int nitems, int nsplit, int Kc, bool symmetric,
+               const FusedOut* fo = nullptr);
+  bool fused_ok_ = true;  // CLRSDP_FUSED_CARRY=0 keeps the separate carry launch for every product
   Ctx& ctx_;
   int nl_, S_;
   DevBuf planes_, sym_map_;

@@ -2014,10 +2014,11 @@ __global__ void scalar_kernel(int prog, mp::Tensor sc, int* flags, double* dout,
     Pp(SL_ALPHA_P, ap);
     Pp(SL_ALPHA_D, ad);
   } else if (prog == SP_OBJECTIVES || prog == SP_OBJECTIVES_INIT) {  // objectives and gap (:1027-1034, :1067-1078)
-    Num<NL> po = nadd(G(SL_CX), G(SL_B0)), dobj = nadd(G(SL_BY), G(SL_B0));
+    const Num<NL> by = nadd(G(SL_CY), G(SL_BY));  // <C,Y> + <b,y> (:1033); SL_CY stays 0 while C = 0
+    Num<NL> po = nadd(G(SL_CX), G(SL_B0)), dobj = nadd(by, G(SL_B0));
     Pp(SL_P_OBJ, po);
     Pp(SL_D_OBJ, dobj);
-    if (prog == SP_OBJECTIVES_INIT) po = G(SL_CX), dobj = G(SL_BY);  // gap of the initial point: no b0 (:1067-1074)
+    if (prog == SP_OBJECTIVES_INIT) po = G(SL_CX), dobj = by;  // gap of the initial point: no b0 (:1067-1074)
     Num<NL> num = mp::fabs(nsub(po, dobj)), den = mp::fabs(nadd(po, dobj));
     if (ncmp(one, den) > 0) den = one;
     Pp(SL_GAP, ndiv(num, den));

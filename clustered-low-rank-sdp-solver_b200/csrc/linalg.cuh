@@ -183,7 +183,7 @@ enum ScalarSlots : int {
   // parameters
   SL_BETA_INF, SL_BETA_FEAS, SL_GAMMA, SL_OMEGA_P, SL_OMEGA_D, SL_GAP_THR, SL_PERR_THR, SL_DERR_THR, SL_B0,
   // temporaries
-  SL_DOT_XY, SL_DOT_SUM, SL_CX, SL_BY, SL_PERR_P, SL_PERR_p, SL_DERR, SL_NTOT, SL_COUNT
+  SL_DOT_XY, SL_DOT_SUM, SL_CX, SL_BY, SL_PERR_P, SL_PERR_p, SL_DERR, SL_NTOT, SL_CY, SL_COUNT
 };
 enum ScalarProgram : int { SP_MU = 0, SP_BETA, SP_ALPHA, SP_OBJECTIVES, SP_ERRORS, SP_OBJECTIVES_INIT };
 // flags[0] = pd_feas (in/out), flags[1] = terminate reason, flags[2..3] = need_primal/need_dual

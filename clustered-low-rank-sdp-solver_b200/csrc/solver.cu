@@ -358,6 +358,7 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
   Ux.alias(U2, 0, blkN), Vx.alias(U2, blkN, blkN);
   T1.alias(T1d, 0, blkN), T2.alias(T2d, 0, blkN);
   for (MpBuf* t : {&Xinv, &R, &P, &Z, &XY, &dX_pred, &dY_pred}) t->alloc(blkN, nl);
+  have_C = false;  // C = 0 until upload_C (the reference's AbsoluteZero, MPMP.jl:691-695)
   Vt.alloc(vtN, nl);
   H.alloc(hN, nl);
   Px.alloc(pN, nl);
@@ -557,6 +558,24 @@ void Solver::upload_objective(const clrsdp_mp* bb, const clrsdp_mp* b0) {
     to_device(b0, 0, 1, scal, SL_B0);
   else
     ew_zero(ctx, nl, scal.t(), SL_B0, 1);
+}
+
+// objective matrix C (MPMP.jl:599): P = sum x_i A_i - X - C (:1116-1118), dual objective <C,Y> + <b,y> + b0 (:1032-1034)
+void Solver::upload_C(const clrsdp_mp* Cw) {
+  if (!structure_set) throw SolverError(CLRSDP_ERR_STATE, "upload_C before set_structure");
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  drop_graph();
+  direct_iters_ = 0;
+  prepared = false;
+  if (!Cw || Cw->n == 0) {
+    have_C = false;
+    ew_zero(ctx, nl, scal.t(), SL_CY, 1);
+    return;
+  }
+  if (Cw->n != blkN) throw SolverError(CLRSDP_ERR_BAD_ARG, "upload_C: C must have the block structure of X");
+  Cmat.alloc(blkN, nl);
+  to_device(Cw, 0, blkN, Cmat, 0);
+  have_C = true;
 }
 
 void Solver::set_params(const clrsdp_mp* rp, const clrsdp_int_params* ipp) {
@@ -887,6 +906,7 @@ void Solver::weighted_A(MpBuf& a, MpBuf& out, MpBuf& E, int sign) {
 // compute_residuals (MPMP.jl:1107-1144)
 void Solver::compute_residuals(bool from_pairings) {
   weighted_A(x, P, X, -1);  // P = sum x_i A_i - X
+  if (have_C) ew_lincomb(ctx, nl, P.t(), 0, P.t(), 0, 1, Cmat.t(), 0, -1, blkN);  // - C (:1116-1118)
   // d = c - B y - Tr(A_* Y)
   GemvArgs g1;
   g1.A = Bmat.t(), g1.x = y.t(), g1.out = tmpx.t();
@@ -1173,6 +1193,13 @@ int Solver::check_status() {
   return -code;
 }
 
+// <C,Y> over all blocks (dot(C, Y), MPMP.jl:1033); stays zero while C = 0
+void Solver::dot_CY() {
+  if (!have_C) return;
+  reduce_dot(ctx, nl, Cmat.t(), 0, Y.t(), 0, blkN, scal.t(), SL_CY, work.t());
+  allreduce(scal, SL_CY, 1, COMB_SUM);
+}
+
 // loop initialisation (MPMP.jl:716-736)
 int Solver::prepare(clrsdp_iter_info* info) {
   if (!have_point) return CLRSDP_ERR_STATE;
@@ -1193,6 +1220,7 @@ int Solver::prepare(clrsdp_iter_info* info) {
   reduce_dot(ctx, nl, c.t(), 0, x.t(), 0, sumS, scal.t(), SL_CX, work.t());
   allreduce(scal, SL_CX, 1, COMB_SUM);
   reduce_dot(ctx, nl, b.t(), 0, y.t(), 0, n_y, scal.t(), SL_BY, work.t());
+  dot_CY();
   compute_residuals(false);
   // the initial duality gap is computed WITHOUT b0 (MPMP.jl:725 -> :1067-1074)
   scalar_program(ctx, nl, SP_OBJECTIVES_INIT, scal.t(), d_flags.as<int>(), nullptr);
@@ -1289,6 +1317,7 @@ void Solver::iteration_body() {
   reduce_dot(ctx, nl, c.t(), 0, x.t(), 0, sumS, scal.t(), SL_CX, work.t());
   allreduce(scal, SL_CX, 1, COMB_SUM);
   reduce_dot(ctx, nl, b.t(), 0, y.t(), 0, n_y, scal.t(), SL_BY, work.t());
+  dot_CY();
   scalar_program(ctx, nl, SP_OBJECTIVES, scal.t(), d_flags.as<int>(), nullptr);
   scalar_program(ctx, nl, SP_ERRORS, scal.t(), d_flags.as<int>(), d_scal_out.as<double>());
 }

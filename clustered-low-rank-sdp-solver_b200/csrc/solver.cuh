@@ -52,6 +52,7 @@ class Solver {
   void set_structure(int J, int n_y, const int* m, const int* L, const int* K, const int* delta, const int* ranks);
   void upload_cluster(int j, const clrsdp_mp* V, const clrsdp_mp* H, const clrsdp_mp* B, const clrsdp_mp* c);
   void upload_objective(const clrsdp_mp* b, const clrsdp_mp* b0);
+  void upload_C(const clrsdp_mp* C);
   void set_params(const clrsdp_mp* rp, const clrsdp_int_params* ip);
   void init_point();
   void upload_point(const clrsdp_mp* x, const clrsdp_mp* X, const clrsdp_mp* y, const clrsdp_mp* Y);
@@ -118,6 +119,7 @@ class Solver {
   int check_status();
   int check_status_local();
   void upload_ntot();
+  void dot_CY();
   // all-reduce of t[off, off+n) over the ranks (no-op on one rank)
   void allreduce(MpBuf& t, int64_t off, int64_t n, int op);
   void mark(int bucket_begin);
@@ -169,6 +171,8 @@ class Solver {
   MpBuf Vt, H, Px, Py, Tt, VD, QP, S, Us, Vs, Linvs, Bmat, Wt, Q, Uq, Vq, Linvq;
   MpBuf x, dx, d, c, rhs, tvec, tmpx, trx, y, dy, p, b, tmpy, zvec, dyr;
   MpBuf dX_pred, dY_pred, dx_pred, dy_pred;
+  MpBuf Cmat;  // objective matrix C (block structure of X), only allocated by upload_C
+  bool have_C = false;
   MpBuf scal, rdiag, lam, work, tscr;
   Slice fs1_, fs2_, sW_;
   // CUDA-graph replay of the iteration body (one launch instead of ~1000)

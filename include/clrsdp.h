@@ -147,8 +147,13 @@ int clrsdp_set_structure(clrsdp_handle h, int J, int n_y, const int* m, const in
  *  B: dim_S[j] x n_y row-major;  c: dim_S[j]. */
 int clrsdp_upload_cluster(clrsdp_handle h, int j, const clrsdp_mp* V, const clrsdp_mp* H,
                           const clrsdp_mp* B, const clrsdp_mp* c);
-/* b: [n_y] objective vector, b0: 1 number (MPMP.jl:597,600). C = 0 only (the default, :599,:691-695). */
+/* b: [n_y] objective vector, b0: 1 number (MPMP.jl:597,600). */
 int clrsdp_upload_objective(clrsdp_handle h, const clrsdp_mp* b, const clrsdp_mp* b0);
+/* The kwarg C (MPMP.jl:599): objective matrix with the block structure of X - blocks in (j,l) order, each nb x nb
+ * row-major, concatenated. It enters the residual P = sum_i x_i A_i - X - C (:1108-1118) and the dual objective
+ * <C,Y> + <b,y> + b0 (:1031-1034, :1067-1070). Without this call, or with C == NULL / C->n == 0, C = 0 (the default,
+ * the reference's AbsoluteZero :589-592, :691-695). With sharded clusters every rank passes the blocks of ITS clusters. */
+int clrsdp_upload_C(clrsdp_handle h, const clrsdp_mp* C);
 int clrsdp_set_params(clrsdp_handle h, const clrsdp_mp* real_params, const clrsdp_int_params* ip);
 
 /* ---- iterate (MPMP.jl:659-695 / :689) ------------------------------------------------------ */

@@ -583,6 +583,8 @@ struct clrsdp_solver {
   bool have_point = false, prepared = false;
   std::vector<Real> x, y;
   BlockDiag X, Y, R, Xinv, P, Z, dX, dY, XYsave;
+  BlockDiag C;  // objective matrix (MPMP.jl:599); have_C = false is the reference's AbsoluteZero (:691-695)
+  bool have_C = false;
   std::vector<Real> p, d, dx, dy;
   // intermediates kept for parity fetches
   std::vector<Mat> S_keep;
@@ -650,8 +652,17 @@ struct clrsdp_solver {
     r_add(r, r, b0);
     return r;
   }
-  Real dual_objective() {
+  Real dot_CY() {  // dot(C, Y) (block_diag_dot, MPMP.jl:205-220); AbsoluteZero -> 0 (:590)
     Real r;
+    if (!have_C) return r;
+    for (size_t q = 0; q < jl.size(); q++) {
+      int j = jl[q].first, l = jl[q].second;
+      for (size_t i = 0; i < Y[j][l].a.size(); i++) r_fma(r, C[j][l].a[i], Y[j][l].a[i]);
+    }
+    return r;
+  }
+  Real dual_objective() {  // <C,Y> + <b,y> + b0 (:1032-1034)
+    Real r = dot_CY();
     for (int i = 0; i < n_y; i++) r_fma(r, b[i], y[i]);
     r_add(r, r, b0);
     return r;
@@ -670,7 +681,7 @@ struct clrsdp_solver {
   }
   // compute_duality_gap(constraints,x,y,Y,C,b) (MPMP.jl:1067-1074): objectives WITHOUT b0
   Real duality_gap_point() {
-    Real po = dot_c(x), dobj;
+    Real po = dot_c(x), dobj = dot_CY();
     for (int i = 0; i < n_y; i++) r_fma(dobj, b[i], y[i]);
     return duality_gap(po, dobj);
   }
@@ -788,6 +799,8 @@ struct clrsdp_solver {
     parallel_for((int)jl.size(), [&](int q) {
       int j = jl[q].first, l = jl[q].second;
       for (size_t i = 0; i < P[j][l].a.size(); i++) r_sub(P[j][l].a[i], P[j][l].a[i], X[j][l].a[i]);
+      if (have_C)  // P -= C (:1116-1118)
+        for (size_t i = 0; i < P[j][l].a.size(); i++) r_sub(P[j][l].a[i], P[j][l].a[i], C[j][l].a[i]);
     });
     // d = c - B y - Tr(A_* Y)
     d.assign(sumS, Real());
@@ -1603,6 +1616,28 @@ REF_API int clrsdp_ref_upload_objective(clrsdp_handle h, const clrsdp_mp* b, con
     from_wire(h->b0, b0, 0, h->nlimb);
   else
     r_zero(h->b0);
+  return 0;
+}
+
+// C: blocks in (j,l) order, each nb x nb row-major, concatenated (like X); NULL or n == 0 restores C = 0
+REF_API int clrsdp_ref_upload_C(clrsdp_handle h, const clrsdp_mp* Cw) {
+  if (!h) return CLRSDP_ERR_BAD_ARG;
+  g_prec = h->prec;
+  if (!Cw || Cw->n == 0) {
+    h->have_C = false;
+    return 0;
+  }
+  int64_t tot = 0;
+  for (auto& c : h->cl)
+    for (auto& bk : c.blk) tot += (int64_t)bk.nb * bk.nb;
+  if (Cw->n != tot) return CLRSDP_ERR_BAD_ARG;
+  h->C = h->like_blocks();
+  int64_t off = 0;
+  for (size_t j = 0; j < h->cl.size(); j++)
+    for (size_t l = 0; l < h->cl[j].blk.size(); l++)
+      for (auto& e : h->C[j][l].a) from_wire(e, Cw, off++, h->nlimb);
+  h->have_C = true;
+  h->prepared = false;
   return 0;
 }
 

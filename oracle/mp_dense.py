@@ -15,7 +15,7 @@ def _mp(a, i, ctx):
 
 
 class DenseSDP:
-    def __init__(self, constraints, b, blockinfo, prec, omega_p=None, omega_d=None):
+    def __init__(self, constraints, b, blockinfo, prec, omega_p=None, omega_d=None, C=None):
         self.ctx = ctx = mpmath.mp.clone()
         ctx.prec = prec
         self.bi = bi = blockinfo
@@ -59,6 +59,13 @@ class DenseSDP:
         self.X = {(j, l): ctx.eye(nb) * op for j, l, nb in self.blocks}
         self.Y = {(j, l): ctx.eye(nb) * od for j, l, nb in self.blocks}
         self.ntot = sum(nb for _, _, nb in self.blocks)
+        # objective matrix C (MPMP.jl:599): list over j of lists over l of MpArray (nb, nb); None = 0
+        self.C = None
+        if C is not None:
+            self.C = {}
+            for j, l, nb in self.blocks:
+                flat = C[j][l].reshape(nb * nb)
+                self.C[(j, l)] = ctx.matrix([[_mp(flat, r * nb + c, ctx) for c in range(nb)] for r in range(nb)])
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _tr(self, i, Z):
@@ -103,6 +110,8 @@ class DenseSDP:
         P = self._sumA(x)
         for k in keys:
             P[k] -= X[k]
+            if self.C is not None:
+                P[k] -= self.C[k]          # P = sum x_i A_i - X - C (MPMP.jl:1108-1118)
         d = [self.c[i] - sum(self.Brows[i][q] * y[q] for q in range(self.n_y)) - self._tr(i, Y) for i in range(self.nx)]
         p = [self.b[q] - sum(self.Brows[i][q] * x[i] for i in range(self.nx)) for q in range(self.n_y)]
         # Schur complement S[p,q] = Tr(A_p X^-1 A_q Y)
@@ -173,6 +182,14 @@ class DenseSDP:
         self.Y = {k: Y[k] + ad * dY[k] for k in keys}
         return dict(mu=mu, S=S, P=P, p=p, d=d, dx_pred=dxp, dy_pred=dyp, dx=dx, dy=dy, dX=dX, dY=dY, Z=Z, alpha_p=ap,
                     alpha_d=ad, beta_c=beta_c, lam_x=lam_x, lam_y=lam_y, Xinv=Xinv)
+
+    def objectives(self):
+        """(<c,x>, <C,Y> + <b,y>) of the current point, without b0 (MPMP.jl:1027-1034)"""
+        po = sum((ci * xi for ci, xi in zip(self.c, self.x)), self.ctx.mpf(0))
+        do = sum((bi * yi for bi, yi in zip(self.b, self.y)), self.ctx.mpf(0))
+        if self.C is not None:
+            do += self.dot(self.C, self.Y)
+        return po, do
 
     def x_index_of(self, j, r, s, k):
         """position of (j,r,s,k) in self.x / the solver's x vector (same ordering: j, then (r,s) pairs, k fastest)"""

@@ -2,7 +2,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 Each rank solves its shard of a clustered SDP through NCCL-coupled handles AND the full problem on its own GPU
 with an uncoupled handle; the log rows (mu, alpha, objectives) and the rank's slice of x, y must agree to
-2^-(p-16) relative (the sums over clusters are grouped differently, so the results are not bit-identical
+2^-(p-16) relative, and rank 0 also runs the CPU oracle on the whole problem and holds the N-GPU result to it (the sums over clusters are grouped differently, so the results are not bit-identical
 between 1 and N GPUs, but they are bit-identical across the ranks of one run)."""
 import ctypes
 import os
@@ -66,6 +66,27 @@ def main():
         bits_Q = rel_err_bits(hs.fetch("Q"), hf.fetch("Q"))
         print(f"[rank {rank}] iter {it+1}: x {bits_x:.1f} y {bits_y:.1f} Q {bits_Q:.1f} bits; alpha_d {rs.alpha_d:.15e}", flush=True)
         ok = ok and min(bits_x, bits_y, bits_Q) >= prec - 16
+    # the N-GPU result against the ORACLE run on the whole problem (rank 0 runs it; same 4 iterations)
+    if rank == 0:
+        from oracle.ref import oracle_handle
+        ho = oracle_handle(prec, os.cpu_count() or 1)
+        solver.load_problem(ho, full_c, full_b, bif)
+        ho.set_params(solver.real_params(ho.nlimb))
+        ho.init_point()
+        ho.prepare()
+        for it in range(4):
+            ro = ho.iterate()
+            assert ro.status == 0
+        for k in ("mu", "alpha_p", "alpha_d", "beta_c", "p_obj_new", "d_obj_new"):
+            a, b = getattr(rs, k), getattr(ro, k)
+            if not np.isclose(a, b, rtol=1e-13, atol=1e-300):
+                ok = False
+                print(f"[rank 0] {k}: {world}-GPU {a!r} vs oracle {b!r}", flush=True)
+        bo_x = rel_err_bits(hs.fetch("x"), ho.fetch("x").take(range(0, nsl)))
+        bo_y = rel_err_bits(hs.fetch("y"), ho.fetch("y"))
+        bo_Q = rel_err_bits(hs.fetch("Q"), ho.fetch("Q"))
+        print(f"[rank 0] after 4 iterations vs the oracle: x {bo_x:.1f} y {bo_y:.1f} Q {bo_Q:.1f} bits", flush=True)
+        ok = ok and min(bo_x, bo_y, bo_Q) >= prec - 16
     # replicated quantities are bit-identical across ranks
     y = hs.fetch("y")
     t = torch.tensor(y.limb.astype(np.int64).sum(axis=0) + y.exp, device="cuda")
