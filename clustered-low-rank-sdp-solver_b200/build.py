@@ -10,8 +10,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["gemm_i8.cu", "linalg.cu", "solver.cu", "capi.cu"]
-HEADERS = ["mpf.cuh", "common.cuh", "gemm_i8.cuh", "linalg.cuh", "solver.cuh", "comm.cuh", os.path.join("..", "..", "include", "clrsdp.h")]
+SOURCES = ["gemm_i8.cu", "linalg.cu", "solver.cu", "multi.cu", "capi.cu"]
+HEADERS = ["mpf.cuh", "common.cuh", "gemm_i8.cuh", "linalg.cuh", "solver.cuh", "multi.cuh", "comm.cuh", os.path.join("..", "..", "include", "clrsdp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 FLAGS += os.environ.get("CLRSDP_EXTRA_NVCC_FLAGS", "").split()

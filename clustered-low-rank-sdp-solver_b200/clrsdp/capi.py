@@ -55,7 +55,7 @@ class IterInfo(ctypes.Structure):
 
 class IntParams(ctypes.Structure):
     _fields_ = [("maxiterations", ctypes.c_int32), ("need_primal_feasible", ctypes.c_int32),
-                ("need_dual_feasible", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("need_dual_feasible", ctypes.c_int32), ("phase_timing", ctypes.c_int32)]
 
 
 class ClrsdpError(RuntimeError):
@@ -83,19 +83,60 @@ def load_product_library():
     return ctypes.CDLL(PRODUCT_LIB, mode=ctypes.RTLD_GLOBAL)
 
 
+def partition(weights, parts):
+    """clrsdp_partition (F16, the reference's distribute_weights_swapping, MPMP.jl:425-465): (set_of, max set weight)."""
+    lib = load_product_library()
+    f = lib.clrsdp_partition
+    f.restype = ctypes.c_double
+    f.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+    out = np.zeros(len(w), dtype=np.int32)
+    mx = f(w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(w), int(parts), out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    if mx < 0:
+        raise ClrsdpError(-1, "clrsdp_partition")
+    return out, mx
+
+
+def cluster_weight(m, L, n_samples, delta, n_y):
+    """clrsdp_cluster_weight: w_j of SURVEY §8e."""
+    lib = load_product_library()
+    f = lib.clrsdp_cluster_weight
+    f.restype = ctypes.c_double
+    f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    d = np.ascontiguousarray(np.asarray(delta, dtype=np.int32))
+    return f(int(m), int(L), int(n_samples), d.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(n_y))
+
+
 class Handle:
     """One solver handle behind the C ABI."""
 
-    def __init__(self, lib, prefix: str, prec_bits: int, device_or_threads: int = 0):
+    def __init__(self, lib, prefix: str, prec_bits: int, device_or_threads=0):
+        """device_or_threads: CUDA ordinal (product library) / thread count (oracle); a LIST of CUDA ordinals creates a
+        multi-device handle (clrsdp_create_multi: several GPUs, one process, the whole problem behind one handle)."""
         self.lib, self.prefix = lib, prefix
         self.prec = int(prec_bits)
         self.nlimb = self.prec // 32
         self._h = ctypes.c_void_p()
+        if isinstance(device_or_threads, (list, tuple)):
+            devs = np.ascontiguousarray(np.asarray(device_or_threads, dtype=np.int32))
+            f = self._fn("create_multi")
+            f.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+            st = f(ctypes.byref(self._h), self.prec, len(devs), devs.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+            if st != 0:
+                raise ClrsdpError(st, prefix + "create_multi")
+            return
         f = self._fn("create")
         f.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]
         st = f(ctypes.byref(self._h), self.prec, int(device_or_threads))
         if st != 0:
             raise ClrsdpError(st, prefix + "create")
+
+    def cluster_owner(self, J):
+        f = self._fn("cluster_owner")
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        out = np.zeros(J, dtype=np.int32)
+        self._check(f(self._h, int(J), out.ctypes.data_as(ctypes.POINTER(ctypes.c_int))), "cluster_owner")
+        return out
 
     def _fn(self, name):
         f = getattr(self.lib, self.prefix + name)
@@ -165,10 +206,12 @@ class Handle:
         self._check(f(self._h, ctypes.byref(sb), ctypes.byref(s0)), "upload_objective")
 
     def set_params(self, real_params: MpArray | None, maxiterations=500, need_primal_feasible=False,
-                   need_dual_feasible=False):
+                   need_dual_feasible=False, phase_timing=False):
+        """phase_timing: fill the reference's 17 per-phase buckets (MPMP.jl:889-898) on every iteration, also when the
+        iteration is replayed from a CUDA graph (event-record nodes inside the graph)."""
         f = self._fn("set_params")
         f.argtypes = [ctypes.c_void_p, ctypes.POINTER(clrsdp_mp), ctypes.POINTER(IntParams)]
-        ip = IntParams(int(maxiterations), int(bool(need_primal_feasible)), int(bool(need_dual_feasible)), 0)
+        ip = IntParams(int(maxiterations), int(bool(need_primal_feasible)), int(bool(need_dual_feasible)), int(bool(phase_timing)))
         if real_params is not None:
             assert real_params.n == P_COUNT
             s = real_params.c_struct()

@@ -167,8 +167,19 @@ def load_problem(h: capi.Handle, constraints, b: MpArray, blockinfo: BlockInfo, 
 
 
 def product_handle(prec=None, device=0) -> capi.Handle:
-    """Handle on the CUDA library. Raises if libclrsdp.so is missing — there is no CPU fallback."""
+    """Handle on the CUDA library. Raises if libclrsdp.so is missing — there is no CPU fallback.
+    `device`: a CUDA ordinal, or a list of ordinals for ONE handle that shards the clusters over several GPUs of the
+    box inside this process (clrsdp_create_multi)."""
     return capi.Handle(capi.load_product_library(), "clrsdp_", prec or precision(), device)
+
+
+def partition_clusters(blockinfo: BlockInfo, n_parts: int):
+    """Cluster -> part assignment by the library's weighted partitioner (F16, MPMP.jl:425-465 on the cluster weights of
+    SURVEY §8e): what clrsdp_create_multi does internally and what a one-process-per-GPU front end calls to pick each
+    rank's clusters. Returns (owner[j], max part weight)."""
+    bi = blockinfo
+    w = [capi.cluster_weight(bi.m[j], bi.L[j], bi.n_samples[j], bi.delta[j], bi.n_y) for j in range(bi.J)]
+    return capi.partition(w, n_parts)
 
 
 HEADER = "%5s %8s %11s %11s %11s %10s %10s %10s %10s %10s %10s %10s" % (
@@ -208,7 +219,7 @@ def solverank1sdp(constraints, b, blockinfo: BlockInfo, *, C=0, b0=0, maxiterati
                              omega_p=omega_p, omega_d=omega_d, duality_gap_threshold=duality_gap_threshold,
                              primal_error_threshold=primal_error_threshold,
                              dual_error_threshold=dual_error_threshold),
-                 maxiterations, need_primal_feasible, need_dual_feasible)
+                 maxiterations, need_primal_feasible, need_dual_feasible, phase_timing=verbose)
     sizes = [bs for j in range(blockinfo.J) for bs in blockinfo.Y_blocksizes[j]]
     n_X = int(sum(s * s for s in sizes))
     if len(initial_solutions) == 4:  # warm start (:689)
@@ -280,10 +291,7 @@ def _print_timings(rows, time_total):
     print("Time inside search directions (both predictor & corrector step)")
     print("%11s %11s %11s %11s %11s" % ("calc Z", "calc rhs x", "solve system", "calc dX", "calc dY"))
     print(("%11.5e " * 5) % tuple(t[12:17]))
-    if len(rows) > 2 and not t.any():
-        print("(per-phase times are only collected when the iteration is launched kernel by kernel: CLRSDP_GRAPH=0; "
-              "the default replays it from a CUDA graph and reports the total per iteration, `seconds`, only: "
-              "%.5e s over the same iterations)" % sum(r.seconds for r in rows[2:]))
+    print("(device time of the same iterations, CUDA events around each: %.5e s)" % sum(r.seconds for r in rows[2:]))
 
 
 # ---- check-pointing the iterate (the reference's warm start: initial_solutions, MPMP.jl:613, :689) ----

@@ -1095,7 +1095,7 @@ void GemmEngine::run_mma(const Slice& A, const Slice& B, const GemmPlan& plan, i
   p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   {
     static int pair = -1;
-    if (pair < 0) pair = getenv("CLRSDP_PAIR_N") ? atoi(getenv("CLRSDP_PAIR_N")) : 0;  // (off until measured on the GPU)
+    if (pair < 0) pair = getenv("CLRSDP_PAIR_N") ? atoi(getenv("CLRSDP_PAIR_N")) : 1;
     p.idesc2 = pair ? ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) : 0u;
   }
   p.sbo16 = (8u * p.BK) >> 4;

@@ -1573,8 +1573,49 @@ __global__ void gemv_kernel(GemvDev g) {
       stm<NL>(g.work, (int64_t)part * g.rows + r, acc);
   }
 }
+// Transposed access (element (r, k) at k*ld + r: B^T x, W dy, L^-T u): a warp owns 32 CONSECUTIVE rows, one per lane, so
+// every load of the warp is one coalesced 128-byte line per limb plane (the row-per-warp kernel above would touch 32
+// sectors for 32 words); each lane runs its own multiply-add chain over its K-part, the parts are summed by
+// gemv_sum_kernel. With items, lanes look their item up individually (a warp may straddle two items).
+template <int NL>
+__global__ void gemv_t_kernel(GemvDev g) {
+  const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int ngrp = (g.rows + 31) >> 5;
+  if (warp >= ngrp * g.nparts) return;
+  const int grp = warp / g.nparts, part = warp % g.nparts;
+  const int r = grp * 32 + lane;
+  if (r >= g.rows) return;
+  int64_t ab = g.a0, xb = g.x0, ld = g.ks;
+  int rl = r, K = g.K;
+  if (g.row_item) {
+    const int it = g.row_item[r];
+    ab = g.aoff[it];
+    xb = g.xoff[it];
+    rl = r - g.row0[it];
+    K = g.itemK[it];
+    ld = K;
+  }
+  const int chunk = (K + g.nparts - 1) / g.nparts;
+  const int k0 = part * chunk, k1 = min(K, k0 + chunk);
+  Num<NL> acc = mp::zero<NL>();
+  for (int k = k0; k < k1; k++) acc = mp::add(acc, mp::mul(ldm<NL>(g.A, ab + (int64_t)k * ld + rl), ldm<NL>(g.x, xb + k)));
+  if (g.nparts == 1)
+    stm<NL>(g.out, g.oo + r, acc);
+  else
+    stm<NL>(g.work, (int64_t)part * g.rows + r, acc);
+}
 template <int NL>
 __global__ void gemv_sum_kernel(GemvDev g) {
+  if (g.nparts > 16) {  // many parts (few rows): one warp per row, lanes stride the parts
+    const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (r >= g.rows) return;
+    Num<NL> acc = mp::zero<NL>();
+    for (int p = lane; p < g.nparts; p += 32) acc = nadd(acc, ldm<NL>(g.work, (int64_t)p * g.rows + r));
+#pragma unroll 1
+    for (int o = 16; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
+    if (lane == 0) stm<NL>(g.out, g.oo + r, acc);
+    return;
+  }
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= g.rows) return;
   Num<NL> acc = mp::zero<NL>();
@@ -1586,20 +1627,32 @@ static int gemv_parts(int rows, int K) {
   int p = std::min(ceil_div(K, 128), ceil_div(148 * 16, std::max(rows, 1)));
   return std::max(1, p);
 }
-size_t gemv_work_elems(int rows, int K) { return (size_t)rows * gemv_parts(rows, K); }
+static int gemv_parts_t(int rows, int K) {  // transposed kernel: about 16 warps per SM, at least 8 terms per part
+  const int ngrp = (rows + 31) / 32;
+  return std::max(1, std::min(ceil_div(K, 8), (148 * 16) / std::max(ngrp, 1)));
+}
+size_t gemv_work_elems(int rows, int K) { return (size_t)rows * std::max(gemv_parts(rows, K), gemv_parts_t(rows, K)); }
 void gemv(Ctx& ctx, int nl, const GemvArgs& a, mp::Tensor work) {
   if (a.rows <= 0) return;
   GemvDev g{a.A, a.x, a.out, work, a.a0, a.x0, a.oo, a.rs, a.ks, a.rows, a.K, 1, a.d_row_item, a.d_aoff, a.d_xoff,
             a.d_row0, a.d_K, a.item_trans};
-  g.nparts = a.d_row_item ? 1 : gemv_parts(a.rows, a.K);
+  const bool transposed = a.d_row_item ? a.item_trans != 0 : (a.rs == 1 && a.ks != 1);
+  // (items: every item is K_item x K_item here, so a.rows / number of items bounds K; the work buffer is sized by the caller
+  // with gemv_work_elems(rows, rows))
+  g.nparts = transposed ? gemv_parts_t(a.rows, a.d_row_item ? std::max(1, a.K_hint) : a.K) : (a.d_row_item ? 1 : gemv_parts(a.rows, a.K));
   DISPATCH_NL(nl, {
-    int64_t warps = (int64_t)a.rows * g.nparts;
-    int tk = ctx.begin("gemv", (double)a.rows * a.K * 4.0 * (NL + 1));
-    gemv_kernel<NL><<<ceil_div(warps * 32, 128), 128, 0, ctx.stream>>>(g);
+    int tk = ctx.begin(transposed ? "gemv_t" : "gemv", (double)a.rows * a.K * 4.0 * (NL + 1));
+    if (transposed) {
+      int64_t warps = (int64_t)((a.rows + 31) / 32) * g.nparts;
+      gemv_t_kernel<NL><<<ceil_div(warps * 32, 128), 128, 0, ctx.stream>>>(g);
+    } else {
+      int64_t warps = (int64_t)a.rows * g.nparts;
+      gemv_kernel<NL><<<ceil_div(warps * 32, 128), 128, 0, ctx.stream>>>(g);
+    }
     ctx.end(tk);
     if (g.nparts > 1) {
       tk = ctx.begin("gemv_sum");
-      gemv_sum_kernel<NL><<<ceil_div(a.rows, 128), 128, 0, ctx.stream>>>(g);
+      gemv_sum_kernel<NL><<<g.nparts > 16 ? ceil_div((int64_t)a.rows * 32, 128) : ceil_div(a.rows, 128), 128, 0, ctx.stream>>>(g);
       ctx.end(tk);
     }
   });

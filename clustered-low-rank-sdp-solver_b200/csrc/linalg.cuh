@@ -107,6 +107,7 @@ struct GemvArgs {
   const int* d_row0 = nullptr;
   const int* d_K = nullptr;
   int item_trans = 0;  // with items: 0 -> A_item[r][k], 1 -> A_item[k][r]; leading dimension = K_item
+  int K_hint = 0;      // with items: the largest K_item (sizes the K-split of the transposed kernel)
 };
 void gemv(Ctx& ctx, int nl, const GemvArgs& g, mp::Tensor work);
 size_t gemv_work_elems(int rows, int K);

@@ -70,6 +70,7 @@ Solver::~Solver() {
   drop_graph();
   if (comm_.comm) NcclApi::get().CommDestroy(comm_.comm);
   for (auto e : ev_) cudaEventDestroy(e);
+  for (auto e : gev_) cudaEventDestroy(e);
   for (auto e : ctx.pool) cudaEventDestroy(e);
   if (main_stream_) ctx.stream = main_stream_;
   if (ctx.stream) cudaStreamDestroy(ctx.stream);
@@ -370,7 +371,7 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
   Bmat.alloc((int64_t)sumS * n_y, nl);
   Wt.alloc((int64_t)sumS * n_y, nl);
   for (MpBuf* t : {&Q, &Uq, &Vq, &Linvq}) t->alloc((int64_t)n_y * n_y, nl);
-  for (MpBuf* t : {&x, &dx, &d, &c, &rhs, &tvec, &tmpx, &trx, &dx_pred}) t->alloc(sumS, nl);
+  for (MpBuf* t : {&x, &dx, &d, &c, &rhs, &rhs0, &tvec, &tmpx, &trx, &dx_pred}) t->alloc(sumS, nl);
   for (MpBuf* t : {&y, &dy, &p, &b, &tmpy, &zvec, &dyr, &dy_pred}) t->alloc(n_y, nl);
   xscale.ensure(sizeof(int) * (size_t)std::max(sumS, 1));
   xsign.ensure(sizeof(int) * (size_t)std::max(sumS, 1));
@@ -380,7 +381,8 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
   for (auto& g : cgroups_) maxrd = std::max<int64_t>(maxrd, (int64_t)g.clusters.size() * g.dimS);
   rdiag.alloc(maxrd, nl);
   lam.alloc(2 * blocks_.size(), nl);
-  work.alloc(std::max<size_t>({(size_t)4096, reduce_work_elems(), gemv_work_elems(n_y, sumS), gemv_work_elems(sumS, n_y)}), nl);
+  work.alloc(std::max<size_t>({(size_t)4096, reduce_work_elems(), gemv_work_elems(n_y, sumS), gemv_work_elems(sumS, n_y),
+                                 gemv_work_elems(sumS, sumS), gemv_work_elems(n_y, n_y)}), nl);
   n_status = 2 * (int)blocks_.size() + J + 1;  // X blocks, Y blocks, S_j, Q
   d_status.ensure(sizeof(int) * n_status);
   d_lamflag.ensure(sizeof(int) * 2 * std::max<size_t>(1, blocks_.size()));
@@ -587,6 +589,7 @@ void Solver::set_params(const clrsdp_mp* rp, const clrsdp_int_params* ipp) {
     for (int i = 0; i < CLRSDP_P_COUNT; i++) to_device(rp, i, 1, scal, slots[i]);
   }
   if (ipp) ip = *ipp;
+  phase_timing_ = ip.phase_timing != 0;
   drop_graph();
   int fl[4] = {0, 0, ip.need_primal_feasible, ip.need_dual_feasible};
   CLR_CUDA(cudaMemcpyAsync(d_flags.as<int>() + 2, fl + 2, 2 * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
@@ -981,6 +984,16 @@ void Solver::decomposition() {
     o.dst = Wt.t();
     o.d_off = g.offW.as<int64_t>();
     o.rs = sumS, o.cs = 1;
+    static int float_sites = getenv("CLRSDP_FLOAT_SITES") ? atoi(getenv("CLRSDP_FLOAT_SITES")) : 0;  // measuring aid
+    if (float_sites & 1) {
+      SmallGemmArgs sg;
+      sg.A = Bmat.t(), sg.B = Linvs.t(), sg.C = Wt.t();
+      sg.offA = g.offBt.as<int64_t>(), sg.offB = g.offS.as<int64_t>(), sg.offC = g.offW.as<int64_t>();
+      sg.ars = 1, sg.aks = n_y, sg.brs = g.dimS, sg.bks = 1, sg.crs = sumS, sg.ccs = 1;
+      sg.batch = (int)g.clusters.size(), sg.M = n_y, sg.N = g.dimS, sg.K = g.dimS;
+      // (D^-1 B: scale a copy of B's rows first)
+      throw SolverError(-1, "CLRSDP_FLOAT_SITES & 1 not implemented");
+    }
     ge()->multiply(g.sBt, g.sLinv, plan_of((int)g.clusters.size(), n_y, g.dimS), o);
   }
   mark(-1 - CLRSDP_T_CINVB);
@@ -996,6 +1009,15 @@ void Solver::decomposition() {
     OutDesc o;
     o.dst = Q.t();
     o.rs = n_y, o.cs = 1;
+    static int float_sites_q = getenv("CLRSDP_FLOAT_SITES") ? atoi(getenv("CLRSDP_FLOAT_SITES")) : 0;  // measuring aid
+    if (float_sites_q & 2) {  // Q by plain multiprecision multiply-adds (no block fixed point)
+      SmallGemmArgs sg;
+      sg.A = Wt.t(), sg.B = Wt.t(), sg.C = Q.t();
+      sg.ars = sumS, sg.aks = 1, sg.brs = sumS, sg.bks = 1, sg.crs = n_y, sg.ccs = 1;
+      sg.batch = 1, sg.M = n_y, sg.N = n_y, sg.K = sumS;
+      sg.ksign = xsign.as<int>(), sg.ksign_ld = sumS;
+      small_gemm(ctx, nl, sg);
+    } else
     ge()->multiply(sW, sWs_, plan_of(1, n_y, n_y), o, EPI_STORE, nullptr, true);  // symmetric: upper tiles only
     allreduce(Q, 0, (int64_t)n_y * n_y, COMB_SUM);  // the cross-cluster reduction (sum(Q), :1494)
   }
@@ -1035,6 +1057,7 @@ void Solver::search_direction() {
   mark(CLRSDP_T_SYS);
   {
     // S_j^-1 = D^-1 L'^-T Sigma L'^-1 D^-1:  t_j = Sigma L'_j^-1 (D_j^-1 rhs_j)
+    ew_lincomb(ctx, nl, rhs0.t(), 0, rhs.t(), 0, 1, rhs.t(), 0, 0, sumS);  // rhs_x itself, for the refinement below
     vec_scale(ctx, nl, rhs.t(), 0, sumS, -1, xscale.as<int>());
     GemvArgs a;
     a.A = Linvs.t(), a.x = rhs.t(), a.out = tvec.t();
@@ -1042,6 +1065,7 @@ void Solver::search_direction() {
     a.d_row_item = d_row_item.as<int>(), a.d_aoff = d_linv_off.as<int64_t>(), a.d_xoff = d_x_off64.as<int64_t>();
     a.d_row0 = d_row0.as<int>(), a.d_K = d_itemK.as<int>();
     a.item_trans = 0;  // A_item[r][k], leading dimension = K_item
+    for (auto& cg : cgroups_) a.K_hint = std::max(a.K_hint, cg.dimS);
     gemv(ctx, nl, a, work.t());
     vec_flip(ctx, nl, tvec.t(), 0, sumS, xsign.as<int>());  // t <- Sigma t
     // tmpy = sum_j W_j^T Sigma_j t_j = Wt t
@@ -1074,6 +1098,70 @@ void Solver::search_direction() {
     bt.item_trans = 1;  // A_item[k][r]
     gemv(ctx, nl, bt, work.t());
     vec_scale(ctx, nl, dx.t(), 0, sumS, -1, xscale.as<int>());  // L^-T = D^-1 L'^-T
+    static int refine_mode = getenv("CLRSDP_REFINE") ? atoi(getenv("CLRSDP_REFINE")) : 4;  // measuring aid, see the order below
+    auto refine_second = [&]() {
+    // One step of iterative refinement on the SECOND block equation, B^T dx = p. The reference obtains dy from
+    // Q = (B^T U^-1)(L^-1 B) and dx from the same two factors (MPMP.jl:1457-1495, :1751-1773), so B^T dx = p holds to
+    // rounding. Here Q = W^T Sigma W comes from the block fixed-point GEMM while dx is formed by floating gemvs with W
+    // and L'^-1: the two differ by dQ ~ 2^-(p+16) rowmax_a rowmax_b, which is large in absolute terms when S_j is
+    // singular to working precision (one huge row of L'^-1 per cluster on BASELINE config 3: K = 128 samples of
+    // polynomials of degree <= 126), and the primal residual p then stagnates around dQ dy instead of contracting by
+    // 1 - alpha per iteration (measured: 4e-42 and growing where the LU oracle is at 3e-69). So: r = p - B^T dx with the
+    // resident B (floating), dy += Q^-1 r, dx += S^-1 B Q^-1 r = D^-1 L'^-T Sigma W (Q^-1 r); the first block equation is
+    // untouched (S ddx - B ddy = 0) and the defect of the second becomes dQ ddy, quadratically small.
+    GemvArgs bx;
+    bx.A = Bmat.t(), bx.x = dx.t(), bx.out = tmpy.t();
+    bx.rs = 1, bx.ks = n_y, bx.rows = n_y, bx.K = sumS;
+    gemv(ctx, nl, bx, work.t());
+    allreduce(tmpy, 0, n_y, COMB_SUM);                                               // B^T dx over all clusters
+    ew_lincomb(ctx, nl, dyr.t(), 0, p.t(), 0, 1, tmpy.t(), 0, -1, n_y);              // r = p - B^T dx
+    GemvArgs r1 = q1;
+    r1.x = dyr.t(), r1.out = zvec.t();
+    gemv(ctx, nl, r1, work.t());
+    vec_flip(ctx, nl, zvec.t(), 0, n_y, qsign.as<int>());
+    GemvArgs r2 = q2;
+    r2.x = zvec.t(), r2.out = tmpy.t();
+    gemv(ctx, nl, r2, work.t());                                                     // ddy = Q^-1 r
+    ew_lincomb(ctx, nl, dy.t(), 0, dy.t(), 0, 1, tmpy.t(), 0, 1, n_y);
+    GemvArgs wr = wd;
+    wr.x = tmpy.t(), wr.out = tmpx.t();
+    gemv(ctx, nl, wr, work.t());                                                     // W ddy
+    vec_flip(ctx, nl, tmpx.t(), 0, sumS, xsign.as<int>());
+    GemvArgs mr = bt;
+    mr.x = tmpx.t(), mr.out = trx.t();
+    gemv(ctx, nl, mr, work.t());                                                     // L'^-T Sigma W ddy
+    vec_scale(ctx, nl, trx.t(), 0, sumS, -1, xscale.as<int>());
+    ew_lincomb(ctx, nl, dx.t(), 0, dx.t(), 0, 1, trx.t(), 0, 1, sumS);               // dx += S^-1 B ddy
+    };
+    auto refine_first = [&]() {
+    // ... and one step on the FIRST block equation, S dx - B dy = rhs_x, with the final dy: applying S^-1 through the
+    // explicit inverse factors has the forward error eps |M|^T |M| |v| instead of the eps cond(S) |dx| of triangular
+    // solves; near the optimum (cond(S) large) that shows as a dual residual d that stops contracting (measured: 1e-52
+    // where the LU oracle is at 1e-73). r = rhs_x + B dy - S dx is small, so the same factors applied to it are accurate.
+    GemvArgs bd;
+    bd.A = Bmat.t(), bd.x = dy.t(), bd.out = tmpx.t();
+    bd.rs = n_y, bd.ks = 1, bd.rows = sumS, bd.K = n_y;
+    gemv(ctx, nl, bd, work.t());                                                     // B dy
+    ew_lincomb(ctx, nl, tmpx.t(), 0, rhs0.t(), 0, 1, tmpx.t(), 0, 1, sumS);          // rhs_x + B dy
+    GemvArgs sd = a;
+    sd.A = S.t(), sd.x = dx.t(), sd.out = trx.t();
+    gemv(ctx, nl, sd, work.t());                                                     // S_j dx_j
+    ew_lincomb(ctx, nl, tmpx.t(), 0, tmpx.t(), 0, 1, trx.t(), 0, -1, sumS);          // r
+    vec_scale(ctx, nl, tmpx.t(), 0, sumS, -1, xscale.as<int>());
+    GemvArgs m1 = a;
+    m1.x = tmpx.t(), m1.out = trx.t();
+    gemv(ctx, nl, m1, work.t());                                                     // L'^-1 D^-1 r
+    vec_flip(ctx, nl, trx.t(), 0, sumS, xsign.as<int>());
+    GemvArgs m2 = bt;
+    m2.x = trx.t(), m2.out = tmpx.t();
+    gemv(ctx, nl, m2, work.t());                                                     // L'^-T Sigma ...
+    vec_scale(ctx, nl, tmpx.t(), 0, sumS, -1, xscale.as<int>());
+    ew_lincomb(ctx, nl, dx.t(), 0, dx.t(), 0, 1, tmpx.t(), 0, 1, sumS);              // dx += S^-1 r
+    };
+    // order: 1 = second only, 2 = first only, 3 = second then first, 4 = first then second
+    if (refine_mode == 1 || refine_mode == 3) refine_second();
+    if (refine_mode == 2 || refine_mode == 3 || refine_mode == 4) refine_first();
+    if (refine_mode == 4) refine_second();
   }
   mark(-1 - CLRSDP_T_SYS);
   mark(CLRSDP_T_DX);
@@ -1140,20 +1228,35 @@ void Solver::join_side() {
 }
 
 // ---- timing marks: bucket >= 0 begins a bucket, -1-bucket ends it -----------------------------------
+// Directly launched iterations record ordinary events. Inside the captured graph the marks become EVENT-RECORD NODES
+// (cudaEventRecordExternal) when phase timing is switched on (clrsdp_int_params.phase_timing): every replay then
+// re-records the same events, so the reference's 17 buckets (MPMP.jl:889-898, table :972-1012) are filled on the
+// default path too; switched off, the graph carries no event nodes and only the whole iteration is timed.
 void Solver::mark(int code) {
-  if (capturing_) return;  // the phase buckets are only filled on the directly launched path
+  const int bkt = code >= 0 ? code : -1 - code, sign = code >= 0 ? +1 : -1;
+  if (capturing_) {
+    if (!phase_timing_) return;
+    cudaEvent_t e;
+    if (graph_marks_.size() < gev_.size()) {
+      e = gev_[graph_marks_.size()];
+    } else {
+      CLR_CUDA(cudaEventCreate(&e));
+      gev_.push_back(e);
+    }
+    CLR_CUDA(cudaEventRecordWithFlags(e, ctx.stream, cudaEventRecordExternal));
+    graph_marks_.push_back(Mark{bkt, sign, e});
+    return;
+  }
   cudaEvent_t e;
-  if (ev_marks_.size() < ev_.size()) {
-    e = ev_[ev_marks_.size()];
+  if (n_direct_marks_ < ev_.size()) {
+    e = ev_[n_direct_marks_];
   } else {
     CLR_CUDA(cudaEventCreate(&e));
     ev_.push_back(e);
   }
+  n_direct_marks_++;
   CLR_CUDA(cudaEventRecord(e, ctx.stream));
-  if (code >= 0)
-    ev_marks_.emplace_back(code, +1);
-  else
-    ev_marks_.emplace_back(-1 - code, -1);
+  ev_marks_.push_back(Mark{bkt, sign, e});
 }
 
 int Solver::check_status_local() {
@@ -1330,6 +1433,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
   on_side_ = false;
   join_pending_ = false;
   ev_marks_.clear();
+  n_direct_marks_ = 0;
   CLR_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int) * n_status, ctx.stream));
   mark(CLRSDP_T_COUNT);  // whole iteration (extra bucket, reported as `seconds`)
   clrsdp_iter_info row;
@@ -1348,6 +1452,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
       cudaGraph_t graph = nullptr;
       const uint64_t e0 = alloc_epoch();
       const int64_t l0 = ctx.launches;
+      graph_marks_.clear();
       CLR_CUDA(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
       capturing_ = true;
       try {
@@ -1381,6 +1486,7 @@ int Solver::iterate(clrsdp_iter_info* info) {
     if (gexec_) {
       CLR_CUDA(cudaGraphLaunch(gexec_, ctx.stream));
       ctx.launches += graph_launches_;
+      ev_marks_.insert(ev_marks_.end(), graph_marks_.begin(), graph_marks_.end());  // re-recorded by this replay
       ran = true;
     }
   }
@@ -1412,12 +1518,12 @@ int Solver::iterate(clrsdp_iter_info* info) {
     std::vector<int> open(CLRSDP_T_COUNT + 1, -1);
     double total = 0;
     for (size_t i = 0; i < ev_marks_.size(); i++) {
-      int bkt = ev_marks_[i].first;
-      if (ev_marks_[i].second > 0) {
+      int bkt = ev_marks_[i].bucket;
+      if (ev_marks_[i].sign > 0) {
         open[bkt] = (int)i;
       } else if (open[bkt] >= 0) {
         float ms = 0;
-        cudaEventElapsedTime(&ms, ev_[open[bkt]], ev_[i]);
+        cudaEventElapsedTime(&ms, ev_marks_[open[bkt]].ev, ev_marks_[i].ev);
         if (bkt < CLRSDP_T_COUNT)
           row.timings[bkt] += ms * 1e-3;
         else

@@ -1,5 +1,6 @@
 // solver.cuh — the handle behind the C ABI: problem structure, HBM-resident state, one IPM iteration.
 #pragma once
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -45,37 +46,79 @@ struct ClusterGroup {
   DevBuf sig;   // per iteration: [clusters][dimS] signs of the pivots of S'_j = U^T Sigma U (1 = negative)
 };
 
-class Solver {
+// What the C ABI needs from a handle: implemented by Solver (one GPU) and by MultiSolver (multi.cuh: several GPUs of one
+// box behind one handle, one process).
+struct SolverApi {
+  virtual ~SolverApi() {}
+  virtual void set_structure(int J, int n_y, const int* m, const int* L, const int* K, const int* delta, const int* ranks) = 0;
+  virtual void upload_cluster(int j, const clrsdp_mp* V, const clrsdp_mp* H, const clrsdp_mp* B, const clrsdp_mp* c) = 0;
+  virtual void upload_objective(const clrsdp_mp* b, const clrsdp_mp* b0) = 0;
+  virtual void upload_C(const clrsdp_mp* C) = 0;
+  virtual void set_params(const clrsdp_mp* rp, const clrsdp_int_params* ip) = 0;
+  virtual void init_point() = 0;
+  virtual void upload_point(const clrsdp_mp* x, const clrsdp_mp* X, const clrsdp_mp* y, const clrsdp_mp* Y) = 0;
+  virtual void download_point(clrsdp_mp_out* x, clrsdp_mp_out* X, clrsdp_mp_out* y, clrsdp_mp_out* Y) = 0;
+  virtual int prepare(clrsdp_iter_info* info) = 0;
+  virtual int iterate(clrsdp_iter_info* info) = 0;
+  virtual int solve(clrsdp_iter_info* rows, int max_rows, int* n_rows) = 0;
+  virtual int64_t fetch(const char* name, int j, int l, clrsdp_mp_out* out) = 0;
+  virtual void comm_init(int n_ranks, int rank, const uint8_t* id) = 0;
+  virtual void pin_host(void* p, size_t bytes) = 0;
+  virtual void unpin_host(void* p) = 0;
+  virtual double measure_i8_peak() = 0;
+  virtual void op_gemm(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, clrsdp_mp_out* C) = 0;
+  virtual void op_gemm_planes(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, int32_t* planes,
+                              int* n_planes, int32_t* row_exp, int32_t* col_exp) = 0;
+  virtual int op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, clrsdp_mp_out* Linv) = 0;
+  virtual void op_signed_factor(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* Minv, int32_t* signs) = 0;
+  virtual void op_lambda_min(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lam) = 0;
+  virtual void op_elementwise(int op, const clrsdp_mp* a, const clrsdp_mp* b, clrsdp_mp_out* c) = 0;
+  virtual int64_t launch_count() = 0;
+  virtual void profile_reset(bool enable) = 0;
+  virtual std::map<std::string, ProfEntry> profile_table() = 0;
+};
+
+class Solver : public SolverApi {
  public:
   Solver(int prec_bits, int device);
-  ~Solver();
-  void set_structure(int J, int n_y, const int* m, const int* L, const int* K, const int* delta, const int* ranks);
-  void upload_cluster(int j, const clrsdp_mp* V, const clrsdp_mp* H, const clrsdp_mp* B, const clrsdp_mp* c);
-  void upload_objective(const clrsdp_mp* b, const clrsdp_mp* b0);
-  void upload_C(const clrsdp_mp* C);
-  void set_params(const clrsdp_mp* rp, const clrsdp_int_params* ip);
-  void init_point();
-  void upload_point(const clrsdp_mp* x, const clrsdp_mp* X, const clrsdp_mp* y, const clrsdp_mp* Y);
-  void download_point(clrsdp_mp_out* x, clrsdp_mp_out* X, clrsdp_mp_out* y, clrsdp_mp_out* Y);
-  int prepare(clrsdp_iter_info* info);
-  int iterate(clrsdp_iter_info* info);
-  int solve(clrsdp_iter_info* rows, int max_rows, int* n_rows);
-  int64_t fetch(const char* name, int j, int l, clrsdp_mp_out* out);
-  void comm_init(int n_ranks, int rank, const uint8_t* id);
-  void pin_host(void* p, size_t bytes);
-  void unpin_host(void* p);
-  double measure_i8_peak() {
+  ~Solver() override;
+  void set_structure(int J, int n_y, const int* m, const int* L, const int* K, const int* delta, const int* ranks) override;
+  void upload_cluster(int j, const clrsdp_mp* V, const clrsdp_mp* H, const clrsdp_mp* B, const clrsdp_mp* c) override;
+  void upload_objective(const clrsdp_mp* b, const clrsdp_mp* b0) override;
+  void upload_C(const clrsdp_mp* C) override;
+  void set_params(const clrsdp_mp* rp, const clrsdp_int_params* ip) override;
+  void init_point() override;
+  void upload_point(const clrsdp_mp* x, const clrsdp_mp* X, const clrsdp_mp* y, const clrsdp_mp* Y) override;
+  void download_point(clrsdp_mp_out* x, clrsdp_mp_out* X, clrsdp_mp_out* y, clrsdp_mp_out* Y) override;
+  int prepare(clrsdp_iter_info* info) override;
+  int iterate(clrsdp_iter_info* info) override;
+  int solve(clrsdp_iter_info* rows, int max_rows, int* n_rows) override;
+  int64_t fetch(const char* name, int j, int l, clrsdp_mp_out* out) override;
+  void comm_init(int n_ranks, int rank, const uint8_t* id) override;
+  void pin_host(void* p, size_t bytes) override;
+  void unpin_host(void* p) override;
+  double measure_i8_peak() override {
     CLR_CUDA(cudaSetDevice(ctx.device));
     return gemm_->measure_i8_peak();
   }
   // phase-level ops
-  void op_gemm(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, clrsdp_mp_out* C);
+  void op_gemm(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, clrsdp_mp_out* C) override;
   void op_gemm_planes(int batch, int M, int N, int K, const clrsdp_mp* A, const clrsdp_mp* B, int32_t* planes,
-                      int* n_planes, int32_t* row_exp, int32_t* col_exp);
-  int op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, clrsdp_mp_out* Linv);
-  void op_signed_factor(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* Minv, int32_t* signs);
-  void op_lambda_min(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lam);
-  void op_elementwise(int op, const clrsdp_mp* a, const clrsdp_mp* b, clrsdp_mp_out* c);
+                      int* n_planes, int32_t* row_exp, int32_t* col_exp) override;
+  int op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, clrsdp_mp_out* Linv) override;
+  void op_signed_factor(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* Minv, int32_t* signs) override;
+  void op_lambda_min(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lam) override;
+  void op_elementwise(int op, const clrsdp_mp* a, const clrsdp_mp* b, clrsdp_mp_out* c) override;
+  int64_t launch_count() override { return ctx.launches; }
+  void profile_reset(bool enable) override {
+    ctx.resolve();
+    ctx.prof.clear();
+    ctx.profiling = enable;
+  }
+  std::map<std::string, ProfEntry> profile_table() override {
+    ctx.resolve();
+    return ctx.prof;
+  }
 
   Ctx ctx;
   int nl;
@@ -169,7 +212,7 @@ class Solver {
   MpBuf XY2, dXY2, Linv2, U2, W2, T1d, T2d;  // paired arenas: X|Y, dX|dY, Lx^-1|Ly^-1, work
   MpBuf X, Y, Xinv, R, P, Z, dX, dY, XY, T1, T2, Ux, Vx, Linvx, Linvy;  // X,Y,dX,dY,Linv*,T1,T2,Ux are views
   MpBuf Vt, H, Px, Py, Tt, VD, QP, S, Us, Vs, Linvs, Bmat, Wt, Q, Uq, Vq, Linvq;
-  MpBuf x, dx, d, c, rhs, tvec, tmpx, trx, y, dy, p, b, tmpy, zvec, dyr;
+  MpBuf x, dx, d, c, rhs, rhs0, tvec, tmpx, trx, y, dy, p, b, tmpy, zvec, dyr;
   MpBuf dX_pred, dY_pred, dx_pred, dy_pred;
   MpBuf Cmat;  // objective matrix C (block structure of X), only allocated by upload_C
   bool have_C = false;
@@ -186,8 +229,14 @@ class Solver {
   int n_status = 0;
   // iteration bookkeeping
   int iter = 1;
-  std::vector<cudaEvent_t> ev_;
-  std::vector<std::pair<int, int>> ev_marks_;  // (bucket, +1 begin / -1 end)
+  struct Mark {
+    int bucket, sign;  // +1 begin / -1 end
+    cudaEvent_t ev;
+  };
+  std::vector<cudaEvent_t> ev_, gev_;             // events of directly recorded marks / of the event-record nodes of the graph
+  std::vector<Mark> ev_marks_, graph_marks_;      // marks of this iteration / marks captured into the graph
+  size_t n_direct_marks_ = 0;
+  bool phase_timing_ = false;                     // clrsdp_int_params.phase_timing
   double h_scal[SL_COUNT];
   int h_flags[4];
 };

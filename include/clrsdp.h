@@ -96,7 +96,10 @@ typedef struct {
   int32_t maxiterations;        /* 500 (MPMP.jl:601); the loop runs while iter < maxiterations (:752) */
   int32_t need_primal_feasible; /* MPMP.jl:610 */
   int32_t need_dual_feasible;   /* MPMP.jl:611 */
-  int32_t reserved;
+  int32_t phase_timing;         /* != 0: fill the 17 per-phase buckets of clrsdp_iter_info on every iteration (event-record
+                                   nodes inside the replayed CUDA graph, ~1 % of an iteration); 0: only `seconds`. The
+                                   reference always collects them (MPMP.jl:889-898); the Python/Julia shims switch this
+                                   on whenever they print the timing table (:972-1012). */
 } clrsdp_int_params;
 
 /* The 17 timing buckets of the reference (MPMP.jl:889-898), seconds for THIS iteration. */
@@ -207,11 +210,28 @@ int clrsdp_op_lambda_min(clrsdp_handle h, int batch, int n, const clrsdp_mp* A, 
 int clrsdp_op_elementwise(clrsdp_handle h, int op, const clrsdp_mp* a, const clrsdp_mp* b,
                           clrsdp_mp_out* c);
 
-/* ---- multi-GPU (clusters sharded over ranks) ------------------------------------ */
-/* One process per GPU. Rank 0 obtains an id, the host language broadcasts the 128 bytes (e.g.
- * torch.distributed.broadcast), every rank calls comm_init. After that set_structure/upload_cluster
- * are given ONLY the local clusters; Q, the n_y-vectors and the scalar reductions are all-reduced
- * as fixed-point int64 lanes over NCCL inside iterate. */
+/* ---- multi-GPU (clusters sharded over GPUs) -------------------------------------- */
+/* (a) ONE PROCESS, several GPUs behind one handle (what a Julia front end uses: no extra processes, no
+ * rendezvous). dev_ids: n_dev distinct CUDA ordinals (NULL = 0..n_dev-1). The handle takes the WHOLE problem through
+ * the same calls as a single-GPU handle (global cluster indices, iterates in global order); set_structure assigns the
+ * clusters to the devices with clrsdp_partition on the weights clrsdp_cluster_weight, the library routes data to the
+ * owning device and runs prepare / iterate / solve on all devices at once (one host thread per device inside the
+ * library; communicators from one ncclUniqueId). n_dev == 1 gives a plain single-GPU handle. */
+int clrsdp_create_multi(clrsdp_handle* h, int prec_bits, int n_dev, const int* dev_ids);
+/* owner[j] = index (0..n_dev-1) of the device that holds cluster j (after set_structure; all 0 for one device) */
+int clrsdp_cluster_owner(clrsdp_handle h, int J, int* owner);
+/* F16 - the reference's distribute_weights_swapping (MPMP.jl:425-465; it spreads (j,l) blocks over threads, :492-499;
+ * here: clusters over GPUs): sets of cardinalities differing by at most one, contiguous at first, then improved by swaps
+ * between the heaviest and the lightest set. set_of[i] = set of item i; returns the largest set weight (< 0 on error). */
+double clrsdp_partition(const double* weights, int n, int parts, int* set_of);
+/* w_j of SURVEY §8e: 40 sum_l nb^3 + dim_S^3/3 + dim_S^2 n_y + n_y^2 dim_S  (delta: the L vector lengths of cluster j) */
+double clrsdp_cluster_weight(int m, int L, int n_samples, const int* delta, int n_y);
+
+/* (b) One process per GPU (torchrun-style). Rank 0 obtains an id, the host language broadcasts the 128 bytes (e.g.
+ * torch.distributed.broadcast), every rank calls comm_init. After that set_structure/upload_cluster are given ONLY the
+ * local clusters (any subset, e.g. the sets of clrsdp_partition).
+ * In both modes the only collectives are the ones SURVEY §8e lists - Q (n_y^2), three n_y-vectors and the scalar
+ * sum / max / min reductions per iteration - inside prepare / iterate. */
 int clrsdp_comm_unique_id(uint8_t id[128]);
 int clrsdp_comm_init(clrsdp_handle h, int n_ranks, int rank, const uint8_t id[128]);
 

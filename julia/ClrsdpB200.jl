@@ -81,7 +81,7 @@ struct IterInfo
     timings::NTuple{T_COUNT,Float64}
 end
 
-const HIGHER_PRECISION = (-10, -11, -12, -13, -14)   # NOT_PD_X, NOT_PD_Y, SINGULAR_S, SINGULAR_Q, EIG
+const HIGHER_PRECISION = (-10, -11, -12, -13, -14, -16)   # NOT_PD_X, NOT_PD_Y, SINGULAR_S, SINGULAR_Q, EIG, DIVERGED
 function chk(h, st, what)
     st == 0 && return
     if st in HIGHER_PRECISION                        # the reference's messages (MPMP.jl:793, :1439, :1503, :1882)
@@ -120,12 +120,15 @@ function solverank1sdp(constraints, b, blockinfo; C = 0, b0 = 0, maxiterations =
         omega_p = BigFloat(10)^10, omega_d = BigFloat(10)^10, duality_gap_threshold = BigFloat(10)^(-15),
         primal_error_threshold = BigFloat(10)^(-30), dual_error_threshold = BigFloat(10)^(-30),
         need_primal_feasible = false, need_dual_feasible = false, testing = true, initial_solutions = [],
-        device = 0)
-    C == 0 || error("the B200 path supports C = 0 only (the reference's default, MPMP.jl:599)")
+        devices = [0])
+    # `devices`: CUDA ordinals. One entry = one GPU; several = ONE handle that shards the clusters over those GPUs of the
+    # box inside this Julia process (clrsdp_create_multi: weighted partition of the clusters, one library thread per
+    # device, NCCL between them) - no extra processes, nothing else changes below.
     bi = blockinfo
     href = Ref{Ptr{Cvoid}}(C_NULL)
-    st = ccall((:clrsdp_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint), href, precision(BigFloat), device)
-    st == 0 || error("clrsdp_create failed ($st): no sm_100 device or unsupported precision — there is no CPU fallback")
+    st = ccall((:clrsdp_create_multi, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cint}), href, precision(BigFloat),
+               length(devices), Cint.(devices))
+    st == 0 || error("clrsdp_create_multi failed ($st): no sm_100 device or unsupported precision — there is no CPU fallback")
     h = href[]
     try
         delta = Cint[bi.Y_blocksizes[j][l] ÷ bi.m[j] for j in 1:bi.J for l in 1:bi.L[j]]
@@ -145,9 +148,13 @@ function solverank1sdp(constraints, b, blockinfo; C = 0, b0 = 0, maxiterations =
         bw, b0w = MpArr(b), MpArr([b0])
         GC.@preserve bw b0w chk(h, ccall((:clrsdp_upload_objective, LIB), Cint, (Ptr{Cvoid}, Ref{CMp}, Ref{CMp}),
                                          h, cmp(bw), cmp(b0w)), "upload_objective")
+        if C != 0                                                       # objective matrix (MPMP.jl:599, :1108-1118, :1031-1034)
+            Cw = flatten_blocks([C.blocks[j].blocks for j in 1:bi.J])
+            GC.@preserve Cw chk(h, ccall((:clrsdp_upload_C, LIB), Cint, (Ptr{Cvoid}, Ref{CMp}), h, cmp(Cw)), "upload_C")
+        end
         rp = MpArr([beta_infeasible, beta_feasible, gamma, omega_p, omega_d, duality_gap_threshold,
                     primal_error_threshold, dual_error_threshold])   # order: CLRSDP_P_* of clrsdp.h
-        ip = Cint[maxiterations, need_primal_feasible, need_dual_feasible, 0]
+        ip = Cint[maxiterations, need_primal_feasible, need_dual_feasible, 1]   # 1: fill the 17 timing buckets (:889-898)
         GC.@preserve rp chk(h, ccall((:clrsdp_set_params, LIB), Cint, (Ptr{Cvoid}, Ref{CMp}, Ptr{Cint}), h, cmp(rp), ip), "set_params")
         if length(initial_solutions) == 4                             # warm start (MPMP.jl:689)
             x0, X0, y0, Y0 = initial_solutions

@@ -118,6 +118,9 @@ static int g_gemm_fixed = 0;
 // 2^-(p-CLRSDP_REF_CLAMP) raised to that floor), kept because it reproduces round 1's loss of the iterate on sphere packing
 // d = 8 at 256 bits. CLRSDP_REF_REFINE=<n> adds n steps of iterative refinement of the Schur solve (measured: no help).
 static int g_clamp_bits = 16, g_refine = 0;
+static int g_guard_sites = 0xff;        // CLRSDP_REF_GUARD_SITES: which products the reduced window applies to (1 = W, 2 = Q, 4 = rest)
+static thread_local int g_site = 4;
+static int g_fixed_guard = 64;  // CLRSDP_REF_FIXED_GUARD: guard bits of the fixed-point window below a row's largest entry (GPU: 16)
 
 struct FixedRows {  // rows[r][k]: Lw limbs, sign, and the row exponent: value = +-limbs * 2^(E - 64 Lw)
   int Lw = 0, K = 0;
@@ -153,6 +156,7 @@ static void to_fixed(FixedRows& F, int rows, int K, long prec, Get get) {
       const int ws = (int)(sh / 64), bs = (int)(sh % 64);
       for (int i = 0; i + ws < Lw; i++) dst[i] = tmp[i + ws];
       if (bs) __gmpn_rshift(dst, dst, Lw, (unsigned)bs);
+      if (g_fixed_guard < 64 && (g_guard_sites & g_site)) dst[0] &= ~(((mp_limb_t)1 << (64 - g_fixed_guard)) - 1);  // experiment: window of p + guard bits
       F.sign[(size_t)r * K + k] = x.v._mpfr_sign < 0 ? -1 : 1;
     }
   }
@@ -724,7 +728,7 @@ struct clrsdp_solver {
               r_mul(w, a[v_off + k], bk.H[col]);  // ref(a,k+v_offset)*H  (:1654)
               for (int i = 0; i < dl; i++) r_mul(vs_scaled(i, col), w, bk.V(i, col));
             }
-          gemm(Qp, vs_scaled, bk.VT);  // VD * V^T (:1659)
+          g_site = 128; gemm(Qp, vs_scaled, bk.VT); g_site = 4;  // VD * V^T (:1659)
           if (r != s)
             for (auto& e : Qp.a) r_half(e);  // factor 1/2 of E_rs (:1661-1663)
           for (int i = 0; i < dl; i++)
@@ -868,8 +872,8 @@ struct clrsdp_solver {
       int dl = bk.delta, bs = bk.Nv, m = c.m;
       Mat Px(m * bs, m * bs), Py(m * bs, m * bs), partX, partY, Xp, Yp;
       for (int s = 0; s < m; s++) {
-        gemm_cols(partX, Xinv[j][l], s * dl, dl, bk.V);  // X_inv[:, s-block] * V (:1291-1293)
-        gemm_cols(partY, Y[j][l], s * dl, dl, bk.V);     // (:1294-1296)
+        g_site = 16; gemm_cols(partX, Xinv[j][l], s * dl, dl, bk.V); g_site = 4;  // X_inv[:, s-block] * V (:1291-1293)
+        g_site = 16; gemm_cols(partY, Y[j][l], s * dl, dl, bk.V); g_site = 4;     // (:1294-1296)
         for (int r = 0; r < m; r++) {
           Mat subX(dl, bs), subY(dl, bs);
           for (int i = 0; i < dl; i++)
@@ -877,8 +881,8 @@ struct clrsdp_solver {
               subX(i, v) = partX(r * dl + i, v);
               subY(i, v) = partY(r * dl + i, v);
             }
-          gemm(Xp, bk.VT, subX);  // V^T (X^-1 V) (:1300-1306)
-          gemm(Yp, bk.VT, subY);  // (:1308-1315)
+          g_site = 16; gemm(Xp, bk.VT, subX); g_site = 4;  // V^T (X^-1 V) (:1300-1306)
+          g_site = 16; gemm(Yp, bk.VT, subY); g_site = 4;  // (:1308-1315)
           for (int a = 0; a < bs; a++)
             for (int v = 0; v < bs; v++) {
               Px(r * bs + a, s * bs + v) = Xp(a, v);
@@ -1027,7 +1031,9 @@ struct clrsdp_solver {
       Mat DB(cl[j].dimS, n_y);
       for (int i = 0; i < cl[j].dimS; i++)
         for (int k = 0; k < n_y; k++) mpfr_mul_2si(&DB(i, k).v, &cl[j].B(i, k).v, -dec.sc[j][i], MPFR_RNDN);
+      g_site = 1;
       gemm(dec.W[j], dec.Linv[j], DB);
+      g_site = 4;
     });
     n_clamped_S = 0;
     for (int j = 0; j < J; j++) n_clamped_S += cl_[j];
@@ -1037,7 +1043,9 @@ struct clrsdp_solver {
       for (int i = 0; i < cl[j].dimS; i++)
         if (dec.sg[j][i] < 0)
           for (int k = 0; k < n_y; k++) r_neg(Wt(k, i), Wt(k, i));
+      g_site = 2;
       gemm(Qj, Wt, dec.W[j]);
+      g_site = 4;
       for (size_t i = 0; i < Q.a.size(); i++) r_add(Q.a[i], Q.a[i], Qj.a[i]);
     }
     Q_keep = Q;
@@ -1056,11 +1064,11 @@ struct clrsdp_solver {
       int n = cl[j].dimS;
       Mat rhs(n, 1);
       for (int i = 0; i < n; i++) mpfr_mul_2si(&rhs(i, 0).v, &rx[x_idx[j] + i].v, -dec.sc[j][i], MPFR_RNDN);
-      gemm(tv[j], dec.Linv[j], rhs);
+      g_site = 8; gemm(tv[j], dec.Linv[j], rhs); g_site = 4;
       for (int i = 0; i < n; i++)
         if (dec.sg[j][i] < 0) r_neg(tv[j](i, 0), tv[j](i, 0));  // tv = Sigma L^-1 D^-1 rx
       Mat Wt = transpose(dec.W[j]);
-      gemm(ty[j], Wt, tv[j]);
+      g_site = 8; gemm(ty[j], Wt, tv[j]); g_site = 4;
     });
     Mat dyr(n_y, 1), z, dyv;
     for (int k = 0; k < n_y; k++) {
@@ -1068,23 +1076,23 @@ struct clrsdp_solver {
       for (int j = 0; j < J; j++) r_add(sum, sum, ty[j](k, 0));
       r_sub(dyr(k, 0), ry[k], sum);
     }
-    gemm(z, dec.LinvQ, dyr);
+    g_site = 8; gemm(z, dec.LinvQ, dyr); g_site = 4;
     for (int k = 0; k < n_y; k++)
       if (dec.sgQ[k] < 0) r_neg(z(k, 0), z(k, 0));
     Mat LqT = transpose(dec.LinvQ);
-    gemm(dyv, LqT, z);
+    g_site = 8; gemm(dyv, LqT, z); g_site = 4;
     sdy.assign(n_y, Real());
     for (int k = 0; k < n_y; k++) sdy[k] = dyv(k, 0);
     sdx.assign(sumS, Real());
     parallel_for(J, [&](int j) {
       Mat u, sol;
-      gemm(u, dec.W[j], dyv);
+      g_site = 8; gemm(u, dec.W[j], dyv); g_site = 4;
       for (int i = 0; i < cl[j].dimS; i++) {
         if (dec.sg[j][i] < 0) r_neg(u(i, 0), u(i, 0));  // Sigma (W dy) + Sigma t
         r_add(u(i, 0), u(i, 0), tv[j](i, 0));
       }
       Mat LiT = transpose(dec.Linv[j]);
-      gemm(sol, LiT, u);
+      g_site = 8; gemm(sol, LiT, u); g_site = 4;
       for (int i = 0; i < cl[j].dimS; i++) mpfr_mul_2si(&sdx[x_idx[j] + i].v, &sol(i, 0).v, -dec.sc[j][i], MPFR_RNDN);
     });
   }
@@ -1125,9 +1133,9 @@ struct clrsdp_solver {
     parallel_for((int)jl.size(), [&](int q) {  // Z = sym(X^-1 (P Y - R)) (:1700-1729)
       int j = jl[q].first, l = jl[q].second;
       Mat T;
-      gemm(T, P[j][l], Y[j][l]);
+      g_site = 32; gemm(T, P[j][l], Y[j][l]); g_site = 4;
       for (size_t i = 0; i < T.a.size(); i++) r_sub(T.a[i], T.a[i], R[j][l].a[i]);
-      gemm(T, Xinv[j][l], T);
+      g_site = 32; gemm(T, Xinv[j][l], T); g_site = 4;
       Mat& Zb = Z[j][l];
       for (int i = 0; i < T.r; i++)
         for (int i2 = 0; i2 < T.c; i2++) {
@@ -1194,9 +1202,9 @@ struct clrsdp_solver {
     parallel_for((int)jl.size(), [&](int q) {  // dY = sym(X^-1 (R - dX Y)) (:1791-1820)
       int j = jl[q].first, l = jl[q].second;
       Mat T;
-      gemm(T, dX[j][l], Y[j][l]);
+      g_site = 64; gemm(T, dX[j][l], Y[j][l]); g_site = 4;
       for (size_t i = 0; i < T.a.size(); i++) r_sub(T.a[i], R[j][l].a[i], T.a[i]);
-      gemm(T, Xinv[j][l], T);
+      g_site = 64; gemm(T, Xinv[j][l], T); g_site = 4;
       Mat& D = dY[j][l];
       for (int i = 0; i < T.r; i++)
         for (int i2 = 0; i2 < T.c; i2++) {
@@ -1505,6 +1513,8 @@ REF_API int clrsdp_ref_create(clrsdp_handle* h, int prec_bits, int nthreads) {
     const char* gm = getenv("CLRSDP_REF_GEMM");
     g_gemm_fixed = (gm && std::string(gm) == "fixed") ? 1 : 0;
     if (const char* cb = getenv("CLRSDP_REF_CLAMP")) g_clamp_bits = atoi(cb);
+    if (const char* fg = getenv("CLRSDP_REF_FIXED_GUARD")) g_fixed_guard = std::min(64, std::max(1, atoi(fg)));
+    if (const char* gs = getenv("CLRSDP_REF_GUARD_SITES")) g_guard_sites = atoi(gs);
     if (const char* rf = getenv("CLRSDP_REF_REFINE")) g_refine = atoi(rf);
   }
   if (!h || prec_bits < 64 || prec_bits % 32) return CLRSDP_ERR_BAD_ARG;

@@ -3,7 +3,7 @@
 Oracle parity AT FULL SIZE: `test_cfg3_full_size_iterations_match_oracle` runs two whole iterations of the headline
 bench workload on the GPU and on the oracle (a few seconds per iteration on the box's host cores) and compares every
 field; `test_cfg5_shape_iterations_match_oracle_512bit` does the same on a cluster-subsampled instance of BASELINE
-config 5's shape (block 128, 256 samples, n_y = 1024) at 512 bits. Beside them, size-independent properties of the
+config 5's shape (block 128, 256 samples) at 512 bits. Beside them, size-independent properties of the
 quantities the iteration produces:
 
   * X^-1 X = I and U^T-free reconstruction L^-1 X L^-T = I for sampled blocks (host mpmath, p - 40 bits: the blocks
@@ -97,54 +97,63 @@ def test_sliced_gemm_is_linear_at_block_size():
 
 
 def _pair(cons, b, bi, prec, env=None):
+    """GPU handle, oracle handle, and the oracle at p + 64 bits on the same (exactly widened) instance: the arbiter for
+    quantities whose conditioning exceeds 2^16 (test_gpu_solver.agree)."""
     import os
     from oracle.ref import oracle_handle
+    from test_gpu_solver import widen_problem
     hg = solver.product_handle(prec)
     for k, v in (env or {}).items():
         os.environ[k] = v
     try:
         ho = oracle_handle(prec, os.cpu_count() or 1)
+        ht = oracle_handle(prec + 64, os.cpu_count() or 1)
     finally:
         for k in (env or {}):
             os.environ.pop(k, None)
-    for h in (hg, ho):
-        solver.load_problem(h, cons, b, bi)
+    wc, wb = widen_problem(cons, b, 2)
+    for h, (c_, b_) in ((hg, (cons, b)), (ho, (cons, b)), (ht, (wc, wb))):
+        solver.load_problem(h, c_, b_, bi)
         h.set_params(solver.real_params(h.nlimb))
         h.init_point()
         h.prepare()
-    return hg, ho
+    return hg, ho, ht
 
 
 def test_cfg3_full_size_iterations_match_oracle():
     """The headline bench workload itself (BASELINE config 3: J = 64, block 64, K = 128, n_y = 256, 256 bit, the bench's
-    seed): two iterations on the GPU and on the oracle, compared field by field at relative 2^-(p-16): all vectors
+    seed): two iterations on the GPU and on the oracle, compared field by field at relative 2^-(p-16) (where the conditioning
+    of the instance pushes both arithmetics past that: GPU no worse than the oracle against the same iteration at p + 64
+    bits, test_gpu_solver.agree): all vectors
     (d, dx, dy, x, y of both the predictor and the corrector), p, Q (65 536 entries), the driver scalars and objectives
     in full; S_j and the thirteen block fields for the clusters 0, 21, 42 and 63."""
     from test_gpu_solver import compare_iteration
     cons, b, _ = instances.synthetic_clustered_sdp(J=64, delta=64, K=128, n_y=256, prec=PREC, seed=20261018)
     bi = solver.get_block_info(cons)
-    hg, ho = _pair(cons, b, bi, PREC)
+    hg, ho, ht = _pair(cons, b, bi, PREC)
     for it in range(2):
-        rg, ro = hg.iterate(), ho.iterate()
-        assert rg.status == 0 and ro.status == 0
-        compare_iteration(hg, ho, bi, PREC, PREC - 16, clusters=(0, 21, 42, 63))
+        rg, ro, rt = hg.iterate(), ho.iterate(), ht.iterate()
+        assert rg.status == 0 and ro.status == 0 and rt.status == 0
+        compare_iteration(hg, ho, bi, PREC, PREC - 16, ht, clusters=(0, 21, 42, 63))
         assert rg.pd_feasible == ro.pd_feasible and rg.terminate == ro.terminate
         assert rg.alpha_p == pytest.approx(ro.alpha_p, rel=1e-13) and rg.alpha_d == pytest.approx(ro.alpha_d, rel=1e-13)
 
 
 def test_cfg5_shape_iterations_match_oracle_512bit():
-    """BASELINE config 5's cluster shape (block 128, K = 256, dim_S = 256, n_y = 1024) at its precision, 512 bits, on a
-    cluster subsample (J = 2 of the 512, the configuration's own seed): two iterations GPU against oracle, every field at
-    relative 2^-(p-16). The oracle runs its block fixed-point products here (CLRSDP_REF_GEMM=fixed: exact integer dot
-    products, one rounding per entry - as accurate as its fma loops, test_oracle_pin.py, and 2-3x faster: about a
-    minute per iteration at this shape)."""
+    """BASELINE config 5's block and cluster shape (block 128, K = 256, dim_S = 256) at its precision, 512 bits, on a
+    cluster subsample: J = 3 of the 512 clusters (the configuration's own seed) with n_y = 512 - the free variables are
+    halved with the clusters so that sum dim_S = 768 > n_y and Q = B^T S^-1 B stays non-singular (with J = 2 and
+    n_y = 1024 it has rank 512 and the oracle's own dy is noise). Two iterations GPU against oracle, every field at
+    relative 2^-(p-16), with the oracle at p + 64 bits as the arbiter where the conditioning exceeds 2^16. The oracle
+    runs its block fixed-point products here (CLRSDP_REF_GEMM=fixed: exact integer dot products, one rounding per entry -
+    as accurate as its fma loops, test_oracle_pin.py, and 2-3x faster: ~20 s per iteration at this shape)."""
     from test_gpu_solver import compare_iteration
     prec = 512
-    cons, b, _ = instances.synthetic_clustered_sdp(J=2, delta=128, K=256, n_y=1024, prec=prec, seed=20261019)
+    cons, b, _ = instances.synthetic_clustered_sdp(J=3, delta=128, K=256, n_y=512, prec=prec, seed=20261019)
     bi = solver.get_block_info(cons)
-    assert list(bi.dim_S) == [256, 256] and bi.n_y == 1024 and bi.Y_blocksizes[0][0] == 128
-    hg, ho = _pair(cons, b, bi, prec, env={"CLRSDP_REF_GEMM": "fixed"})
+    assert list(bi.dim_S) == [256] * 3 and bi.n_y == 512 and bi.Y_blocksizes[0][0] == 128
+    hg, ho, ht = _pair(cons, b, bi, prec, env={"CLRSDP_REF_GEMM": "fixed"})
     for it in range(2):
-        rg, ro = hg.iterate(), ho.iterate()
-        assert rg.status == 0 and ro.status == 0
-        compare_iteration(hg, ho, bi, prec, prec - 16)
+        rg, ro, rt = hg.iterate(), ho.iterate(), ht.iterate()
+        assert rg.status == 0 and ro.status == 0 and rt.status == 0
+        compare_iteration(hg, ho, bi, prec, prec - 16, ht)
