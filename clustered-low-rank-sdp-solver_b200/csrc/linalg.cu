@@ -4,10 +4,13 @@
 #include "../../include/clrsdp.h"
 #include "comm.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstring>
 
 namespace clr {
+namespace cg = cooperative_groups;
 using mp::Num;
 
 #define DISPATCH_NL(nl, ...)                                  \
@@ -208,35 +211,47 @@ trinv_kernel(mp::Tensor U, const int64_t* __restrict__ offU, int64_t shiftU, mp:
 // Warp 0 runs the chain one step ahead (row k+1, one element per lane: two multiplications and one
 // subtraction per step) while the other warps apply step k to the rows below: ONE __syncthreads per step.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int PANEL_THREADS = 512;
+constexpr int PANEL_THREADS = 544;  // warp 0: pivot row one step ahead; warps 1..15: elimination; warp 16: the row scale tau
+constexpr int PANEL_ELIM = 480;     // threads of warps 1..15
 constexpr int PANEL_W = 32;
 __host__ __device__ inline int pk_u(int w, int r, int c) { return r * w - (r * (r - 1)) / 2 + (c - r); }  // r <= c
 __host__ __device__ inline int pk_g(int r, int j) { return (r * (r + 1)) / 2 + j; }                      // j <= r
 template <int NL>
 __device__ __forceinline__ void panel_elim(uint32_t* Us, uint32_t* Gs, int w, int k, int r, int qp, const Num<NL>& mu,
                                            int ek) {
-  // qp enumerates the active columns of row r: G part q = qp <= k, U part q = qp + (r - k - 1) >= r
-  Num<NL> gam = mp::mul_2exp(smem_get<NL>(Us, pk_u(w, k, r)), -ek);
-  if (qp <= k) {
-    int at = pk_g(r, qp);
-    smem_put<NL>(Gs, at, mp::mul_sub_mul(mu, smem_get<NL>(Gs, at), gam, smem_get<NL>(Gs, pk_g(k, qp))));
-  } else {
-    int q = qp + (r - k - 1), at = pk_u(w, r, q);
-    smem_put<NL>(Us, at, mp::mul_sub_mul(mu, smem_get<NL>(Us, at), gam, smem_get<NL>(Us, pk_u(w, k, q))));
-  }
+  // qp enumerates the active columns of row r: G part q = qp <= k, U part q = qp + (r - k - 1) >= r.
+  // ONE instance of the fused operation for both parts (addresses by selection): the lanes of a warp straddle the two
+  // parts in almost every step, and with a branch per part the warp ran the ~700-instruction a*b - c*d twice.
+  const Num<NL> gam = mp::mul_2exp(smem_get<NL>(Us, pk_u(w, k, r)), -ek);
+  const bool gp = qp <= k;
+  const int q = qp + (r - k - 1);
+  uint32_t* const base = gp ? Gs : Us;
+  const int at = gp ? pk_g(r, qp) : pk_u(w, r, q);
+  const int pt = gp ? pk_g(k, qp) : pk_u(w, k, q);
+  smem_put<NL>(base, at, mp::mul_sub_mul(mu, smem_get<NL>(base, at), gam, smem_get<NL>(base, pt)));
 }
+// CLUSTER version (CL > 1 CTAs per matrix, launched as one thread-block cluster): the elimination is throughput-bound
+// on the integer pipes of ONE SM when a CTA owns the whole panel (w^3/2 fused a*b - c*d operations of ~800 instructions
+// each), and the factorisations with few matrices in the batch (Q: one matrix; the S_j: one per cluster) leave most SMs
+// idle. Rows are owned cyclically (row r by CTA r % CL): a CTA eliminates its own rows in its own shared memory, and the
+// owner of row k+1 - which its warp 0 finishes one step ahead, as before - keeps it in place; after the cluster barrier
+// of the step the other CTAs copy it out of the owner's shared memory through DSMEM. Every CTA therefore ends with all
+// final rows, computes the row scales f_k itself and stores its share of the two outputs.
 template <int NL>
 __global__ void __launch_bounds__(PANEL_THREADS)
 panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shiftA, int ldA, mp::Tensor Lm,
                     const int64_t* __restrict__ offL, int64_t shiftL, int ldL, int w, int write_u,
-                    int* __restrict__ status, int* __restrict__ sig, int sig_ld) {
+                    int* __restrict__ status, int* __restrict__ sig, int sig_ld, int CL, int dbg) {
   extern __shared__ uint32_t sm[];
+  __shared__ long long tdbg[4][36];
   const int ntri = w * (w + 1) / 2;
   uint32_t* Us = sm;                                  // packed upper triangle of the scaled work matrix R'
   uint32_t* Gs = sm + (size_t)ntri * (NL + 2);        // packed lower triangle of G' (diagonal slots: tau)
   uint32_t* Fs = sm + (size_t)2 * ntri * (NL + 2);    // f_k per row
   __shared__ int bad;
-  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = CL > 1 ? (int)cluster.block_rank() : 0;
+  const int b = blockIdx.x / CL, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int64_t oa = offA[b] + shiftA, ol = offL[b] + shiftL;
   if (tid == 0) bad = status[b];
   for (int idx = tid; idx < w * w; idx += nthr) {
@@ -254,7 +269,7 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
   // scale tau just carries its sign. Only a pivot that is exactly zero or below 2^-(p+8) times the scale of its row is
   // replaced (by that bound, sign kept) - a perturbation below the rounding errors already in the matrix.
   constexpr int FLOOR_BITS = 32 * NL + 8;
-  if (tid == 0) {
+  if (tid == 0) {  // (every CTA of a cluster does this on its own copy: same data, same result)
     Num<NL> a = smem_get<NL>(Us, pk_u(w, 0, 0));
     if (sig) {
       if (mp::is_zero(a) || a.e <= -FLOOR_BITS) {
@@ -266,52 +281,91 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
       bad = 1;
     }
   }
-  __syncthreads();
+  if (CL > 1) cluster.sync(); else __syncthreads();   // (cluster: nobody pushes into a CTA that is still loading)
   for (int k = 0; k + 1 < w && !bad; k++) {
     // rows 0..k are final (scaled); apply elimination step k to the rows below
+    if (dbg && lane == 0 && (warp == 0 || warp == 1 || warp == 15)) tdbg[warp == 15 ? 2 : warp][k] = clock64();
     Num<NL> mu = smem_get<NL>(Us, pk_u(w, k, k));
     const int ek = mu.e;
     mu.e = 0;
     if (warp == 0) {
       const int r = k + 1;
-      if (lane < w) panel_elim<NL>(Us, Gs, w, k, r, lane, mu, ek);  // exactly w active columns: one per lane
-      __syncwarp();
-      if (lane == 0) {
-        Num<NL> a = smem_get<NL>(Us, pk_u(w, r, r));
-        if (sig) {  // the unpivoted rows carry the scale tau_{k+1} = mu_k tau_k: threshold by exponents only (no
-                    // multiplication on the pivot chain): |a| < 2^te  <=>  a.e <= te
-          const int te = smem_get<NL>(Gs, pk_g(k, k)).e - FLOOR_BITS;
-          if (mp::is_zero(a) || a.e <= te) {
-            Num<NL> f = mp::from_pow2<NL>(te);
-            f.neg = mp::is_zero(a) ? 0u : a.neg;
-            smem_put<NL>(Us, pk_u(w, r, r), f);
+      if (r % CL == crank) {
+        if (lane < w) panel_elim<NL>(Us, Gs, w, k, r, lane, mu, ek);  // exactly w active columns: one per lane
+        __syncwarp();
+        if (lane == 0) {
+          Num<NL> a = smem_get<NL>(Us, pk_u(w, r, r));
+          if (sig) {  // the unpivoted rows carry the scale tau_{k+1} = mu_k tau_k: threshold by exponents only (no
+                      // multiplication on the pivot chain): |a| < 2^te  <=>  a.e <= te
+            const int te = smem_get<NL>(Gs, pk_g(k, k)).e - FLOOR_BITS;
+            if (mp::is_zero(a) || a.e <= te) {
+              Num<NL> f = mp::from_pow2<NL>(te);
+              f.neg = mp::is_zero(a) ? 0u : a.neg;
+              smem_put<NL>(Us, pk_u(w, r, r), f);
+            }
+          } else if (mp::is_zero(a) || a.neg) {
+            bad = 1;
           }
-        } else if (mp::is_zero(a) || a.neg) {
-          bad = 1;
         }
       }
+    } else if (warp == 16) {
+      // the common diagonal of the unpivoted rows of G': tau_{k+1} = mu_k tau_k (only row k+1's slot is kept). A warp of
+      // its own: on an elimination warp this multiplication (1500 cycles with the call) was added to the longest path
+      // of every step.
+      if (lane == 0) smem_put<NL>(Gs, pk_g(k + 1, k + 1), nmul(mu, smem_get<NL>(Gs, pk_g(k, k))));
     } else {
-      // the common diagonal of the unpivoted rows of G': tau_{k+1} = mu_k tau_k (only row k+1's slot is kept)
-      if (tid == 32) smem_put<NL>(Gs, pk_g(k + 1, k + 1), nmul(mu, smem_get<NL>(Gs, pk_g(k, k))));
-      // rows r = k+2+i, i in [0,R): row i has cnt_i = w-1-i active columns; rows i and R-1-i are paired so that
-      // every pair has the same number of elements
+      // rows r = k+2+i, i in [0,R): row i has cnt_i = w-1-i active columns
       const int R = w - (k + 2);
-      const int C = 2 * (w - 1) - (R - 1);  // cnt_i + cnt_{R-1-i}
-      const int npair = R >> 1;
-      const int total = npair * C + ((R & 1) ? (w - 1 - (R >> 1)) : 0);
-      for (int idx = tid - 32; idx < total; idx += nthr - 32) {
-        int i, qp;
-        if (idx < npair * C) {
-          int pr = idx / C, j = idx % C, c0 = w - 1 - pr;
-          if (j < c0) i = pr, qp = j; else i = R - 1 - pr, qp = j - c0;
-        } else {
-          i = R >> 1, qp = idx - npair * C;
+      if (CL == 1) {
+        // rows i and R-1-i are paired so that every pair has the same number of elements
+        const int C = 2 * (w - 1) - (R - 1);  // cnt_i + cnt_{R-1-i}
+        const int npair = R >> 1;
+        const int total = npair * C + ((R & 1) ? (w - 1 - (R >> 1)) : 0);
+        for (int idx = tid - 32; idx < total; idx += PANEL_ELIM) {
+          int i, qp;
+          if (idx < npair * C) {
+            int pr = idx / C, j = idx % C, c0 = w - 1 - pr;
+            if (j < c0) i = pr, qp = j; else i = R - 1 - pr, qp = j - c0;
+          } else {
+            i = R >> 1, qp = idx - npair * C;
+          }
+          panel_elim<NL>(Us, Gs, w, k, k + 2 + i, qp, mu, ek);
         }
-        panel_elim<NL>(Us, Gs, w, k, k + 2 + i, qp, mu, ek);
+      } else {
+        // own rows only: i = i0 + j CL; w - 1 slots per row (at most one round of the 480 threads for CL >= 2, w = 32)
+        const int i0 = ((crank - (k + 2)) % CL + CL) % CL;
+        const int Rm = R > i0 ? (R - i0 + CL - 1) / CL : 0;
+        for (int idx = tid - 32; idx < Rm * (w - 1); idx += PANEL_ELIM) {
+          const int j = idx / (w - 1), qp = idx % (w - 1), i = i0 + j * CL;
+          if (qp < w - 1 - i) panel_elim<NL>(Us, Gs, w, k, k + 2 + i, qp, mu, ek);
+        }
+      }
+    }
+    if (dbg && lane == 0 && warp == 1) tdbg[3][k] = clock64();
+    if (CL > 1) {
+      // every CTA but the owner PULLS the finished row k+1 (G part: columns 0..k, U part: columns k+1..w-1; the diagonal
+      // slot of G - tau - is computed by every CTA itself) and the failure flag out of the owner's shared memory: one
+      // 8-byte DSMEM load per thread (a push by the owner's warp 0 - 72 remote stores per lane to 7 destinations on the
+      // pivot chain - measured 3.6 us per step). The owner never touches the row again, so no second cluster barrier.
+      cluster.sync();
+      const int r = k + 1, owner = r % CL;
+      if (crank != owner) {
+        const int g0 = pk_g(r, 0) * (NL + 2), gw = (k + 1) * (NL + 2);
+        const int u0 = pk_u(w, r, r) * (NL + 2), uw = (w - r) * (NL + 2);
+        const uint32_t* rG = cluster.map_shared_rank(Gs, owner);
+        const uint32_t* rU = cluster.map_shared_rank(Us, owner);
+        // (NL + 2 is even and every number starts at a multiple of NL + 2 words: 8-byte alignment)
+        for (int i = 2 * tid; i < gw; i += 2 * nthr)
+          *reinterpret_cast<uint2*>(Gs + g0 + i) = *reinterpret_cast<const uint2*>(rG + g0 + i);
+        for (int i = 2 * tid; i < uw; i += 2 * nthr)
+          *reinterpret_cast<uint2*>(Us + u0 + i) = *reinterpret_cast<const uint2*>(rU + u0 + i);
+        if (tid == nthr - 1 && *cluster.map_shared_rank(&bad, owner)) bad = 1;
       }
     }
     __syncthreads();
   }
+  if (dbg && tid == 0) tdbg[0][w - 1] = clock64();
+  if (CL > 1) cluster.sync();  // nobody leaves while its rows may still be read
   // f_k = rsqrt(|tau_k d'_k|), one row per lane. Signed mode: the true pivot d_k = d'_k / tau_k has the sign
   // sigma_k = sign(tau_k d'_k); row k of L^-1 (L = U^T) is G'_k * sign(tau_k) f_k, row k of U is R'_k * sign(d'_k) f_k.
   __shared__ uint32_t sgn_tau[PANEL_W], sgn_d[PANEL_W];
@@ -321,7 +375,7 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
     sgn_d[lane] = sig ? dk.neg : 0u;
     Num<NL> prod = nmul(tau, dk);
     if (sig) {
-      sig[(int64_t)b * sig_ld + lane] = (int)prod.neg;
+      if (crank == 0) sig[(int64_t)b * sig_ld + lane] = (int)prod.neg;
       prod.neg = 0u;
     }
     Num<NL> f, root = nsqrt_rsqrt(prod, f);
@@ -330,7 +384,7 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
   }
   __syncthreads();
   if (!bad) {
-    for (int idx = tid; idx < w * w; idx += nthr) {
+    for (int idx = tid + crank * nthr; idx < w * w; idx += nthr * CL) {
       int r = idx / w, c = idx % w;
       Num<NL> f = smem_get<NL>(Fs, r);
       if (write_u) {
@@ -343,12 +397,32 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
       stm<NL>(Lm, ol + (int64_t)r * ldL + c, g);
     }
   }
-  if (tid == 0) status[b] = bad;
+  if (tid == 0 && crank == 0) status[b] = bad;
+  if (dbg && blockIdx.x == 0 && tid == 0) {
+    long long tend = clock64();
+    printf("panel dbg (w=%d CL=%d): step: warp0 start->next | warp1 work | warp15 start\n", w, CL);
+    for (int k = 0; k + 1 < w; k++)
+      printf("  k=%2d  step %6lld  w1 busy %6lld  w15 lag %6lld\n", k, tdbg[0][k + 1] - tdbg[0][k], tdbg[3][k] - tdbg[1][k],
+             tdbg[2][k] - tdbg[0][k]);
+    printf("  tail %lld\n", tend - tdbg[0][w - 1]);
+  }
 }
 int panel_width(int nl) { (void)nl; return PANEL_W; }
+static int panel_cluster_env() {
+  static int v = -2;
+  if (v == -2) v = getenv("CLRSDP_PANEL_CLUSTER") ? atoi(getenv("CLRSDP_PANEL_CLUSTER")) : -1;  // measuring aid: force CL
+  return v;
+}
 void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status, int* d_sig,
                   int sig_ld) {
   if (A.n > panel_width(nl)) throw SolverError(-1, "panel_factor: block larger than the panel width");
+  // CTAs per matrix: as many as keep the grid within the SMs (a power of two up to the portable cluster size 8)
+  int CL = 1;
+  if (panel_cluster_env() == 0)
+    while (CL < 8 && (int64_t)A.batch * CL * 2 <= ctx.sm_count) CL *= 2;
+  if (A.n < 8) CL = 1;
+  if (panel_cluster_env() > 0) CL = panel_cluster_env();
+  static int panel_dbg = getenv("CLRSDP_PANEL_DEBUG") ? atoi(getenv("CLRSDP_PANEL_DEBUG")) : 0;
   DISPATCH_NL(nl, {
     size_t words = ((size_t)A.n * (A.n + 1) + A.n) * (NL + 2);
     static bool attr[17] = {false};
@@ -358,9 +432,15 @@ void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, boo
     }
     std::string nm = "panel_factor_n" + std::to_string(A.n);
     int tk = ctx.begin(nm.c_str());
-    panel_factor_kernel<NL><<<A.batch, PANEL_THREADS, words * sizeof(uint32_t), ctx.stream>>>(
-        A.t, A.d_off, A.shift, A.stride(), Linv.t, Linv.d_off, Linv.shift, Linv.stride(), A.n, write_u ? 1 : 0,
-        d_status, d_sig, sig_ld);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(A.batch * CL)), cfg.blockDim = dim3(PANEL_THREADS);
+    cfg.dynamicSmemBytes = words * sizeof(uint32_t), cfg.stream = ctx.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)CL, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    CLR_CUDA(cudaLaunchKernelEx(&cfg, panel_factor_kernel<NL>, A.t, A.d_off, A.shift, A.stride(), Linv.t, Linv.d_off,
+                                Linv.shift, Linv.stride(), A.n, write_u ? 1 : 0, d_status, d_sig, sig_ld, CL, panel_dbg));
     ctx.end(tk);
   });
 }
@@ -1541,12 +1621,49 @@ struct GemvDev {
   const int* row0;
   const int* itemK;
   int item_trans;
+  int lpr;  // lanes per row of the row-major kernel (a power of two <= 32)
+  // fused header-word operations (see GemvArgs)
+  const int* x_flip;
+  const int* x_scale;
+  int x_scale_sign;
+  const int* o_flip;
+  const int* o_scale;
+  int o_scale_sign;
+  mp::Tensor e;
+  int64_t e0;
+  int e_mode;
 };
 template <int NL>
+__device__ __forceinline__ Num<NL> gemv_x(const GemvDev& g, int64_t at) {
+  Num<NL> v = ldm<NL>(g.x, at);
+  if (!mp::is_zero(v)) {
+    if (g.x_scale) v.e += g.x_scale_sign * g.x_scale[at - g.x0];
+    if (g.x_flip) v.neg ^= (uint32_t)(g.x_flip[at - g.x0] & 1);
+  }
+  return v;
+}
+// result of row r: sign flip, power-of-two scale, combination with e (in this order), store
+template <int NL>
+__device__ __forceinline__ void gemv_finish(const GemvDev& g, int r, Num<NL> acc) {
+  if (!mp::is_zero(acc)) {
+    if (g.o_flip) acc.neg ^= (uint32_t)(g.o_flip[r] & 1);
+    if (g.o_scale) acc.e += g.o_scale_sign * g.o_scale[r];
+  }
+  if (g.e_mode == 1)
+    acc = mp::add(ldm<NL>(g.e, g.e0 + r), acc);
+  else if (g.e_mode == 2)
+    acc = mp::sub(ldm<NL>(g.e, g.e0 + r), acc);
+  stm<NL>(g.out, g.oo + r, acc);
+}
+template <int NL>
 __global__ void gemv_kernel(GemvDev g) {
-  int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (warp >= g.rows * g.nparts) return;
-  int r = warp / g.nparts, part = warp % g.nparts;
+  // a group of `lpr` adjacent lanes per (row, K-part): short rows (the K = dim_S items) would otherwise spend as much on the
+  // shuffle reduction (5 multiprecision additions) as on their 4 multiply-adds per lane
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lpr = g.lpr, sub = (int)(gt % lpr);
+  const int64_t grp = gt / lpr;
+  const bool live = grp < (int64_t)g.rows * g.nparts;
+  int r = live ? (int)(grp / g.nparts) : 0, part = live ? (int)(grp % g.nparts) : 0;
   int64_t ab = g.a0, xb = g.x0;
   int rl = r, K = g.K;
   int64_t rs = g.rs, ks = g.ks;
@@ -1560,15 +1677,15 @@ __global__ void gemv_kernel(GemvDev g) {
     ks = g.item_trans ? K : 1;
   }
   int chunk = (K + g.nparts - 1) / g.nparts;
-  int k0 = part * chunk, k1 = min(K, k0 + chunk);
+  int k0 = part * chunk, k1 = live ? min(K, k0 + chunk) : 0;
   Num<NL> acc = mp::zero<NL>();
-  for (int k = k0 + lane; k < k1; k += 32)
-    acc = mp::add(acc, mp::mul(ldm<NL>(g.A, ab + (int64_t)rl * rs + (int64_t)k * ks), ldm<NL>(g.x, xb + k)));
+  for (int k = k0 + sub; k < k1; k += lpr)
+    acc = mp::add(acc, mp::mul(ldm<NL>(g.A, ab + (int64_t)rl * rs + (int64_t)k * ks), gemv_x<NL>(g, xb + k)));
 #pragma unroll 1
-  for (int o = 16; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
-  if (lane == 0) {
+  for (int o = lpr >> 1; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
+  if (live && sub == 0) {
     if (g.nparts == 1)
-      stm<NL>(g.out, g.oo + r, acc);
+      gemv_finish<NL>(g, r, acc);
     else
       stm<NL>(g.work, (int64_t)part * g.rows + r, acc);
   }
@@ -1598,9 +1715,9 @@ __global__ void gemv_t_kernel(GemvDev g) {
   const int chunk = (K + g.nparts - 1) / g.nparts;
   const int k0 = part * chunk, k1 = min(K, k0 + chunk);
   Num<NL> acc = mp::zero<NL>();
-  for (int k = k0; k < k1; k++) acc = mp::add(acc, mp::mul(ldm<NL>(g.A, ab + (int64_t)k * ld + rl), ldm<NL>(g.x, xb + k)));
+  for (int k = k0; k < k1; k++) acc = mp::add(acc, mp::mul(ldm<NL>(g.A, ab + (int64_t)k * ld + rl), gemv_x<NL>(g, xb + k)));
   if (g.nparts == 1)
-    stm<NL>(g.out, g.oo + r, acc);
+    gemv_finish<NL>(g, r, acc);
   else
     stm<NL>(g.work, (int64_t)part * g.rows + r, acc);
 }
@@ -1613,14 +1730,14 @@ __global__ void gemv_sum_kernel(GemvDev g) {
     for (int p = lane; p < g.nparts; p += 32) acc = nadd(acc, ldm<NL>(g.work, (int64_t)p * g.rows + r));
 #pragma unroll 1
     for (int o = 16; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
-    if (lane == 0) stm<NL>(g.out, g.oo + r, acc);
+    if (lane == 0) gemv_finish<NL>(g, r, acc);
     return;
   }
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= g.rows) return;
   Num<NL> acc = mp::zero<NL>();
   for (int p = 0; p < g.nparts; p++) acc = nadd(acc, ldm<NL>(g.work, (int64_t)p * g.rows + r));
-  stm<NL>(g.out, g.oo + r, acc);
+  gemv_finish<NL>(g, r, acc);
 }
 static int gemv_parts(int rows, int K) {
   if ((int64_t)rows >= 148 * 8 || K <= 256) return 1;
@@ -1635,19 +1752,26 @@ size_t gemv_work_elems(int rows, int K) { return (size_t)rows * std::max(gemv_pa
 void gemv(Ctx& ctx, int nl, const GemvArgs& a, mp::Tensor work) {
   if (a.rows <= 0) return;
   GemvDev g{a.A, a.x, a.out, work, a.a0, a.x0, a.oo, a.rs, a.ks, a.rows, a.K, 1, a.d_row_item, a.d_aoff, a.d_xoff,
-            a.d_row0, a.d_K, a.item_trans};
+            a.d_row0, a.d_K, a.item_trans, 32, a.x_flip, a.x_scale, a.x_scale_sign, a.o_flip, a.o_scale, a.o_scale_sign,
+            a.e, a.e0, a.e_mode};
   const bool transposed = a.d_row_item ? a.item_trans != 0 : (a.rs == 1 && a.ks != 1);
   // (items: every item is K_item x K_item here, so a.rows / number of items bounds K; the work buffer is sized by the caller
   // with gemv_work_elems(rows, rows))
   g.nparts = transposed ? gemv_parts_t(a.rows, a.d_row_item ? std::max(1, a.K_hint) : a.K) : (a.d_row_item ? 1 : gemv_parts(a.rows, a.K));
+  {  // at least ~16 terms per lane
+    const int kk = (a.d_row_item ? std::max(1, a.K_hint) : a.K) / g.nparts;
+    static int lpr_env = getenv("CLRSDP_GEMV_LPR") ? atoi(getenv("CLRSDP_GEMV_LPR")) : 0;  // measuring aid
+    while (g.lpr > 4 && kk < 16 * g.lpr) g.lpr >>= 1;
+    if (lpr_env) g.lpr = lpr_env;
+  }
   DISPATCH_NL(nl, {
     int tk = ctx.begin(transposed ? "gemv_t" : "gemv", (double)a.rows * a.K * 4.0 * (NL + 1));
     if (transposed) {
       int64_t warps = (int64_t)((a.rows + 31) / 32) * g.nparts;
       gemv_t_kernel<NL><<<ceil_div(warps * 32, 128), 128, 0, ctx.stream>>>(g);
     } else {
-      int64_t warps = (int64_t)a.rows * g.nparts;
-      gemv_kernel<NL><<<ceil_div(warps * 32, 128), 128, 0, ctx.stream>>>(g);
+      int64_t thr = (int64_t)a.rows * g.nparts * g.lpr;
+      gemv_kernel<NL><<<ceil_div(thr, 128), 128, 0, ctx.stream>>>(g);
     }
     ctx.end(tk);
     if (g.nparts > 1) {

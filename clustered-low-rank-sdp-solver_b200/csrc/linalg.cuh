@@ -108,6 +108,19 @@ struct GemvArgs {
   const int* d_K = nullptr;
   int item_trans = 0;  // with items: 0 -> A_item[r][k], 1 -> A_item[k][r]; leading dimension = K_item
   int K_hint = 0;      // with items: the largest K_item (sizes the K-split of the transposed kernel)
+  // Header-word operations fused into the product (they replace separate vec_flip / vec_scale / lincomb launches on the
+  // latency chain of the Schur solve). x side, indexed like x from x0: x_k <- (-1)^x_flip[k] 2^(x_scale_sign x_scale[k]) x_k.
+  // Result side, indexed by row, applied in this order: sign flip, power-of-two scale, then e_mode 1: out = e + acc,
+  // e_mode 2: out = e - acc (e may alias out).
+  const int* x_flip = nullptr;
+  const int* x_scale = nullptr;
+  int x_scale_sign = 0;
+  const int* o_flip = nullptr;
+  const int* o_scale = nullptr;
+  int o_scale_sign = 0;
+  mp::Tensor e;
+  int64_t e0 = 0;
+  int e_mode = 0;
 };
 void gemv(Ctx& ctx, int nl, const GemvArgs& g, mp::Tensor work);
 size_t gemv_work_elems(int rows, int K);

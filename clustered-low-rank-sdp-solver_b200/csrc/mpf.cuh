@@ -216,6 +216,50 @@ MP_HD uint32_t inc_n(uint32_t (&x)[N], uint32_t c) {
   return c;
 #endif
 }
+// x += y + cin (cin = 0 or 1), returns carry out
+template <int N>
+MP_HD uint32_t addc_n(uint32_t (&x)[N], const uint32_t (&y)[N], uint32_t cin) {
+#if defined(__CUDA_ARCH__)
+  uint32_t t;
+  asm volatile("add.cc.u32 %0, %1, 0xffffffff;" : "=r"(t) : "r"(cin));  // carry flag = cin
+#pragma unroll
+  for (int i = 0; i < N; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+  uint32_t c;
+  asm volatile("addc.u32 %0, 0, 0;" : "=r"(c));
+  return c;
+#else
+  uint32_t c = cin;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint64_t s = (uint64_t)x[i] + y[i] + c;
+    x[i] = (uint32_t)s;
+    c = (uint32_t)(s >> 32);
+  }
+  return c;
+#endif
+}
+// The signed combination X <- | X +- Y | of two aligned magnitudes WITHOUT data-dependent branches (sub = 0: X + Y,
+// sub = 1: X - Y). Returns through `flip` whether the result changed sign (|Y| > |X|) and through `ovf` whether the
+// sum carried out of the top limb (the result has then been shifted right by one bit with the carry on top).
+// On the GPU the lanes of a warp hold unrelated numbers: an if (same sign) add else subtract executes both sides for
+// every warp, and the elimination / product kernels that live on these operations are instruction-bound.
+template <int N>
+MP_HD void combine_n(uint32_t (&X)[N], uint32_t (&Y)[N], uint32_t sub, uint32_t& flip, uint32_t& ovf) {
+  const uint32_t m = 0u - sub;  // all ones when subtracting
+#pragma unroll
+  for (int i = 0; i < N; i++) Y[i] ^= m;
+  const uint32_t c = addc_n<N>(X, Y, sub);  // X + Y, or X + ~Y + 1 = X - Y (carry = no borrow)
+  flip = sub & (c ^ 1u);
+  ovf = (sub ^ 1u) & c;
+  const uint32_t nm = 0u - flip;            // negative difference: two's complement
+#pragma unroll
+  for (int i = 0; i < N; i++) X[i] ^= nm;
+  inc_n<N>(X, flip);
+  // carry out of a sum: one bit to the right, the carry becomes the top bit (shift count 0 or 1)
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) X[i] = funnel_r(X[i], X[i + 1], ovf);
+  X[N - 1] = (X[N - 1] >> ovf) | (ovf << 31);
+}
 // compare magnitudes of two N-limb arrays: -1, 0, 1
 template <int N>
 MP_HD int cmp_n(const uint32_t (&x)[N], const uint32_t (&y)[N]) {
@@ -264,48 +308,33 @@ MP_HD void round_guard(Num<NL>& out, const uint32_t (&x)[NL + 1], int32_t e, uin
 // ---------------------------------------------------------------------------------------------------
 template <int NL>
 MP_HD Num<NL> add(const Num<NL>& a, const Num<NL>& b) {
-  if (is_zero(a)) return b;
-  if (is_zero(b)) return a;
-  bool sw = b.e > a.e;
+  // One path for all operands (see combine_n). A zero carries the smallest exponent (EXP_ZERO), so it becomes the
+  // operand Y that is shifted out entirely, and x + 0 = x comes out exactly (guard limb 0: nothing to round).
+  const bool sw = b.e > a.e;
   uint32_t X[NL + 1], Y[NL + 1];
   X[0] = 0;
   Y[0] = 0;
+  const uint32_t ka = is_zero(a) ? 0u : 0xffffffffu, kb = is_zero(b) ? 0u : 0xffffffffu;  // (a zero has no mantissa)
 #pragma unroll
   for (int i = 0; i < NL; i++) {
-    X[i + 1] = sw ? b.m[i] : a.m[i];
-    Y[i + 1] = sw ? a.m[i] : b.m[i];
+    X[i + 1] = sw ? (b.m[i] & kb) : (a.m[i] & ka);
+    Y[i + 1] = sw ? (a.m[i] & ka) : (b.m[i] & kb);
   }
-  int32_t ex = sw ? b.e : a.e, ey = sw ? a.e : b.e;
-  uint32_t nx = sw ? b.neg : a.neg, ny = sw ? a.neg : b.neg;
-  uint32_t d = (uint32_t)(ex - ey);
-  Num<NL> out;
-  if (d > 32u * NL + 31u) {  // y is below the guard limb
-#pragma unroll
-    for (int i = 0; i < NL; i++) out.m[i] = X[i + 1];
-    out.e = ex;
-    out.neg = nx;
-    return out;
-  }
-  if (d >> 5) shr_limbs<NL + 1>(Y, d >> 5);
-  if (d & 31u) shr_bits<NL + 1>(Y, d & 31u);
-  if (nx == ny) {
-    uint32_t c = add_n<NL + 1>(X, Y);
-    if (c) {
-      shr_bits<NL + 1>(X, 1);
-      X[NL] |= 0x80000000u;
-      ex += 1;
-    }
-    round_guard<NL>(out, X, ex, nx);
-    return out;
-  }
-  // opposite signs: X - Y; a borrow (only possible when the exponents are equal) means |Y| > |X|: negate, flip the sign
-  if (sub_n<NL + 1>(X, Y)) {
-    neg_n<NL + 1>(X);
-    nx = ny;
-  }
-  int sh = normalize_n<NL + 1>(X);
+  int32_t ex = sw ? b.e : a.e;
+  const int32_t ey = sw ? a.e : b.e;
+  uint32_t nx = sw ? b.neg : a.neg;
+  const uint32_t ny = sw ? a.neg : b.neg;
+  const uint32_t d = (uint32_t)(ex - ey);
+  const uint32_t q = d >> 5;
+  shr_limbs<NL + 1>(Y, q > (uint32_t)(NL + 1) ? (uint32_t)(NL + 1) : q);  // y below the guard limb: Y = 0
+  shr_bits<NL + 1>(Y, d & 31u);
+  uint32_t flip, ovf;
+  combine_n<NL + 1>(X, Y, (nx ^ ny) & 1u, flip, ovf);
+  nx = flip ? ny : nx;
+  const int sh = normalize_n<NL + 1>(X);
   if (sh < 0) return zero<NL>();
-  round_guard<NL>(out, X, ex - sh, nx);
+  Num<NL> out;
+  round_guard<NL>(out, X, ex + (int32_t)ovf - sh, nx);
   return out;
 }
 template <int NL>
@@ -386,47 +415,41 @@ MP_HD Num<NL> mul(const Num<NL>& a, const Num<NL>& b) {
 // The building block of the elimination steps and three-term recurrences on the latency-bound paths.
 template <int NL>
 MP_HD Num<NL> mul_sub_mul(const Num<NL>& a, const Num<NL>& b, const Num<NL>& c, const Num<NL>& d) {
+  // One path for all operands (see combine_n): a product with a zero factor gets a zero mantissa and an exponent below
+  // everything, so it is the operand that is shifted out, and the other product is normalised and rounded exactly as
+  // mul() would (the rows of the elimination are full of zeros and of either sign: with branches a warp ran the
+  // two-product, the one-product, the adding and the subtracting variants one after the other).
   const bool z1 = is_zero(a) || is_zero(b), z2 = is_zero(c) || is_zero(d);
-  if (z2) return z1 ? zero<NL>() : mul(a, b);
-  if (z1) return neg(mul(c, d));
-  uint32_t X[NL + 2], Y[NL + 2];
-  int32_t ex = a.e + b.e, ey = c.e + d.e;
-  uint32_t nx = a.neg ^ b.neg, ny = (c.neg ^ d.neg) ^ 1u;
-  mul_raw<NL>(a, b, X);
-  mul_raw<NL>(c, d, Y);
-  if (ey > ex) {  // X takes the product with the larger exponent
+  uint32_t P1[NL + 2], P2[NL + 2], X[NL + 2], Y[NL + 2];
+  mul_raw<NL>(a, b, P1);
+  mul_raw<NL>(c, d, P2);
+  constexpr int32_t E_NONE = -(1 << 30);
+  const int32_t e1 = z1 ? E_NONE : a.e + b.e, e2 = z2 ? E_NONE : c.e + d.e;
+  const uint32_t n1 = (a.neg ^ b.neg) & 1u, n2 = ((c.neg ^ d.neg) ^ 1u) & 1u;
+  const bool sw = e2 > e1;  // X takes the product with the larger exponent
+  const uint32_t k1 = z1 ? 0u : 0xffffffffu, k2 = z2 ? 0u : 0xffffffffu;
 #pragma unroll
-    for (int i = 0; i < NL + 2; i++) {
-      uint32_t t = X[i];
-      X[i] = Y[i];
-      Y[i] = t;
-    }
-    int32_t te = ex; ex = ey; ey = te;
-    uint32_t tn = nx; nx = ny; ny = tn;
+  for (int i = 0; i < NL + 2; i++) {
+    X[i] = sw ? (P2[i] & k2) : (P1[i] & k1);
+    Y[i] = sw ? (P1[i] & k1) : (P2[i] & k2);
   }
-  uint32_t dd = (uint32_t)(ex - ey);
-  if (dd < 32u * (NL + 2)) {
-    if (dd >> 5) shr_limbs<NL + 2>(Y, dd >> 5);
-    if (dd & 31u) shr_bits<NL + 2>(Y, dd & 31u);
-    if (nx == ny) {
-      uint32_t cy = add_n<NL + 2>(X, Y);
-      if (cy) {
-        shr_bits<NL + 2>(X, 1);
-        X[NL + 1] |= 0x80000000u;
-        ex += 1;
-      }
-    } else if (sub_n<NL + 2>(X, Y)) {  // |Y| > |X| (possible when the exponents are equal or X is not normalised)
-      neg_n<NL + 2>(X);
-      nx = ny;
-    }
-  }
-  int sh = normalize_n<NL + 2>(X);
+  const int32_t ex = sw ? e2 : e1, ey = sw ? e1 : e2;
+  uint32_t nx = sw ? n2 : n1;
+  const uint32_t ny = sw ? n1 : n2;
+  const uint32_t dd = (uint32_t)(ex - ey);
+  const uint32_t q = dd >> 5;
+  shr_limbs<NL + 2>(Y, q > (uint32_t)(NL + 2) ? (uint32_t)(NL + 2) : q);
+  shr_bits<NL + 2>(Y, dd & 31u);
+  uint32_t flip, ovf;
+  combine_n<NL + 2>(X, Y, nx ^ ny, flip, ovf);
+  nx = flip ? ny : nx;
+  const int sh = normalize_n<NL + 2>(X);
   if (sh < 0) return zero<NL>();
   uint32_t G[NL + 1];
 #pragma unroll
   for (int i = 0; i <= NL; i++) G[i] = X[i + 1];
   Num<NL> out;
-  round_guard<NL>(out, G, ex - sh, nx);
+  round_guard<NL>(out, G, ex + (int32_t)ovf - sh, nx);
   return out;
 }
 

@@ -50,7 +50,15 @@ Solver::Solver(int prec_bits, int device) : nl(prec_bits / 32), prec(prec_bits) 
     CLR_CUDA(cudaEventCreateWithFlags(&h.ev_go, cudaEventDisableTiming));
     CLR_CUDA(cudaEventCreateWithFlags(&h.ev_done, cudaEventDisableTiming));
   }
+  for (auto& h : trailh_) {  // the remainder updates of the lookahead factorisation (see chol_inverse)
+    h.gemm.reset(new GemmEngine(ctx, nl));
+    CLR_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+    CLR_CUDA(cudaEventCreateWithFlags(&h.ev_go, cudaEventDisableTiming));
+    CLR_CUDA(cudaEventCreateWithFlags(&h.ev_done, cudaEventDisableTiming));
+  }
   if (const char* g = getenv("CLRSDP_INVH")) use_invh_ = atoi(g) != 0;
+  if (const char* g = getenv("CLRSDP_LOOKAHEAD")) use_lookahead_ = atoi(g) != 0;
+  if (const char* g = getenv("CLRSDP_LOOKAHEAD_RATIO")) lookahead_ratio_ = atof(g);
   scal.alloc(SL_COUNT, nl);
   work.alloc(4096, nl);
   d_flags.ensure(4 * sizeof(int));
@@ -77,11 +85,13 @@ Solver::~Solver() {
   if (side_stream_) cudaStreamDestroy(side_stream_);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_join_) cudaEventDestroy(ev_join_);
-  for (auto& h : invh_) {
-    if (h.stream) cudaStreamDestroy(h.stream);
-    if (h.ev_go) cudaEventDestroy(h.ev_go);
-    if (h.ev_done) cudaEventDestroy(h.ev_done);
-  }
+  for (auto* hs : {invh_, trailh_})
+    for (int i = 0; i < 2; i++) {
+      auto& h = hs[i];
+      if (h.stream) cudaStreamDestroy(h.stream);
+      if (h.ev_go) cudaEventDestroy(h.ev_go);
+      if (h.ev_done) cudaEventDestroy(h.ev_done);
+    }
 }
 
 // ---- multi-GPU ------------------------------------------------------------------------------------------
@@ -759,6 +769,20 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
     product(ge2, s1, s2, op_rows(Linv, k0, k0, wk, wk), tb, wk, k0, out_sub(Linv, k0, 0), EPI_NEG, nullptr);
   };
   bool forked = false;
+  // LOOKAHEAD. The pivot chain panel_factor(k0) -> U12 -> trailing update -> panel_factor(k0 + w) is the critical path of
+  // the factorisation, but the next panel only needs the next ROW BLOCK of the trailing matrix. When the trailing matrix
+  // is large compared with that row block, the update is split: the row block A[k1:k1+w1, k1:n] is updated on this
+  // stream, the remainder A[k1+w1:n, k1+w1:n] on a helper stream (own GEMM workspace) beside the next panel. Every
+  // (panel, row block) contribution is still applied exactly once; a row block is touched by the remainder updates of
+  // the earlier panels (helper stream, in order) before the row-block update of its predecessor (this stream, which
+  // waits for the helper), so the order of the subtractions per entry is fixed: results do not depend on timing.
+  InvHelper& TH = trailh_[side ? 1 : 0];
+  bool trail_pending = false, trail_used = false;
+  auto wait_trail = [&]() {
+    if (!trail_pending) return;
+    CLR_CUDA(cudaStreamWaitEvent(ctx.stream, TH.ev_done, 0));
+    trail_pending = false;
+  };
   for (int k0 = 0; k0 < n; k0 += PANEL) {
     const int wk = std::min(PANEL, n - k0), n2 = n - k0 - wk;
     panel_factor(ctx, nl, Uw.sub(k0, k0, wk), Linv.sub(k0, k0, wk), want_u, d_stat, d_sig ? d_sig + k0 : nullptr, n);
@@ -791,15 +815,39 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
       }
       // A22 -= U12^T U12   (signed: Y12^T Sigma1 Y12)
       mp::Tensor ut = Uw.t;
-      OperandDesc u12 = op_cols(Uw, k0, k0 + wk, n2, wk);
-      if (d_sig) {
-        OperandDesc u12s = u12;
-        u12s.d_ksign = d_sig + k0, u12s.ksign_ld = n;
-        product(gemm_loc, fs2_, fs1_, u12, u12s, n2, n2, out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
+      const int k1 = k0 + wk, w1 = std::min(PANEL, n2), nr = n2 - w1;
+      auto update = [&](GemmEngine* ge2, Slice& s1, Slice& s2, int c0, int M, int c1, int N) {
+        // A[c0:c0+M, c1:c1+N] -= U12[:, c0..]^T Sigma U12[:, c1..]
+        OperandDesc ua = op_cols(Uw, k0, c0, M, wk), ub = op_cols(Uw, k0, c1, N, wk);
+        if (d_sig) {
+          ub.d_ksign = d_sig + k0, ub.ksign_ld = n;
+          product(ge2, s2, s1, ua, ub, M, N, out_sub(Uw, c0, c1), EPI_SUB_FROM, &ut);
+        } else if (c0 == c1 && M == N) {
+          product(ge2, s2, s2, ua, ua, M, N, out_sub(Uw, c0, c1), EPI_SUB_FROM, &ut);
+        } else {
+          product(ge2, s2, s1, ua, ub, M, N, out_sub(Uw, c0, c1), EPI_SUB_FROM, &ut);
+        }
+      };
+      wait_trail();  // the remainder updates of the earlier panels have reached the rows written below
+      const bool ahead = use_lookahead_ && nr > 0 && (double)nr * nr >= lookahead_ratio_ * (double)w1 * n2;
+      if (!ahead) {
+        update(gemm_loc, fs1_, fs2_, k1, n2, k1, n2);
       } else {
-        product(gemm_loc, fs2_, fs2_, u12, u12, n2, n2, out_sub(Uw, k0 + wk, k0 + wk), EPI_SUB_FROM, &ut);
+        cudaStream_t cur = ctx.stream;
+        CLR_CUDA(cudaEventRecord(TH.ev_go, cur));  // U12 is complete
+        CLR_CUDA(cudaStreamWaitEvent(TH.stream, TH.ev_go, 0));
+        ctx.stream = TH.stream;
+        update(TH.gemm.get(), TH.s1, TH.s2, k1 + w1, nr, k1 + w1, nr);
+        CLR_CUDA(cudaEventRecord(TH.ev_done, TH.stream));
+        ctx.stream = cur;
+        trail_pending = trail_used = true;
+        update(gemm_loc, fs1_, fs2_, k1, w1, k1, n2);  // the next panel's row block
       }
     }
+  }
+  if (trail_used) {  // join (also when the last remainder has been waited for: the capture needs the stream back)
+    CLR_CUDA(cudaEventRecord(TH.ev_done, TH.stream));
+    CLR_CUDA(cudaStreamWaitEvent(ctx.stream, TH.ev_done, 0));
   }
   if (forked) {
     CLR_CUDA(cudaEventRecord(H.ev_done, H.stream));
@@ -1057,8 +1105,12 @@ void Solver::search_direction() {
   mark(CLRSDP_T_SYS);
   {
     // S_j^-1 = D^-1 L'^-T Sigma L'^-1 D^-1:  t_j = Sigma L'_j^-1 (D_j^-1 rhs_j)
-    ew_lincomb(ctx, nl, rhs0.t(), 0, rhs.t(), 0, 1, rhs.t(), 0, 0, sumS);  // rhs_x itself, for the refinement below
-    vec_scale(ctx, nl, rhs.t(), 0, sumS, -1, xscale.as<int>());
+    // The diagonal factors (Sigma: sign flips, D^-1: exponent shifts) and the vector additions of this chain are header-
+    // word operations fused into the products (GemvArgs x_flip / x_scale / o_flip / o_scale / e): every launch on this
+    // path is latency, and there were 28 of them per direction beside the 15 products.
+    const int* xs = xscale.as<int>();
+    const int* xg = xsign.as<int>();
+    const int* qg = qsign.as<int>();
     GemvArgs a;
     a.A = Linvs.t(), a.x = rhs.t(), a.out = tvec.t();
     a.rows = sumS, a.K = 0;
@@ -1066,8 +1118,10 @@ void Solver::search_direction() {
     a.d_row0 = d_row0.as<int>(), a.d_K = d_itemK.as<int>();
     a.item_trans = 0;  // A_item[r][k], leading dimension = K_item
     for (auto& cg : cgroups_) a.K_hint = std::max(a.K_hint, cg.dimS);
+    GemvArgs a0 = a;   // (the plain per-cluster product, without fused operations)
+    a.x_scale = xs, a.x_scale_sign = -1;  // D^-1 rhs
+    a.o_flip = xg;                        // t <- Sigma t
     gemv(ctx, nl, a, work.t());
-    vec_flip(ctx, nl, tvec.t(), 0, sumS, xsign.as<int>());  // t <- Sigma t
     // tmpy = sum_j W_j^T Sigma_j t_j = Wt t
     GemvArgs w;
     w.A = Wt.t(), w.x = tvec.t(), w.out = tmpy.t();
@@ -1075,14 +1129,15 @@ void Solver::search_direction() {
     gemv(ctx, nl, w, work.t());
     allreduce(tmpy, 0, n_y, COMB_SUM);  // sum(temp_y), :1761
     ew_lincomb(ctx, nl, dyr.t(), 0, p.t(), 0, 1, tmpy.t(), 0, -1, n_y);  // p - sum_j B^T U^-1 t_j (:1761)
-    // dy = Q^-1 dyr = Lq^-T (Lq^-1 dyr)
+    // dy = Q^-1 dyr = Lq^-T Sigma_q (Lq^-1 dyr)
     join_side();  // the factor of Q comes from the side stream
     GemvArgs q1;
     q1.A = Linvq.t(), q1.x = dyr.t(), q1.out = zvec.t();
     q1.rs = n_y, q1.ks = 1, q1.rows = n_y, q1.K = n_y;
+    q1.o_flip = qg;
     gemv(ctx, nl, q1, work.t());
-    vec_flip(ctx, nl, zvec.t(), 0, n_y, qsign.as<int>());  // Q^-1 = Lq^-T Sigma_q Lq^-1
     GemvArgs q2 = q1;
+    q2.o_flip = nullptr;
     q2.x = zvec.t(), q2.out = dy.t();
     q2.rs = 1, q2.ks = n_y;
     gemv(ctx, nl, q2, work.t());
@@ -1090,14 +1145,14 @@ void Solver::search_direction() {
     GemvArgs wd;
     wd.A = Wt.t(), wd.x = dy.t(), wd.out = tmpx.t();
     wd.rs = 1, wd.ks = sumS, wd.rows = sumS, wd.K = n_y;
+    GemvArgs wd0 = wd;
+    wd.o_flip = xg, wd.e = tvec.t(), wd.e_mode = 1;
     gemv(ctx, nl, wd, work.t());
-    vec_flip(ctx, nl, tmpx.t(), 0, sumS, xsign.as<int>());  // u = Sigma (t + W dy)
-    ew_lincomb(ctx, nl, tmpx.t(), 0, tvec.t(), 0, 1, tmpx.t(), 0, 1, sumS);
-    GemvArgs bt = a;
+    GemvArgs bt = a0;
     bt.x = tmpx.t(), bt.out = dx.t();
     bt.item_trans = 1;  // A_item[k][r]
+    bt.o_scale = xs, bt.o_scale_sign = -1;  // L^-T = D^-1 L'^-T
     gemv(ctx, nl, bt, work.t());
-    vec_scale(ctx, nl, dx.t(), 0, sumS, -1, xscale.as<int>());  // L^-T = D^-1 L'^-T
     static int refine_mode = getenv("CLRSDP_REFINE") ? atoi(getenv("CLRSDP_REFINE")) : 4;  // measuring aid, see the order below
     auto refine_second = [&]() {
     // One step of iterative refinement on the SECOND block equation, B^T dx = p. The reference obtains dy from
@@ -1117,21 +1172,19 @@ void Solver::search_direction() {
     ew_lincomb(ctx, nl, dyr.t(), 0, p.t(), 0, 1, tmpy.t(), 0, -1, n_y);              // r = p - B^T dx
     GemvArgs r1 = q1;
     r1.x = dyr.t(), r1.out = zvec.t();
-    gemv(ctx, nl, r1, work.t());
-    vec_flip(ctx, nl, zvec.t(), 0, n_y, qsign.as<int>());
+    gemv(ctx, nl, r1, work.t());                                                     // Sigma_q Lq^-1 r
     GemvArgs r2 = q2;
     r2.x = zvec.t(), r2.out = tmpy.t();
     gemv(ctx, nl, r2, work.t());                                                     // ddy = Q^-1 r
     ew_lincomb(ctx, nl, dy.t(), 0, dy.t(), 0, 1, tmpy.t(), 0, 1, n_y);
-    GemvArgs wr = wd;
+    GemvArgs wr = wd0;
     wr.x = tmpy.t(), wr.out = tmpx.t();
-    gemv(ctx, nl, wr, work.t());                                                     // W ddy
-    vec_flip(ctx, nl, tmpx.t(), 0, sumS, xsign.as<int>());
+    wr.o_flip = xg;
+    gemv(ctx, nl, wr, work.t());                                                     // Sigma W ddy
     GemvArgs mr = bt;
-    mr.x = tmpx.t(), mr.out = trx.t();
-    gemv(ctx, nl, mr, work.t());                                                     // L'^-T Sigma W ddy
-    vec_scale(ctx, nl, trx.t(), 0, sumS, -1, xscale.as<int>());
-    ew_lincomb(ctx, nl, dx.t(), 0, dx.t(), 0, 1, trx.t(), 0, 1, sumS);               // dx += S^-1 B ddy
+    mr.x = tmpx.t(), mr.out = dx.t();
+    mr.e = dx.t(), mr.e_mode = 1;
+    gemv(ctx, nl, mr, work.t());                                                     // dx += D^-1 L'^-T Sigma W ddy = S^-1 B ddy
     };
     auto refine_first = [&]() {
     // ... and one step on the FIRST block equation, S dx - B dy = rhs_x, with the final dy: applying S^-1 through the
@@ -1141,22 +1194,19 @@ void Solver::search_direction() {
     GemvArgs bd;
     bd.A = Bmat.t(), bd.x = dy.t(), bd.out = tmpx.t();
     bd.rs = n_y, bd.ks = 1, bd.rows = sumS, bd.K = n_y;
-    gemv(ctx, nl, bd, work.t());                                                     // B dy
-    ew_lincomb(ctx, nl, tmpx.t(), 0, rhs0.t(), 0, 1, tmpx.t(), 0, 1, sumS);          // rhs_x + B dy
-    GemvArgs sd = a;
-    sd.A = S.t(), sd.x = dx.t(), sd.out = trx.t();
-    gemv(ctx, nl, sd, work.t());                                                     // S_j dx_j
-    ew_lincomb(ctx, nl, tmpx.t(), 0, tmpx.t(), 0, 1, trx.t(), 0, -1, sumS);          // r
-    vec_scale(ctx, nl, tmpx.t(), 0, sumS, -1, xscale.as<int>());
-    GemvArgs m1 = a;
+    bd.e = rhs.t(), bd.e_mode = 1;
+    gemv(ctx, nl, bd, work.t());                                                     // rhs_x + B dy
+    GemvArgs sd = a0;
+    sd.A = S.t(), sd.x = dx.t(), sd.out = tmpx.t();
+    sd.e = tmpx.t(), sd.e_mode = 2;
+    gemv(ctx, nl, sd, work.t());                                                     // r = rhs_x + B dy - S_j dx_j
+    GemvArgs m1 = a;                                                                 // Sigma L'^-1 D^-1 r
     m1.x = tmpx.t(), m1.out = trx.t();
-    gemv(ctx, nl, m1, work.t());                                                     // L'^-1 D^-1 r
-    vec_flip(ctx, nl, trx.t(), 0, sumS, xsign.as<int>());
+    gemv(ctx, nl, m1, work.t());
     GemvArgs m2 = bt;
-    m2.x = trx.t(), m2.out = tmpx.t();
-    gemv(ctx, nl, m2, work.t());                                                     // L'^-T Sigma ...
-    vec_scale(ctx, nl, tmpx.t(), 0, sumS, -1, xscale.as<int>());
-    ew_lincomb(ctx, nl, dx.t(), 0, dx.t(), 0, 1, tmpx.t(), 0, 1, sumS);              // dx += S^-1 r
+    m2.x = trx.t(), m2.out = dx.t();
+    m2.e = dx.t(), m2.e_mode = 1;
+    gemv(ctx, nl, m2, work.t());                                                     // dx += D^-1 L'^-T ... = S^-1 r
     };
     // order: 1 = second only, 2 = first only, 3 = second then first, 4 = first then second
     if (refine_mode == 1 || refine_mode == 3) refine_second();

@@ -192,6 +192,9 @@ class Solver : public SolverApi {
   };
   InvHelper invh_[2];
   bool use_invh_ = true;
+  InvHelper trailh_[2];            // lookahead: remainder of the trailing update beside the next panel (chol_inverse)
+  bool use_lookahead_ = true;
+  double lookahead_ratio_ = 2.0;   // split when (remainder)^2 >= ratio * (row block width) * (trailing width)
   Comm comm_;
   int ntot_local = 0;
   // structure

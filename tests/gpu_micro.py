@@ -25,6 +25,7 @@ def table(h, title, reps):
 
 def main():
     prec = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    only = sys.argv[2] if len(sys.argv) > 2 else "all"   # "chol": the factorisations only
     h = solver.product_handle(prec, 0)
     rng = random.Random(1)
     for batch, n in [(128, 64), (64, 128), (1, 256), (128, 32), (1, 32)]:
@@ -35,6 +36,8 @@ def main():
             h.op_cholesky(batch, n, A)
         table(h, f"cholesky+inverse batch={batch} n={n}", 3)
         h.profile_reset(False)
+    if only == "chol":
+        return
     for batch, n in [(128, 64), (1, 64), (16, 128)]:
         mats = []
         nrng = np.random.default_rng(n)

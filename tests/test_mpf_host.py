@@ -19,7 +19,8 @@ SHIM = os.path.join(HERE, "helpers", "libmpf_host.so")
 
 @pytest.fixture(scope="module")
 def shim():
-    if not os.path.exists(SHIM) or os.path.getmtime(SHIM) < os.path.getmtime(SHIM_SRC):
+    hdr = os.path.join(HERE, "..", "clustered-low-rank-sdp-solver_b200", "csrc", "mpf.cuh")
+    if not os.path.exists(SHIM) or os.path.getmtime(SHIM) < max(os.path.getmtime(SHIM_SRC), os.path.getmtime(hdr)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", SHIM_SRC, "-o", SHIM])
     lib = ctypes.CDLL(SHIM)
     lib.mpf_host_op.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(clrsdp_mp), ctypes.POINTER(clrsdp_mp),
