@@ -306,35 +306,53 @@ MP_HD void round_guard(Num<NL>& out, const uint32_t (&x)[NL + 1], int32_t e, uin
 }
 
 // ---------------------------------------------------------------------------------------------------
+// (A branch-free variant of add - one path through combine_n, as in mul_sub_mul - was measured on the B200: the
+// kernels that live on add (small products, traces, reductions) have warps whose lanes mostly agree in sign and whose
+// shifts are short, and ran 1.3-1.7x slower with it; the branches stay.)
 template <int NL>
 MP_HD Num<NL> add(const Num<NL>& a, const Num<NL>& b) {
-  // One path for all operands (see combine_n). A zero carries the smallest exponent (EXP_ZERO), so it becomes the
-  // operand Y that is shifted out entirely, and x + 0 = x comes out exactly (guard limb 0: nothing to round).
-  const bool sw = b.e > a.e;
+  if (is_zero(a)) return b;
+  if (is_zero(b)) return a;
+  bool sw = b.e > a.e;
   uint32_t X[NL + 1], Y[NL + 1];
   X[0] = 0;
   Y[0] = 0;
-  const uint32_t ka = is_zero(a) ? 0u : 0xffffffffu, kb = is_zero(b) ? 0u : 0xffffffffu;  // (a zero has no mantissa)
 #pragma unroll
   for (int i = 0; i < NL; i++) {
-    X[i + 1] = sw ? (b.m[i] & kb) : (a.m[i] & ka);
-    Y[i + 1] = sw ? (a.m[i] & ka) : (b.m[i] & kb);
+    X[i + 1] = sw ? b.m[i] : a.m[i];
+    Y[i + 1] = sw ? a.m[i] : b.m[i];
   }
-  int32_t ex = sw ? b.e : a.e;
-  const int32_t ey = sw ? a.e : b.e;
-  uint32_t nx = sw ? b.neg : a.neg;
-  const uint32_t ny = sw ? a.neg : b.neg;
-  const uint32_t d = (uint32_t)(ex - ey);
-  const uint32_t q = d >> 5;
-  shr_limbs<NL + 1>(Y, q > (uint32_t)(NL + 1) ? (uint32_t)(NL + 1) : q);  // y below the guard limb: Y = 0
-  shr_bits<NL + 1>(Y, d & 31u);
-  uint32_t flip, ovf;
-  combine_n<NL + 1>(X, Y, (nx ^ ny) & 1u, flip, ovf);
-  nx = flip ? ny : nx;
-  const int sh = normalize_n<NL + 1>(X);
-  if (sh < 0) return zero<NL>();
+  int32_t ex = sw ? b.e : a.e, ey = sw ? a.e : b.e;
+  uint32_t nx = sw ? b.neg : a.neg, ny = sw ? a.neg : b.neg;
+  uint32_t d = (uint32_t)(ex - ey);
   Num<NL> out;
-  round_guard<NL>(out, X, ex + (int32_t)ovf - sh, nx);
+  if (d > 32u * NL + 31u) {  // y is below the guard limb
+#pragma unroll
+    for (int i = 0; i < NL; i++) out.m[i] = X[i + 1];
+    out.e = ex;
+    out.neg = nx;
+    return out;
+  }
+  if (d >> 5) shr_limbs<NL + 1>(Y, d >> 5);
+  if (d & 31u) shr_bits<NL + 1>(Y, d & 31u);
+  if (nx == ny) {
+    uint32_t c = add_n<NL + 1>(X, Y);
+    if (c) {
+      shr_bits<NL + 1>(X, 1);
+      X[NL] |= 0x80000000u;
+      ex += 1;
+    }
+    round_guard<NL>(out, X, ex, nx);
+    return out;
+  }
+  // opposite signs: X - Y; a borrow (only possible when the exponents are equal) means |Y| > |X|: negate, flip the sign
+  if (sub_n<NL + 1>(X, Y)) {
+    neg_n<NL + 1>(X);
+    nx = ny;
+  }
+  int sh = normalize_n<NL + 1>(X);
+  if (sh < 0) return zero<NL>();
+  round_guard<NL>(out, X, ex - sh, nx);
   return out;
 }
 template <int NL>
@@ -420,6 +438,7 @@ MP_HD Num<NL> mul_sub_mul(const Num<NL>& a, const Num<NL>& b, const Num<NL>& c, 
   // mul() would (the rows of the elimination are full of zeros and of either sign: with branches a warp ran the
   // two-product, the one-product, the adding and the subtracting variants one after the other).
   const bool z1 = is_zero(a) || is_zero(b), z2 = is_zero(c) || is_zero(d);
+  if (z1 && z2) return zero<NL>();  // (skips work only where a whole warp sits on structural zeros)
   uint32_t P1[NL + 2], P2[NL + 2], X[NL + 2], Y[NL + 2];
   mul_raw<NL>(a, b, P1);
   mul_raw<NL>(c, d, P2);

@@ -829,7 +829,10 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
         }
       };
       wait_trail();  // the remainder updates of the earlier panels have reached the rows written below
-      const bool ahead = use_lookahead_ && nr > 0 && (double)nr * nr >= lookahead_ratio_ * (double)w1 * n2;
+      // (measured: the split pays when the remainder is a tensor-core product - BASELINE config 5's Q, 93.1 -> 90.6 ms per
+      // iteration - and costs 1 % when everything is a CUDA-core product that shares the SMs with the next panel - config 3's Q)
+      const bool ahead = use_lookahead_ && nr > 0 && (double)nr * nr >= lookahead_ratio_ * (double)w1 * n2 &&
+                         (int64_t)batch * nr * nr * wk > SMALL_GEMM_PMAC;
       if (!ahead) {
         update(gemm_loc, fs1_, fs2_, k1, n2, k1, n2);
       } else {
