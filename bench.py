@@ -100,6 +100,76 @@ class ClockSampler(threading.Thread):
                     samples=len(self.rows), how=self.how)
 
 
+def traffic_from_profile():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant sliced-GEMM launch (batch-64 64x64x64 at 256 bit), read
+    from the committed ncu summary (newest profiles/r*_ncu_mma_planes_full.txt) - never a literal in this file."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_mma_planes_full.txt")), key=os.path.getmtime)
+    for path in reversed(files):
+        rd = wr = None
+        grid = None
+        with open(path) as f:
+            for line in f:
+                m = re.search(r"dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+)", line)
+                if m and rd is None:
+                    rd = float(m.group(1)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(2)]
+                m = re.search(r"dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", line)
+                if m and wr is None:
+                    wr = float(m.group(1)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(2)]
+                m = re.search(r"Grid Size\s+\((\d+)", line)
+                if m and grid is None:
+                    grid = int(m.group(1))
+                if rd is not None and wr is not None:
+                    break
+        if rd is not None and wr is not None:
+            return int(rd + wr), f"{os.path.relpath(path, ROOT)} (first launch: grid {grid}, {rd / 1e6:.2f} MB read + {wr / 1e6:.2f} MB written)"
+    return None, "no ncu summary under profiles/"
+
+
+def mma_roofline_of(name, steps, warmup, int8_peak_tops, device=0):
+    """The sliced-GEMM roofline entry on another workload in the same run (one GPU): `steps` profiled iterations."""
+    from clrsdp import solver
+    saved = dict(WORKLOAD)
+    WORKLOAD.clear()
+    WORKLOAD.update(WORKLOADS[name])
+    try:
+        prec = WORKLOAD["prec"]
+        cons, b, bi = build_problem(WORKLOAD["J_per_gpu"], 0, WORKLOAD["J_per_gpu"], prec)
+        h = solver.product_handle(prec, device)
+        solver.load_problem(h, cons, b, bi)
+        h.set_params(solver.real_params(h.nlimb))
+        h.init_point()
+        h.prepare()
+        dev = []
+        for i in range(warmup + steps):
+            r = h.iterate()
+            if i >= warmup:
+                dev.append(r.seconds)
+        h.init_point()
+        h.prepare()
+        h.profile_reset(True)
+        prof_s = 0.0
+        for _ in range(steps):
+            prof_s += h.iterate().seconds
+        prof = h.profile_dump()
+        h.profile_reset(False)
+        mma = dict(ms=0.0, launches=0, work=0.0)
+        for k, v in prof.items():
+            if k.startswith("mma_planes"):
+                for f in mma:
+                    mma[f] += v[f]
+        tops = (2.0 * mma["work"] / (mma["ms"] * 1e-3) / 1e12) if mma["ms"] > 0 else 0.0
+        macs, pmac = algorithmic_int8_macs(bi, prec)
+        return dict(workload=name, config=dict(WORKLOAD), bound="tensor", kernel="mma_planes_kernel", achieved=tops, peak=int8_peak_tops,
+                    unit="TOP/s (int8)", frac=tops / int8_peak_tops if int8_peak_tops else None, launches=mma["launches"],
+                    ms_per_step=float(np.mean(dev)) * 1e3, steps=steps, share_of_step=mma["ms"] * 1e-3 / prof_s if prof_s else None,
+                    int8_mac_per_iter=macs)
+    finally:
+        WORKLOAD.clear()
+        WORKLOAD.update(saved)
+
+
 def build_problem(J, j_offset, j_total, nl_prec):
     from clrsdp import instances, solver
     cons, b, info = instances.synthetic_clustered_sdp(J=J, delta=WORKLOAD["delta"], K=WORKLOAD["K"], n_y=WORKLOAD["n_y"],
@@ -233,6 +303,8 @@ def main():
     ap.add_argument("--cpu-fma", action="store_true", help="also time the oracle with classical mpfr_fma product loops")
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table here")
+    ap.add_argument("--no-second-roofline", action="store_true",
+                    help="skip the roofline entry of the cfg5shard workload (a few iterations at BASELINE config 5's sizes)")
     args = ap.parse_args()
     WORKLOAD.clear()
     WORKLOAD.update(WORKLOADS[args.workload])
@@ -397,13 +469,10 @@ def main():
         a["ms"] += v["ms"]
         a["launches"] += v["launches"]
     top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]
+    traffic, traffic_src = traffic_from_profile()
     roofline = dict(bound="tensor", kernel="mma_planes_kernel", achieved=mma_tops, peak=int8_peak_tops, unit="TOP/s (int8)",
                     frac=mma_tops / int8_peak_tops if int8_peak_tops else None,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant shape (64 x 64x64x64 at
-                    # 256 bit: 9.0 + 11.1 MB) from the committed ncu --set full capture; its algorithmic bytes are
-                    # 17.8 MB of digits read + 35.7 MB of int32 planes written, most of which stays in the 126 MB L2
-                    traffic=20016896 if args.workload == "cfg3" else None,
-                    traffic_source="profiles/r1i_ncu_mma_planes_full.txt (the batch-64 64x64x64 launch, grid 128 / 198.7 KB smem: 8.98 MB read + 11.04 MB written)",
+                    traffic=traffic if args.workload == "cfg3" else None, traffic_source=traffic_src,
                     peak_source="measured in this run (tcgen05.mma kind::i8 issue loop on all SMs); MEASURED_PEAKS.json has "
                                 f"no int8 entry (its bf16 figure: {peaks['bf16_tflops']} TFLOP/s, {peaks['source']})",
                     achieved_note="ALGORITHMIC int8 ops (M*N*K*s(s+1)/2 MACs per product, s = p/8; no guard digits, no tile "
@@ -422,6 +491,14 @@ def main():
                          note="upload_point + prepare + iterate + download_point through the C ABI with host buffers"),
                 gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline,
                 algorithmic=dict(pmac_per_iter=pmac, int8_mac_per_iter=macs))
+    if world == 1 and args.workload == "cfg3" and not args.no_second_roofline:
+        # the sliced-GEMM kernel at the sizes it was designed for (one GPU's share of BASELINE config 5: block 128, K = 256,
+        # n_y = 1024, 512 bit): a second roofline entry in the same driver-visible line
+        try:
+            del h
+            line["roofline_cfg5shard"] = mma_roofline_of("cfg5shard", 4, 2, int8_peak_tops, local_rank)
+        except Exception as e:
+            line["roofline_cfg5shard"] = dict(error=str(e))
     if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1, both=args.cpu_fma)

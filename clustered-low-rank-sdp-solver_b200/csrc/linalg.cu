@@ -408,10 +408,11 @@ panel_factor_kernel(mp::Tensor A, const int64_t* __restrict__ offA, int64_t shif
   }
 }
 int panel_width(int nl) { (void)nl; return PANEL_W; }
+// CLRSDP_PANEL_CLUSTER (measuring aid, read per launch so that tests can switch it): unset = one CTA per matrix,
+// 0 = as many CTAs per matrix as keep the grid within the SMs, n > 0 = clusters of n CTAs.
 static int panel_cluster_env() {
-  static int v = -2;
-  if (v == -2) v = getenv("CLRSDP_PANEL_CLUSTER") ? atoi(getenv("CLRSDP_PANEL_CLUSTER")) : -1;  // measuring aid: force CL
-  return v;
+  const char* e = getenv("CLRSDP_PANEL_CLUSTER");
+  return e ? atoi(e) : -1;
 }
 void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, bool write_u, int* d_status, int* d_sig,
                   int sig_ld) {

@@ -59,6 +59,7 @@ Solver::Solver(int prec_bits, int device) : nl(prec_bits / 32), prec(prec_bits) 
   if (const char* g = getenv("CLRSDP_INVH")) use_invh_ = atoi(g) != 0;
   if (const char* g = getenv("CLRSDP_LOOKAHEAD")) use_lookahead_ = atoi(g) != 0;
   if (const char* g = getenv("CLRSDP_LOOKAHEAD_RATIO")) lookahead_ratio_ = atof(g);
+  if (const char* g = getenv("CLRSDP_LOOKAHEAD_MIN_PMAC")) lookahead_min_pmac_ = atoll(g);  // (tests: split small products too)
   scal.alloc(SL_COUNT, nl);
   work.alloc(4096, nl);
   d_flags.ensure(4 * sizeof(int));
@@ -832,7 +833,7 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
       // (measured: the split pays when the remainder is a tensor-core product - BASELINE config 5's Q, 93.1 -> 90.6 ms per
       // iteration - and costs 1 % when everything is a CUDA-core product that shares the SMs with the next panel - config 3's Q)
       const bool ahead = use_lookahead_ && nr > 0 && (double)nr * nr >= lookahead_ratio_ * (double)w1 * n2 &&
-                         (int64_t)batch * nr * nr * wk > SMALL_GEMM_PMAC;
+                         (int64_t)batch * nr * nr * wk > lookahead_min_pmac_;
       if (!ahead) {
         update(gemm_loc, fs1_, fs2_, k1, n2, k1, n2);
       } else {

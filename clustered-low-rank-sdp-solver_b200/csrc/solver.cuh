@@ -195,6 +195,7 @@ class Solver : public SolverApi {
   InvHelper trailh_[2];            // lookahead: remainder of the trailing update beside the next panel (chol_inverse)
   bool use_lookahead_ = true;
   double lookahead_ratio_ = 2.0;   // split when (remainder)^2 >= ratio * (row block width) * (trailing width)
+  int64_t lookahead_min_pmac_ = 1500000;  // ... and the remainder is a tensor-core product (= SMALL_GEMM_PMAC)
   Comm comm_;
   int ntot_local = 0;
   // structure

@@ -28,7 +28,7 @@ for r in csv.DictReader(io.StringIO("".join(lines))):
     a[1] += ms
     tot += ms
     n += 1
-out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c {n}  (CLRSDP_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline)",
+out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c {n}  (CLRSDP_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline [--no-second-roofline])",
        f"# {tag}: {n} consecutive launches = about two IPM iterations of BASELINE config 3, launched directly (the default bench replays",
        "# the same kernels from a CUDA graph; two streams are serialised by ncu).",
        "# Times under ncu are cold-cache and serialised: compare SHARES with bench.py's CUDA-event shares (roofline.kernel_ms_per_step), not absolutes.",
@@ -59,7 +59,12 @@ WANT = ["Grid Size", "Block Size", "launch__shared_mem_per_block_dynamic", "laun
 
 
 def dump(rep, header, dst):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # (round 2: the reports exceed what gpurun copies back, so the box exports `ncu -i X.ncu-rep --page raw --csv` to
+    # X.ncu-rep.csv and deletes the report; either form is accepted here)
+    if os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        raw = open(rep + ".csv").read()
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -72,6 +77,30 @@ def dump(rep, header, dst):
     open(dst, "w").write("\n".join(lines) + "\n")
 
 
+if os.path.exists(os.path.join(G, f"{tag}_gemm256.ncu-rep.csv")):   # round 2: single products, first launch = the dominant shape
+    dump(os.path.join(G, f"{tag}_gemm256.ncu-rep"),
+         ["# ncu --set full --clock-control none --cache-control none -k regex:mma_planes -c 20   (python tests/gpu_micro_gemm.py 256)",
+          f"# {tag}: the sliced-GEMM tensor-core kernel on single products at 256 bit (T = 34 digit planes), 4 launches per shape, in this order:",
+          "#   batch 64 x (64x64x64) [the dominant product of BASELINE config 3; fused carry], batch 128 x (32x32x32), 1 x (256x256x8192)",
+          "#   [Q-shaped: K-split, unfused + carry launch], batch 64 x (256x128x128), batch 64 x (128x128x64).",
+          "# --cache-control none: the caches are NOT flushed between the replay passes (the operands of a product come straight from the",
+          "# slicing kernel through L2 in the solver as well).",
+          f"# full report: gpurun_out/{tag}_gemm256.ncu-rep (scratch, not committed)"],
+         os.path.join(P, f"{tag}_ncu_mma_planes_full.txt"))
+if os.path.exists(os.path.join(G, f"{tag}_gemm512.ncu-rep.csv")):
+    dump(os.path.join(G, f"{tag}_gemm512.ncu-rep"),
+         ["# ncu --set full --clock-control none --cache-control none -k regex:mma_planes -c 16   (python tests/gpu_micro_gemm.py 512 cfg5)",
+          f"# {tag}: the same kernel at the sizes of BASELINE config 5 (512 bit, T = 66 digit planes), 4 launches per shape, in this order:",
+          "#   batch 64 x (128x128x128), batch 64 x (256x256x128), batch 16 x (1024x256x256), 1 x (1024x1024x16384) [Q: symmetric, K-split].",
+          f"# full report: gpurun_out/{tag}_gemm512.ncu-rep (scratch, not committed)"],
+         os.path.join(P, f"{tag}_ncu_mma_planes_cfg5_full.txt"))
+if os.path.exists(os.path.join(G, f"{tag}_cuda.ncu-rep.csv")):
+    dump(os.path.join(G, f"{tag}_cuda.ncu-rep"),
+         ['# ncu --set full --clock-control none -k regex:"slice_rows|panel_factor|gemv|small_gemm|lambda_min" -s 300 -c 24   (CLRSDP_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-second-roofline)',
+          f"# {tag}: the CUDA-core kernels around the sliced GEMM (BASELINE config 3): occupancy, DRAM traffic, issue-stall shares.",
+          "# (cold caches between replay passes and streams serialised: DRAM figures are upper bounds)",
+          f"# full report: gpurun_out/{tag}_cuda.ncu-rep (scratch, not committed)"],
+         os.path.join(P, f"{tag}_ncu_cuda_core_kernels_full.txt"))
 if os.path.exists(os.path.join(G, f"{tag}_mma.ncu-rep")):
     dump(os.path.join(G, f"{tag}_mma.ncu-rep"),
          ["# ncu --set full --clock-control none --import-source on -k regex:mma_planes -s 90 -c 6   (CLRSDP_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline)",

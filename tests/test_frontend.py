@@ -10,7 +10,7 @@ import pytest
 
 from clrsdp import frontend as fe
 from clrsdp import instances, solver
-from clrsdp.wire import rel_err_bits
+from clrsdp.wire import MpArray, rel_err_bits
 from oracle.ref import oracle_handle
 
 mpmath.mp.prec = 320
@@ -234,3 +234,44 @@ def test_bivariate_matrix_program_structure_and_oracle_solve():
     solver.set_precision(prec)
     out, rows = solver.solverank1sdp(cons, b, bi, handle=oracle_handle(prec, 4), verbose=False, return_info=True)
     assert rows[-1].terminate == 3 and out[7] < mpmath.mpf(10) ** -15
+
+
+def test_sdpb_format_roundtrip_and_limits(tmp_path):
+    """clrsdp.sdpb_io (row f4; the example's missing WriteFilesSDPB.write_files, ex:97): the sphere-packing constraints
+    (rank-1 samples, weights {1, x}: exactly SDPB's block form) survive the SDPB directory bit for bit; what SDPB's format
+    cannot express (rank > 1 samples, L > 2, negative signs) is refused by name, a positive H != 1 is folded into the basis."""
+    import json
+    from clrsdp import instances, sdpb_io
+    prec = 192
+    solver.set_precision(prec)
+    try:
+        cons, b, _ = instances.sphere_packing_2point(n=3, d=3, prec=prec)
+        bi = solver.get_block_info(cons)
+        sdpb_io.write_sdpb(tmp_path / "sdp", cons, bi, b, b0="0")
+        with open(tmp_path / "sdp" / "control.json") as f:
+            assert json.load(f)["num_blocks"] == bi.J
+        with open(tmp_path / "sdp" / "block_info_1.json") as f:
+            info = json.load(f)
+        assert info == dict(dim=bi.m[1], num_points=bi.n_samples[1])
+        cons2, b2, b0 = sdpb_io.read_sdpb(tmp_path / "sdp")
+        same = lambda a, o: np.array_equal(a.sign, o.sign) and np.array_equal(a.exp, o.exp) and np.array_equal(a.limb, o.limb)
+        assert b0 == "0" and same(b2, b) and len(cons2) == len(cons)
+        for a, o in zip(cons2, cons):
+            assert same(a.B, o.B) and same(a.c, o.c) and a.L == o.L
+            for l in range(o.L):
+                assert same(a.V[l], o.V[l]) and same(a.H[l], o.H[l]) and list(a.ranks[l]) == list(o.ranks[l])
+        bi2 = solver.get_block_info(cons2)
+        assert (bi2.J, bi2.n_y, list(bi2.dim_S)) == (bi.J, bi.n_y, list(bi.dim_S))
+        # H = 4 is folded into the basis as sqrt(H) = 2: the block read back has H = 1 and vectors twice as long
+        c0 = cons[1]
+        four = MpArray.from_mpf([mpmath.mpf(4)] * c0.H[0].n, prec // 32)
+        scaled = [solver.Constraint(V=c0.V, ranks=c0.ranks, H=[four] + list(c0.H[1:]), B=c0.B, c=c0.c)]
+        sdpb_io.write_sdpb(tmp_path / "h4", scaled, solver.get_block_info(scaled), b)
+        back = sdpb_io.read_sdpb(tmp_path / "h4")[0][0]
+        assert [2 * v for v in c0.V[0].reshape(c0.V[0].n).to_fractions()] == back.V[0].reshape(back.V[0].n).to_fractions()
+        # not SDPB's block form
+        gen, bg = instances.random_structured_sdp([dict(m=1, K=3, blocks=[dict(delta=3, ranks=[2, 1, 1])])], n_y=2, prec=prec)
+        with pytest.raises(ValueError, match="rank"):
+            sdpb_io.write_sdpb(tmp_path / "bad", gen, solver.get_block_info(gen), bg)
+    finally:
+        solver.set_precision(256)

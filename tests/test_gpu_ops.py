@@ -3,6 +3,7 @@
 Bar (north star): bit-exact for the integer work (digit planes of the sliced GEMM), and within
 2^-(p-16) of the oracle / exact arithmetic for the floating-point results — the tolerance is written
 next to every assertion."""
+import os
 import random
 from fractions import Fraction
 
@@ -197,3 +198,51 @@ def test_signed_factor_inverts_indefinite_matrices(handles, shape):
             err = max(abs(R[i, j]) for i in range(n) for j in range(n))
             # unpivoted LDL^T of an indefinite matrix: element growth enters the bound (measured < 2^30 on these seeds)
             assert err <= mpmath.mpf(2) ** -(prec - 16 - 40), (b, mpmath.nstr(err, 5))
+
+
+@pytest.mark.parametrize("signed", [False, True])
+def test_lookahead_and_cluster_panels_do_not_change_the_factorisation(signed):
+    """The blocked factorisation with the trailing update split into (next row block | remainder on a helper stream)
+    applies the same contributions to every row block, in the same order, as the unsplit update: the factors agree to
+    rounding (the CUDA-core products choose their K-split by the size of the product, so the summation order inside one
+    contribution may differ - not bit-identical) and match the oracle to p - 16 bits. The panel kernel on a thread-block
+    cluster applies exactly the same operations per entry as one CTA per matrix: BIT-IDENTICAL. 5 panels, so that the helper
+    stream of the remainders, the helper stream of the inverse panels and the pivot chain all overlap."""
+    from clrsdp import solver
+    from oracle.ref import oracle_handle
+    prec, batch, n = 256, 2, 160
+    A = spd_batch(random.Random(5), batch, n, prec // 32)
+    keys = ("CLRSDP_LOOKAHEAD", "CLRSDP_LOOKAHEAD_RATIO", "CLRSDP_LOOKAHEAD_MIN_PMAC", "CLRSDP_PANEL_CLUSTER")
+    saved = {k: os.environ.get(k) for k in keys}
+    results = []
+    try:
+        for env in ({"CLRSDP_LOOKAHEAD": "0"},
+                    {"CLRSDP_LOOKAHEAD": "1", "CLRSDP_LOOKAHEAD_RATIO": "0", "CLRSDP_LOOKAHEAD_MIN_PMAC": "0"},
+                    {"CLRSDP_LOOKAHEAD": "1", "CLRSDP_LOOKAHEAD_RATIO": "0", "CLRSDP_LOOKAHEAD_MIN_PMAC": "0",
+                     "CLRSDP_PANEL_CLUSTER": "8"}):
+            for k in keys:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            h = solver.product_handle(prec, 0)      # the switches are read when the handle is created / per launch
+            results.append(h.op_signed_factor(batch, n, A) if signed else h.op_cholesky(batch, n, A))
+            del h
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    plain, ahead, ahead_cluster = results
+    for x, y in zip(ahead, ahead_cluster):          # cluster panels: bit-identical
+        if isinstance(x, np.ndarray):
+            assert np.array_equal(x, y)
+        else:
+            assert np.array_equal(x.limb, y.limb) and np.array_equal(x.exp, y.exp) and np.array_equal(x.sign, y.sign)
+    for x, y in zip(plain, ahead):                  # lookahead: the same factors to rounding (2^-(p-16) relative)
+        if isinstance(x, np.ndarray):
+            assert np.array_equal(x, y)             # pivot signs
+        else:
+            assert rel_err_bits(x, y) >= prec - 16
+    if not signed:
+        Lo, Lio = oracle_handle(prec, 2).op_cholesky(batch, n, A)
+        for r in (plain, ahead):
+            assert rel_err_bits(r[0], Lo) >= prec - 16 and rel_err_bits(r[1], Lio) >= prec - 16
