@@ -68,21 +68,6 @@ __device__ __forceinline__ void fixed_point_digits(const GatherArgs& g, int b, i
   for (int i = 0; i < NLW; i++) W[i] ^= M[i];
 }
 
-template <int NL, int S>
-__device__ __forceinline__ void slice_entry(const GatherArgs& g, int row, int k, int32_t rexp, int8_t* __restrict__ digits) {
-  constexpr int NLW = NL + 2;
-  uint32_t W[NLW];
-  const int b = row / g.rows, r = row % g.rows;
-  fixed_point_digits<NL, S>(g, b, item_off(g, b) + (int64_t)r * g.rs + (int64_t)k * g.ks, k, k < g.K, rexp, W);
-  int8_t* out = digits + ((size_t)(S - 1) * g.rows_total + row) * g.Kp + k;
-  const size_t pstride = (size_t)g.rows_total * g.Kp;
-#pragma unroll
-  for (int i = 0; i < S; i++) {
-    *out = (int8_t)((W[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-    out -= pstride;
-  }
-}
-
 // Four consecutive entries k4 .. k4+3 of one row: their digits are packed into one 32-bit word per digit plane (a 4 x 4
 // byte transpose of the four entries' words by PRMT), so a warp writes 128 contiguous bytes per plane and store
 // instruction instead of 32.
@@ -110,17 +95,50 @@ __device__ __forceinline__ void slice_entry4(const GatherArgs& g, int row, int k
   }
 }
 
-// Row exponent + slicing in one launch. A block of 8 warps owns 8/WPR rows (WPR warps per row): pass 1 takes the
-// maximum exponent over the row's non-zero entries (EXP_ZERO for an all-zero row), pass 2 converts the row.
-// The second read of the row hits L1/L2.
+// Row exponent + slicing in one launch: pass 1 takes the maximum exponent over the row's non-zero entries (EXP_ZERO for an
+// all-zero row), pass 2 converts the row. Every thread converts FOUR consecutive entries of one row and stores their
+// digits as one packed 32-bit word per digit plane (slice_entry4): one-entry-per-thread slicing spent a third of its
+// ~700 instructions per entry on 34 single-byte stores and their address arithmetic.
+//   wpr >= 1: a block of 8 warps owns 8/wpr rows (wpr warps per row; long rows, or few rows);
+//   wpr == 0: SHORT rows (Kp <= 128): lpr = Kp/4 lanes per row, 32/lpr rows per warp, the exponent maximum by a segmented
+//             shuffle - no shared memory, no block barrier.
 constexpr int SLICE_THREADS = 256;
 template <int NL, int S>
 __global__ void __launch_bounds__(SLICE_THREADS, (NL <= 8 ? 4 : 2)) slice_rows_kernel(GatherArgs g, int wpr, int32_t* __restrict__ exps,
                                                                     int8_t* __restrict__ digits) {
   __shared__ int32_t smx[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rpb = 8 / wpr, sub = warp % wpr;
   const uint32_t* hdr = g.w + (size_t)NL * g.n;
+  if (wpr == 0) {
+    const int lpr = g.Kp >> 2, rpw = 32 / lpr;           // Kp in {32, 64, 128}: 8, 16 or 32 lanes per row
+    const int sub = lane & (lpr - 1), k4 = 4 * sub;
+    const int nwarps = (g.rows_total + rpw - 1) / rpw;
+    for (int wg = blockIdx.x * 8 + warp; wg < nwarps; wg += gridDim.x * 8) {
+      const int row = wg * rpw + lane / lpr;
+      const bool live = row < g.rows_total;
+      int32_t mx = mp::EXP_ZERO;
+      if (live) {
+        const int b = row / g.rows, r = row - b * g.rows;
+        const int64_t base = item_off(g, b) + (int64_t)r * g.rs;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int k = k4 + i;
+          if (k < g.K) {
+            int32_t e = ((int32_t)hdr[base + (int64_t)k * g.ks]) >> 1;
+            if (e != mp::EXP_ZERO && g.kshift) e -= g.kshift[b * g.K + k];
+            mx = max(mx, e);
+          }
+        }
+      }
+      for (int o = lpr >> 1; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (live) {
+        if (sub == 0) exps[row] = mx;
+        slice_entry4<NL, S>(g, row, k4, mx, digits);
+      }
+    }
+    return;
+  }
+  const int rpb = 8 / wpr, sub = warp % wpr;
   const int ngroups = (g.rows_total + rpb - 1) / rpb;
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int row = grp * rpb + warp / wpr;
@@ -151,11 +169,7 @@ __global__ void __launch_bounds__(SLICE_THREADS, (NL <= 8 ? 4 : 2)) slice_rows_k
     }
     if (live) {
       if (sub == 0 && lane == 0) exps[row] = mx;
-      if (g.Kp >= 256) {  // long rows: four entries per thread, packed 32-bit digit stores
-        for (int k4 = 4 * (sub * 32 + lane); k4 < g.Kp; k4 += 128 * wpr) slice_entry4<NL, S>(g, row, k4, mx, digits);
-      } else {            // short rows: one entry per thread keeps all lanes busy
-        for (int k = sub * 32 + lane; k < g.Kp; k += 32 * wpr) slice_entry<NL, S>(g, row, k, mx, digits);
-      }
+      for (int k4 = 4 * (sub * 32 + lane); k4 < g.Kp; k4 += 128 * wpr) slice_entry4<NL, S>(g, row, k4, mx, digits);
     }
   }
 }
@@ -705,9 +719,14 @@ mma_planes_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = (uint32_t*)(bars + 33);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // K-split slowest: the CTAs resident at the same time (consecutive block indices) then work on the SAME K range of
+  // different tiles, i.e. they share the rows of A (same mt) and of B (same nt), and their combined working set per digit
+  // group fits L2. With the split fastest the Q product of BASELINE config 5 (1024 x 1024 x 16384, 9 splits) read 160 GB
+  // from DRAM per launch (5.3 TB/s, L2 hit rate 40 %): it was HBM-bound, not tensor-bound.
   int idx = blockIdx.x;
-  const int split = idx % p.nsplit;
-  idx /= p.nsplit;
+  const int tiles_all = (int)(gridDim.x / (unsigned)p.nsplit);
+  const int split = idx / tiles_all;
+  idx -= split * tiles_all;
   int nt, mt;
   if (p.tile_map) {
     const int2 t = p.tile_map[idx % p.n_tile_pairs];
@@ -1016,9 +1035,14 @@ static void slice_impl(Ctx& ctx, const OperandDesc& op, Slice& out) {
   int64_t total = (int64_t)out.rows_total * Kp;
   // long rows (or few of them) get a whole block per row, short rows one warp
   int wpr = (Kp > 256 || (int64_t)out.rows_total * 32 < (int64_t)ctx.sm_count * 256) ? 8 : 1;
-  if (Kp <= 32) wpr = 1;
-  int rpb = 8 / wpr;
-  int grid = (int)std::min<int64_t>(ceil_div(out.rows_total, rpb), (int64_t)ctx.sm_count * 8);
+  int grid;
+  if (Kp <= 128) {   // short rows: Kp/4 lanes per row, no block barrier
+    wpr = 0;
+    const int rpw = 32 / (Kp / 4);
+    grid = (int)std::min<int64_t>(ceil_div(ceil_div(out.rows_total, rpw), 8), (int64_t)ctx.sm_count * 8);
+  } else {
+    grid = (int)std::min<int64_t>(ceil_div(out.rows_total, 8 / wpr), (int64_t)ctx.sm_count * 8);
+  }
   // algorithmic bytes: read (p/8+4) per entry, write S digit bytes
   int tk = ctx.begin("slice", (double)total * (4.0 * (NL + 1) + S));
   slice_rows_kernel<NL, S><<<grid, SLICE_THREADS, 0, ctx.stream>>>(g, wpr, out.exps.as<int32_t>(), out.digits.as<int8_t>());

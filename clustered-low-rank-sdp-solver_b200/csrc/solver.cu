@@ -205,15 +205,18 @@ bool Solver::wire_pinned(const int8_t* sign, const int64_t* exp, const uint32_t*
 void Solver::to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpBuf& dst, int64_t dst_off) {
   if (count <= 0) return;
   if (wire_pinned(src->sign, src->exp, src->limb, src->n)) {
-    wire_se_.ensure((size_t)count * 9);
-    int8_t* d_sign = wire_se_.as<int8_t>() + (size_t)count * 8;
-    int64_t* d_exp = wire_se_.as<int64_t>();
+    // sign / exponent scratch: one region per transfer of a deferred group (upload_point / download_point move four
+    // tensors and synchronise ONCE at the end instead of after every tensor), else the start of the buffer
+    if (!wire_defer_) wire_se_.ensure((size_t)count * 9 + 16), wire_off_ = 0;
+    int64_t* d_exp = reinterpret_cast<int64_t*>(wire_se_.as<char>() + wire_off_);
+    int8_t* d_sign = reinterpret_cast<int8_t*>(d_exp + count);
+    if (wire_defer_) wire_off_ += (((size_t)count * 9 + 15) / 16) * 16;
     CLR_CUDA(cudaMemcpy2DAsync(dst.w() + dst_off, dst.n * sizeof(uint32_t), src->limb + src_off, (size_t)src->n * sizeof(uint32_t),
                                (size_t)count * sizeof(uint32_t), (size_t)nl, cudaMemcpyHostToDevice, ctx.stream));
     CLR_CUDA(cudaMemcpyAsync(d_sign, src->sign + src_off, (size_t)count, cudaMemcpyHostToDevice, ctx.stream));
     CLR_CUDA(cudaMemcpyAsync(d_exp, src->exp + src_off, (size_t)count * 8, cudaMemcpyHostToDevice, ctx.stream));
     wire_pack(ctx, nl, dst.t(), dst_off, count, d_sign, d_exp);
-    CLR_CUDA(cudaStreamSynchronize(ctx.stream));  // the scratch is reused by the next transfer
+    if (!wire_defer_) CLR_CUDA(cudaStreamSynchronize(ctx.stream));  // the scratch is reused by the next transfer
     return;
   }
   uint32_t* stage = stage_buf().ensure((size_t)(nl + 1) * count);
@@ -239,15 +242,16 @@ void Solver::to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpB
 void Solver::to_host(const MpBuf& src, int64_t src_off, int64_t count, clrsdp_mp_out* dst, int64_t dst_off) {
   if (count <= 0) return;
   if (wire_pinned(dst->sign, dst->exp, dst->limb, dst->n)) {
-    wire_se_.ensure((size_t)count * 9);
-    int8_t* d_sign = wire_se_.as<int8_t>() + (size_t)count * 8;
-    int64_t* d_exp = wire_se_.as<int64_t>();
+    if (!wire_defer_) wire_se_.ensure((size_t)count * 9 + 16), wire_off_ = 0;
+    int64_t* d_exp = reinterpret_cast<int64_t*>(wire_se_.as<char>() + wire_off_);
+    int8_t* d_sign = reinterpret_cast<int8_t*>(d_exp + count);
+    if (wire_defer_) wire_off_ += (((size_t)count * 9 + 15) / 16) * 16;
     wire_unpack(ctx, nl, src.t(), src_off, count, d_sign, d_exp);
     CLR_CUDA(cudaMemcpy2DAsync(dst->limb + dst_off, (size_t)dst->n * sizeof(uint32_t), src.w() + src_off, src.n * sizeof(uint32_t),
                                (size_t)count * sizeof(uint32_t), (size_t)nl, cudaMemcpyDeviceToHost, ctx.stream));
     CLR_CUDA(cudaMemcpyAsync(dst->sign + dst_off, d_sign, (size_t)count, cudaMemcpyDeviceToHost, ctx.stream));
     CLR_CUDA(cudaMemcpyAsync(dst->exp + dst_off, d_exp, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx.stream));
-    CLR_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (!wire_defer_) CLR_CUDA(cudaStreamSynchronize(ctx.stream));
     return;
   }
   uint32_t* stage = stage_buf().ensure((size_t)(nl + 1) * count);
@@ -380,6 +384,7 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
   QP.alloc(qpN, nl);
   for (MpBuf* t : {&S, &Us, &Vs, &Linvs}) t->alloc(sN, nl);
   Bmat.alloc((int64_t)sumS * n_y, nl);
+  BmatT.alloc((int64_t)sumS * n_y, nl);  // B^T (n_y x sum dim_S, row-major): the row operand of W = L'^-1 D^-1 B, sliced coalesced
   Wt.alloc((int64_t)sumS * n_y, nl);
   for (MpBuf* t : {&Q, &Uq, &Vq, &Linvq}) t->alloc((int64_t)n_y * n_y, nl);
   for (MpBuf* t : {&x, &dx, &d, &c, &rhs, &rhs0, &tvec, &tmpx, &trx, &dx_pred}) t->alloc(sumS, nl);
@@ -493,7 +498,7 @@ void Solver::upload_tables() {
     std::vector<int64_t> offS, offBt, offW;
     for (int j : g.clusters) {
       offS.push_back(clusters_[j].Soff);
-      offBt.push_back((int64_t)clusters_[j].xoff * n_y);
+      offBt.push_back((int64_t)clusters_[j].xoff);  // into BmatT: columns [xoff_j, xoff_j + dim_S_j) of every row
       offW.push_back(clusters_[j].xoff);
     }
     up(g.offS, offS, s), up(g.offBt, offBt, s), up(g.offW, offW, s);
@@ -543,6 +548,14 @@ void Solver::upload_cluster(int j, const clrsdp_mp* V, const clrsdp_mp* Hh, cons
 }
 
 void Solver::build_static_slices() {
+  {  // BmatT(a, r) = Bmat(r, a): B is static, so the transposed reads of its slicing (rows a, contraction over the
+     // constraints of a cluster: a stride of n_y words between consecutive k) are paid once here instead of every iteration
+    SmallGemmArgs cp;
+    cp.A = Bmat.t(), cp.ars = 1, cp.aks = n_y;
+    cp.C = BmatT.t(), cp.crs = sumS, cp.ccs = 1;
+    cp.batch = 1, cp.M = n_y, cp.N = sumS;
+    rect_copy(ctx, nl, cp);
+  }
   for (auto& g : bgroups_) {
     int nblk = (int)g.blocks.size();
     std::vector<int64_t> voff;
@@ -620,25 +633,54 @@ void Solver::init_point() {  // MPMP.jl:660-686
   have_point = true;
   prepared = false;
 }
+// A group of transfers through the pinned path that share one synchronisation: the scratch is sized for all of them up
+// front (no reallocation while copies are in flight) and every transfer takes its own region of it.
+struct Solver::WireGroup {
+  Solver& s;
+  bool done = false;
+  WireGroup(Solver& s_, size_t numbers) : s(s_) {
+    s.wire_se_.ensure(numbers * 9 + 16 * 8);
+    s.wire_off_ = 0;
+    s.wire_defer_ = true;
+  }
+  void finish() {
+    if (done) return;
+    done = true;
+    s.wire_defer_ = false;
+    s.wire_off_ = 0;
+    CLR_CUDA(cudaStreamSynchronize(s.ctx.stream));  // the host arrays are the caller's again when the call returns
+  }
+  ~WireGroup() {
+    if (!done) {
+      s.wire_defer_ = false;
+      s.wire_off_ = 0;
+      cudaStreamSynchronize(s.ctx.stream);
+    }
+  }
+};
 void Solver::upload_point(const clrsdp_mp* xx, const clrsdp_mp* XX, const clrsdp_mp* yy, const clrsdp_mp* YY) {
   if (!structure_set) throw SolverError(CLRSDP_ERR_STATE, "upload_point before set_structure");
   if (xx->n != sumS || yy->n != n_y || XX->n != blkN || YY->n != blkN)
     throw SolverError(CLRSDP_ERR_BAD_ARG, "upload_point: sizes do not match the structure");
   CLR_CUDA(cudaSetDevice(ctx.device));
+  WireGroup grp(*this, (size_t)(sumS + n_y + 2 * blkN));  // the four transfers are queued back to back, one synchronisation
   to_device(xx, 0, sumS, x, 0);
   to_device(yy, 0, n_y, y, 0);
   to_device(XX, 0, blkN, X, 0);
   to_device(YY, 0, blkN, Y, 0);
+  grp.finish();
   have_point = true;
   prepared = false;
 }
 void Solver::download_point(clrsdp_mp_out* xx, clrsdp_mp_out* XX, clrsdp_mp_out* yy, clrsdp_mp_out* YY) {
   if (!have_point) throw SolverError(CLRSDP_ERR_STATE, "download_point: no point");
   CLR_CUDA(cudaSetDevice(ctx.device));
+  WireGroup grp(*this, (size_t)(sumS + n_y + 2 * blkN));
   if (xx) to_host(x, 0, sumS, xx, 0);
   if (yy) to_host(y, 0, n_y, yy, 0);
   if (XX) to_host(X, 0, blkN, XX, 0);
   if (YY) to_host(Y, 0, blkN, YY, 0);
+  grp.finish();
 }
 
 // ---- operand helpers ------------------------------------------------------------------------------
@@ -1020,10 +1062,10 @@ void Solver::decomposition() {
   // Wt[a][(j,i)] = (L_j^-1 B_j)[i][a]
   for (auto& g : cgroups_) {
     OperandDesc bt;  // rows a (n_y) of (D^-1 B_j)^T
-    bt.src = Bmat.t();
+    bt.src = BmatT.t();
     bt.d_off = g.offBt.as<int64_t>();
     bt.batch = (int)g.clusters.size();
-    bt.rows = n_y, bt.K = g.dimS, bt.rs = 1, bt.ks = n_y;
+    bt.rows = n_y, bt.K = g.dimS, bt.rs = sumS, bt.ks = 1;
     bt.d_kshift = g.equil.as<int>();
     ge()->slice(bt, g.sBt);
     OperandDesc bd;
@@ -1036,16 +1078,6 @@ void Solver::decomposition() {
     o.dst = Wt.t();
     o.d_off = g.offW.as<int64_t>();
     o.rs = sumS, o.cs = 1;
-    static int float_sites = getenv("CLRSDP_FLOAT_SITES") ? atoi(getenv("CLRSDP_FLOAT_SITES")) : 0;  // measuring aid
-    if (float_sites & 1) {
-      SmallGemmArgs sg;
-      sg.A = Bmat.t(), sg.B = Linvs.t(), sg.C = Wt.t();
-      sg.offA = g.offBt.as<int64_t>(), sg.offB = g.offS.as<int64_t>(), sg.offC = g.offW.as<int64_t>();
-      sg.ars = 1, sg.aks = n_y, sg.brs = g.dimS, sg.bks = 1, sg.crs = sumS, sg.ccs = 1;
-      sg.batch = (int)g.clusters.size(), sg.M = n_y, sg.N = g.dimS, sg.K = g.dimS;
-      // (D^-1 B: scale a copy of B's rows first)
-      throw SolverError(-1, "CLRSDP_FLOAT_SITES & 1 not implemented");
-    }
     ge()->multiply(g.sBt, g.sLinv, plan_of((int)g.clusters.size(), n_y, g.dimS), o);
   }
   mark(-1 - CLRSDP_T_CINVB);

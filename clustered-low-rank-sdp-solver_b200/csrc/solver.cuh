@@ -175,6 +175,9 @@ class Solver : public SolverApi {
   DevBuf xsign, qsign;                                 // pivot signs of the S_j (indexed like x) and of Q ([n_y])
   Slice sWs_;                                          // Sigma W: the rows of Wt sliced with the signs on the contraction index
   DevBuf wire_se_;                                     // sign / exponent scratch of the pinned transfer path
+  bool wire_defer_ = false;                            // inside a WireGroup: transfers do not synchronise one by one
+  size_t wire_off_ = 0;                                // next free byte of wire_se_ inside a WireGroup
+  struct WireGroup;
   std::unique_ptr<GemmEngine> gemm_, gemm_side_;
   cudaStream_t side_stream_ = nullptr, main_stream_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
@@ -215,7 +218,7 @@ class Solver : public SolverApi {
   // arenas
   MpBuf XY2, dXY2, Linv2, U2, W2, T1d, T2d;  // paired arenas: X|Y, dX|dY, Lx^-1|Ly^-1, work
   MpBuf X, Y, Xinv, R, P, Z, dX, dY, XY, T1, T2, Ux, Vx, Linvx, Linvy;  // X,Y,dX,dY,Linv*,T1,T2,Ux are views
-  MpBuf Vt, H, Px, Py, Tt, VD, QP, S, Us, Vs, Linvs, Bmat, Wt, Q, Uq, Vq, Linvq;
+  MpBuf Vt, H, Px, Py, Tt, VD, QP, S, Us, Vs, Linvs, Bmat, BmatT, Wt, Q, Uq, Vq, Linvq;
   MpBuf x, dx, d, c, rhs, rhs0, tvec, tmpx, trx, y, dy, p, b, tmpy, zvec, dyr;
   MpBuf dX_pred, dY_pred, dx_pred, dy_pred;
   MpBuf Cmat;  // objective matrix C (block structure of X), only allocated by upload_C
