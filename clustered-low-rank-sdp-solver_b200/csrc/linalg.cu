@@ -2003,8 +2003,8 @@ void schur_assemble(Ctx& ctx, int nl, const StructTables& st, mp::Tensor Px, mp:
 }
 
 // thread per x entry (j, r, s, k)
-template <int NL, int MODE>
-__global__ void trace_kernel(StructTables st, mp::Tensor A, mp::Tensor B, mp::Tensor H, mp::Tensor out) {
+template <int NL>
+__global__ void trace_kernel(StructTables st, mp::Tensor A, mp::Tensor H, mp::Tensor out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st.sumS) return;
   int j = st.x_cluster[i];
@@ -2016,19 +2016,13 @@ __global__ void trace_kernel(StructTables st, mp::Tensor A, mp::Tensor B, mp::Te
   Num<NL> acc = mp::zero<NL>();
   for (int l = 0; l < st.c_L[j]; l++) {
     int bk = st.c_blk0[j] + l;
-    int Nv = st.b_Nv[bk], dl = st.b_delta[bk];
+    int Nv = st.b_Nv[bk];
     const int* rsum = st.rank_sums + st.b_rs0[bk];
     int64_t ho = st.b_Hoff[bk];
     for (int a = rsum[k]; a < rsum[k + 1]; a++) {
-      Num<NL> val;
-      if (MODE == 0) {  // from pairings: Py[(r,a),(s,a)]
-        int ld = m * Nv;
-        val = ldm<NL>(A, st.b_Poff[bk] + (int64_t)(r * Nv + a) * ld + (s * Nv + a));
-      } else {  // sum_i Vt[a][i] * Tt[(r*m+s)*Nv + a][i]
-        int64_t vo = st.b_Voff[bk] + (int64_t)a * dl, to = st.b_Toff[bk] + ((int64_t)(r * m + s) * Nv + a) * dl;
-        val = mp::zero<NL>();
-        for (int q = 0; q < dl; q++) val = nadd(val, nmul(ldm<NL>(A, vo + q), ldm<NL>(B, to + q)));
-      }
+      // from the pairings: Py[(r,a),(s,a)]   (the general method on Z V is trace_zv_kernel below)
+      const int ld = m * Nv;
+      const Num<NL> val = ldm<NL>(A, st.b_Poff[bk] + (int64_t)(r * Nv + a) * ld + (s * Nv + a));
       acc = nadd(acc, nmul(ldm<NL>(H, ho + a), val));
     }
   }
@@ -2037,14 +2031,45 @@ __global__ void trace_kernel(StructTables st, mp::Tensor A, mp::Tensor B, mp::Te
 void trace_from_pairings(Ctx& ctx, int nl, const StructTables& st, mp::Tensor Py, mp::Tensor H, mp::Tensor out) {
   DISPATCH_NL(nl, {
     int tk = ctx.begin("trace_pairings");
-    trace_kernel<NL, 0><<<ceil_div(st.sumS, 128), 128, 0, ctx.stream>>>(st, Py, Py, H, out);
+    trace_kernel<NL><<<ceil_div(st.sumS, 128), 128, 0, ctx.stream>>>(st, Py, H, out);
     ctx.end(tk);
   });
+}
+// trace_A, general method (MPMP.jl:1517-1618): out[i] = sum_l sum_a H[a] * <Vt[a], Tt[(r,s), a]> with one WARP per constraint
+// index i: the lanes stride the vector (coalesced lines of both operands) and the partial sums meet in a shuffle
+// reduction. (One thread per index - trace_kernel<NL, 1> - ran serial dot products of length delta with a stride of
+// delta words between the lanes of a warp, on 256 warps for the whole GPU: 270 us per call at BASELINE config 3.)
+template <int NL>
+__global__ void trace_zv_kernel(StructTables st, mp::Tensor Vt, mp::Tensor Tt, mp::Tensor H, mp::Tensor out) {
+  const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (i >= st.sumS) return;
+  const int j = st.x_cluster[i];
+  const int K = st.c_K[j], m = st.c_m[j];
+  const int loc = i - st.c_xoff[j];
+  int r, s;
+  tri_decode(loc / K, r, s);
+  const int k = loc % K;
+  Num<NL> acc = mp::zero<NL>();
+  for (int l = 0; l < st.c_L[j]; l++) {
+    const int bk = st.c_blk0[j] + l;
+    const int Nv = st.b_Nv[bk], dl = st.b_delta[bk];
+    const int* rsum = st.rank_sums + st.b_rs0[bk];
+    const int64_t ho = st.b_Hoff[bk];
+    for (int a = rsum[k]; a < rsum[k + 1]; a++) {
+      const int64_t vo = st.b_Voff[bk] + (int64_t)a * dl, to = st.b_Toff[bk] + ((int64_t)(r * m + s) * Nv + a) * dl;
+      Num<NL> val = mp::zero<NL>();
+      for (int q = lane; q < dl; q += 32) val = nadd(val, nmul(ldm<NL>(Vt, vo + q), ldm<NL>(Tt, to + q)));
+      acc = nadd(acc, nmul(ldm<NL>(H, ho + a), val));
+    }
+  }
+#pragma unroll 1
+  for (int o = 16; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
+  if (lane == 0) stm<NL>(out, i, acc);
 }
 void trace_from_ZV(Ctx& ctx, int nl, const StructTables& st, mp::Tensor Vt, mp::Tensor Tt, mp::Tensor H, mp::Tensor out) {
   DISPATCH_NL(nl, {
     int tk = ctx.begin("trace_ZV");
-    trace_kernel<NL, 1><<<ceil_div(st.sumS, 64), 64, 0, ctx.stream>>>(st, Vt, Tt, H, out);
+    trace_zv_kernel<NL><<<ceil_div((int64_t)st.sumS * 32, 128), 128, 0, ctx.stream>>>(st, Vt, Tt, H, out);
     ctx.end(tk);
   });
 }
