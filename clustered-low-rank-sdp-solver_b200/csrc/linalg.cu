@@ -1724,21 +1724,20 @@ __global__ void gemv_t_kernel(GemvDev g) {
 }
 template <int NL>
 __global__ void gemv_sum_kernel(GemvDev g) {
-  if (g.nparts > 16) {  // many parts (few rows): one warp per row, lanes stride the parts
-    const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (r >= g.rows) return;
-    Num<NL> acc = mp::zero<NL>();
-    for (int p = lane; p < g.nparts; p += 32) acc = nadd(acc, ldm<NL>(g.work, (int64_t)p * g.rows + r));
-#pragma unroll 1
-    for (int o = 16; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
-    if (lane == 0) gemv_finish<NL>(g, r, acc);
-    return;
-  }
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= g.rows) return;
+  // One group of 2^k >= min(nparts, 32) adjacent lanes per row: the parts are loaded in parallel and meet in a shuffle
+  // reduction (one thread per row summed up to 16 parts in a serial chain of dependent loads: 16 us per call, 19 calls on
+  // the critical path of an iteration).
+  const int lpr = g.lpr;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = (int)(gt % lpr);
+  const int64_t r = gt / lpr;
+  const bool live = r < g.rows;
   Num<NL> acc = mp::zero<NL>();
-  for (int p = 0; p < g.nparts; p++) acc = nadd(acc, ldm<NL>(g.work, (int64_t)p * g.rows + r));
-  gemv_finish<NL>(g, r, acc);
+  if (live)
+    for (int p = sub; p < g.nparts; p += lpr) acc = nadd(acc, ldm<NL>(g.work, (int64_t)p * g.rows + r));
+#pragma unroll 1
+  for (int o = lpr >> 1; o; o >>= 1) acc = nadd(acc, shfl_xor_num(acc, o));
+  if (live && sub == 0) gemv_finish<NL>(g, (int)r, acc);
 }
 static int gemv_parts(int rows, int K) {
   if ((int64_t)rows >= 148 * 8 || K <= 256) return 1;
@@ -1777,7 +1776,9 @@ void gemv(Ctx& ctx, int nl, const GemvArgs& a, mp::Tensor work) {
     ctx.end(tk);
     if (g.nparts > 1) {
       tk = ctx.begin("gemv_sum");
-      gemv_sum_kernel<NL><<<g.nparts > 16 ? ceil_div((int64_t)a.rows * 32, 128) : ceil_div(a.rows, 128), 128, 0, ctx.stream>>>(g);
+      g.lpr = 2;
+      while (g.lpr < 32 && g.lpr < g.nparts) g.lpr <<= 1;
+      gemv_sum_kernel<NL><<<ceil_div((int64_t)a.rows * g.lpr, 128), 128, 0, ctx.stream>>>(g);
       ctx.end(tk);
     }
   });
