@@ -19,6 +19,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -36,6 +37,7 @@ struct NcclApi {
       api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
       api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
       api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+      api.CommAbort = (decltype(api.CommAbort))sym("ncclCommAbort");
       api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
       api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
       api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");

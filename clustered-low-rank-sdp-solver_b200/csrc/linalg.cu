@@ -7,11 +7,13 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 
 namespace clr {
 namespace cg = cooperative_groups;
 using mp::Num;
+constexpr int MAX_DEVICES = 64;  // device ordinals of one box (per-device one-off settings)
 
 #define DISPATCH_NL(nl, ...)                                  \
   switch (nl) {                                               \
@@ -426,10 +428,12 @@ void panel_factor(Ctx& ctx, int nl, const MatBatch& A, const MatBatch& Linv, boo
   static int panel_dbg = getenv("CLRSDP_PANEL_DEBUG") ? atoi(getenv("CLRSDP_PANEL_DEBUG")) : 0;
   DISPATCH_NL(nl, {
     size_t words = ((size_t)A.n * (A.n + 1) + A.n) * (NL + 2);
-    static bool attr[17] = {false};
-    if (!attr[NL]) {
+    // (function attributes belong to the DEVICE that is current: a process-wide "done" flag left every device but the first
+    // of a multi-device handle without the opt-in, and its first panel above 48 KB failed to launch)
+    static std::atomic<bool> attr[MAX_DEVICES][17];
+    if (!attr[ctx.device % MAX_DEVICES][NL].load()) {
       CLR_CUDA(cudaFuncSetAttribute(panel_factor_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr[NL] = true;
+      attr[ctx.device % MAX_DEVICES][NL].store(true);
     }
     std::string nm = "panel_factor_n" + std::to_string(A.n);
     int tk = ctx.begin(nm.c_str());
@@ -1226,11 +1230,11 @@ void lambda_min(Ctx& ctx, int nl, const MatBatch& W, mp::Tensor out, const int* 
   int P = std::max(1, 512 / cx);
   dim3 blk(cx, P, 1);
   DISPATCH_NL(nl, {
-    static bool attr[17] = {false};
-    if (!attr[NL]) {
+    static std::atomic<bool> attr[MAX_DEVICES][17];  // per device, see panel_factor
+    if (!attr[ctx.device % MAX_DEVICES][NL].load()) {
       CLR_CUDA(cudaFuncSetAttribute(lambda_min_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CLR_CUDA(cudaFuncSetAttribute(lambda_min_mixed_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      attr[NL] = true;
+      attr[ctx.device % MAX_DEVICES][NL].store(true);
     }
     // production path: FP64 factorisation + multiprecision refinement; matrices it flags (and sizes that do not fit
     // its shared-memory working set) go through the all-multiprecision kernel

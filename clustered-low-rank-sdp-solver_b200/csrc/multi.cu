@@ -116,6 +116,8 @@ void RankPool::loop(int r) {
       (*task)(r);
     } catch (...) {
       errors_[r] = std::current_exception();
+      // the other ranks may already sit in a collective that waits for this one: release them, or run() never returns
+      if (on_error) on_error(r);
     }
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -157,6 +159,11 @@ MultiSolver::MultiSolver(int prec_bits, int n_dev, const int* dev_ids) : nl_(pre
     ranks_.emplace_back(new Solver(prec_bits, dev_ids ? dev_ids[r] : r));
   }
   pool_.reset(new RankPool(n_dev));
+  pool_->on_error = [this](int) {
+    bool expected = false;
+    if (!aborted_.compare_exchange_strong(expected, true)) return;
+    for (auto& s : ranks_) s->comm_abort();
+  };
   ncclUniqueId uid;
   CLR_NCCL(NcclApi::get().GetUniqueId(&uid));
   // ncclCommInitRank blocks until every rank has joined: one thread per rank

@@ -7,6 +7,7 @@
 // because the NCCL collectives inside them need all ranks in flight together). The host language - the Julia shim's
 // `ccall`s, INTEGRATION.md - needs no processes, no torchrun and no rendezvous of its own.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <memory>
@@ -35,6 +36,7 @@ class RankPool {
   ~RankPool();
   void run(const std::function<void(int)>& f);
   int size() const { return (int)workers_.size(); }
+  std::function<void(int)> on_error;  // called on the failing worker's thread, before run() returns
 
  private:
   void loop(int r);
@@ -113,6 +115,7 @@ class MultiSolver : public SolverApi {
   int nl_, prec_, n_ = 0;
   std::vector<std::unique_ptr<Solver>> ranks_;
   std::unique_ptr<RankPool> pool_;
+  std::atomic<bool> aborted_{false};              // a rank failed: the communicators have been aborted
   // global structure
   int J_ = 0, n_y_ = 0;
   int64_t sumS_ = 0, blkN_ = 0;

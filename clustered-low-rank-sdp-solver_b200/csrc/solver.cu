@@ -109,6 +109,15 @@ void Solver::comm_init(int n_ranks, int rank, const uint8_t* id) {
   drop_graph();
   direct_iters_ = 0;
 }
+// Called (from any thread) when ANOTHER rank of a single-process multi-device handle has failed: the collectives this
+// rank has queued would wait for that rank for ever. ncclCommAbort releases them; the handle is unusable afterwards.
+void Solver::comm_abort() {
+  ncclComm_t c = comm_.comm;
+  if (!c) return;
+  comm_.comm = nullptr;
+  NcclApi::get().CommAbort(c);
+  prepared = false;
+}
 void Solver::allreduce(MpBuf& t, int64_t off, int64_t n, int op) {
   if (!comm_.active() || n <= 0) return;
   size_t words = (size_t)(nl + 1) * n;

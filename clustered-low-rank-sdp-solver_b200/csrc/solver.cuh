@@ -95,6 +95,7 @@ class Solver : public SolverApi {
   int solve(clrsdp_iter_info* rows, int max_rows, int* n_rows) override;
   int64_t fetch(const char* name, int j, int l, clrsdp_mp_out* out) override;
   void comm_init(int n_ranks, int rank, const uint8_t* id) override;
+  void comm_abort();  // release collectives that wait for a failed peer (multi-device handle)
   void pin_host(void* p, size_t bytes) override;
   void unpin_host(void* p) override;
   double measure_i8_peak() override {
