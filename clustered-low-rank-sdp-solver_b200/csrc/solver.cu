@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <map>
@@ -230,6 +231,7 @@ void Solver::to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpB
   }
   uint32_t* stage = stage_buf().ensure((size_t)(nl + 1) * count);
   const int nlv = nl;
+  std::atomic<bool> bad_wire{false};
   parallel_ranges(count, [&](int64_t lo, int64_t hi) {
     for (int k = 0; k < nlv; k++)
       memcpy(stage + (size_t)k * count + lo, src->limb + (size_t)k * src->n + src_off + lo, (size_t)(hi - lo) * 4);
@@ -240,10 +242,14 @@ void Solver::to_device(const clrsdp_mp* src, int64_t src_off, int64_t count, MpB
         hdr[i] = mp::pack_hdr(mp::EXP_ZERO, 0);
         for (int k = 0; k < nlv; k++) stage[(size_t)k * count + i] = 0;
       } else {
-        hdr[i] = mp::pack_hdr((int32_t)src->exp[src_off + i], sg < 0 ? 1u : 0u);
+        const int64_t e = src->exp[src_off + i];
+        // the header word holds the exponent in 31 bits and reserves -2^28 for zero; a mantissa must be normalised
+        if (e <= -(1 << 27) || e >= (1 << 27) || !(src->limb[(size_t)(nlv - 1) * src->n + src_off + i] & 0x80000000u)) bad_wire = true;
+        hdr[i] = mp::pack_hdr((int32_t)e, sg < 0 ? 1u : 0u);
       }
     }
   });
+  if (bad_wire) throw SolverError(CLRSDP_ERR_BAD_ARG, "wire tensor: exponent outside (-2^27, 2^27) or mantissa not normalised (top bit of the top limb clear)");
   CLR_CUDA(cudaMemcpy2DAsync(dst.w() + dst_off, dst.n * sizeof(uint32_t), stage, (size_t)count * sizeof(uint32_t),
                              (size_t)count * sizeof(uint32_t), (size_t)(nl + 1), cudaMemcpyHostToDevice, ctx.stream));
   CLR_CUDA(cudaStreamSynchronize(ctx.stream));  // the staging buffer is reused by the next transfer
@@ -683,6 +689,8 @@ void Solver::upload_point(const clrsdp_mp* xx, const clrsdp_mp* XX, const clrsdp
 }
 void Solver::download_point(clrsdp_mp_out* xx, clrsdp_mp_out* XX, clrsdp_mp_out* yy, clrsdp_mp_out* YY) {
   if (!have_point) throw SolverError(CLRSDP_ERR_STATE, "download_point: no point");
+  if ((xx && xx->n < sumS) || (yy && yy->n < n_y) || (XX && XX->n < blkN) || (YY && YY->n < blkN))
+    throw SolverError(CLRSDP_ERR_BAD_ARG, "download_point: an output array is smaller than the structure");
   CLR_CUDA(cudaSetDevice(ctx.device));
   WireGroup grp(*this, (size_t)(sumS + n_y + 2 * blkN));
   if (xx) to_host(x, 0, sumS, xx, 0);
@@ -768,6 +776,15 @@ void Solver::product(GemmEngine* ge, Slice& sa, Slice& sb, const OperandDesc& a,
   ge->multiply(sa, sb, plan_of(a.batch, M, N), c, epi, extra);
 }
 
+namespace {
+// selects a helper stream for the launches of a block and puts the previous one back on every way out
+struct StreamScope {
+  Ctx& ctx;
+  cudaStream_t saved;
+  StreamScope(Ctx& c, cudaStream_t s) : ctx(c), saved(c.stream) { ctx.stream = s; }
+  ~StreamScope() { ctx.stream = saved; }
+};
+}  // namespace
 void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch& Vw, const MatBatch& Linv,
                           int* d_stat, bool want_u, bool side, int* d_sig, int* d_keep_scale) {
   const int n = A.n, batch = A.batch;
@@ -839,12 +856,12 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
     const int wk = std::min(PANEL, n - k0), n2 = n - k0 - wk;
     panel_factor(ctx, nl, Uw.sub(k0, k0, wk), Linv.sub(k0, k0, wk), want_u, d_stat, d_sig ? d_sig + k0 : nullptr, n);
     if (par && k0 >= PANEL) {
-      cudaStream_t cur = ctx.stream;
-      CLR_CUDA(cudaEventRecord(H.ev_go, cur));
+      CLR_CUDA(cudaEventRecord(H.ev_go, ctx.stream));
       CLR_CUDA(cudaStreamWaitEvent(H.stream, H.ev_go, 0));
-      ctx.stream = H.stream;
-      inverse_panel(k0, H.gemm.get(), H.s1, H.s2, H.tscr);
-      ctx.stream = cur;
+      {
+        StreamScope on_helper(ctx, H.stream);  // (restores the stream when an exception leaves the block, too)
+        inverse_panel(k0, H.gemm.get(), H.s1, H.s2, H.tscr);
+      }
       forked = true;
     }
     if (n2 > 0) {
@@ -888,13 +905,13 @@ void Solver::chol_inverse(const MatBatch& A, const MatBatch& Uw, const MatBatch&
       if (!ahead) {
         update(gemm_loc, fs1_, fs2_, k1, n2, k1, n2);
       } else {
-        cudaStream_t cur = ctx.stream;
-        CLR_CUDA(cudaEventRecord(TH.ev_go, cur));  // U12 is complete
+        CLR_CUDA(cudaEventRecord(TH.ev_go, ctx.stream));  // U12 is complete
         CLR_CUDA(cudaStreamWaitEvent(TH.stream, TH.ev_go, 0));
-        ctx.stream = TH.stream;
-        update(TH.gemm.get(), TH.s1, TH.s2, k1 + w1, nr, k1 + w1, nr);
-        CLR_CUDA(cudaEventRecord(TH.ev_done, TH.stream));
-        ctx.stream = cur;
+        {
+          StreamScope on_helper(ctx, TH.stream);
+          update(TH.gemm.get(), TH.s1, TH.s2, k1 + w1, nr, k1 + w1, nr);
+          CLR_CUDA(cudaEventRecord(TH.ev_done, TH.stream));
+        }
         trail_pending = trail_used = true;
         update(gemm_loc, fs1_, fs2_, k1, w1, k1, n2);  // the next panel's row block
       }
@@ -1750,6 +1767,8 @@ void Solver::op_gemm_planes(int batch, int M, int N, int K, const clrsdp_mp* A, 
 int Solver::op_cholesky(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* L, clrsdp_mp_out* Linv) {
   CLR_CUDA(cudaSetDevice(ctx.device));
   int64_t tot = (int64_t)batch * n * n;
+  if (batch <= 0 || n <= 0 || !A || A->n != tot || (L && L->n < tot) || (Linv && Linv->n < tot))
+    throw SolverError(CLRSDP_ERR_BAD_ARG, "op_cholesky: operand / result sizes");
   MpBuf a, u, v, li, rd;
   a.alloc(tot, nl), u.alloc(tot, nl), v.alloc(tot, nl), li.alloc(tot, nl), rd.alloc((int64_t)batch * n, nl);
   to_device(A, 0, tot, a, 0);
@@ -1813,6 +1832,8 @@ void Solver::op_signed_factor(int batch, int n, const clrsdp_mp* A, clrsdp_mp_ou
   to_host(li, 0, tot, Minv, 0);
 }
 void Solver::op_elementwise(int op, const clrsdp_mp* a, const clrsdp_mp* b2, clrsdp_mp_out* cc) {
+  if (!a || !cc || a->n <= 0 || (b2 && b2->n != a->n) || cc->n < a->n)
+    throw SolverError(CLRSDP_ERR_BAD_ARG, "op_elementwise: operand / result sizes");
   CLR_CUDA(cudaSetDevice(ctx.device));
   MpBuf A, B, C;
   A.alloc(a->n, nl), B.alloc(a->n, nl), C.alloc(a->n, nl);
@@ -1825,6 +1846,8 @@ void Solver::op_elementwise(int op, const clrsdp_mp* a, const clrsdp_mp* b2, clr
 void Solver::op_lambda_min(int batch, int n, const clrsdp_mp* A, clrsdp_mp_out* lamo) {
   CLR_CUDA(cudaSetDevice(ctx.device));
   int64_t tot = (int64_t)batch * n * n;
+  if (batch <= 0 || n <= 0 || !A || !lamo || A->n != tot || lamo->n < batch)
+    throw SolverError(CLRSDP_ERR_BAD_ARG, "op_lambda_min: operand / result sizes");
   MpBuf a, out;
   a.alloc(tot, nl), out.alloc(batch, nl);
   to_device(A, 0, tot, a, 0);

@@ -60,6 +60,10 @@ enum {
   CLRSDP_ERR_NCCL      = -3,
   CLRSDP_ERR_NOT_PD_X  = -10, /* Cholesky of an X block failed  (MPMP.jl:774-798: "try higher precision") */
   CLRSDP_ERR_NOT_PD_Y  = -11, /* Cholesky of a  Y block failed  (MPMP.jl:1846-1848,1881-1884)           */
+  /* -12 .. -14 are kept for ABI stability and for front ends that map them to the reference's messages, but this
+   * implementation does not produce them: S_j and Q are factored as U^T Sigma U with signed pivots, which cannot fail
+   * (a solve that outruns the precision ends with CLRSDP_ERR_DIVERGED or NOT_PD_X/Y instead), and the step-length
+   * eigenvalue has an all-multiprecision fallback for the matrices its fast path flags. */
   CLRSDP_ERR_SINGULAR_S= -12, /* factorisation of S_j failed    (MPMP.jl:1438-1440)                     */
   CLRSDP_ERR_SINGULAR_Q= -13, /* factorisation of Q failed      (MPMP.jl:1502-1504)                     */
   CLRSDP_ERR_EIG       = -14, /* step-length eigen solve failed (MPMP.jl:1861-1862,1881-1884)           */
@@ -230,8 +234,9 @@ double clrsdp_cluster_weight(int m, int L, int n_samples, const int* delta, int 
 /* (b) One process per GPU (torchrun-style). Rank 0 obtains an id, the host language broadcasts the 128 bytes (e.g.
  * torch.distributed.broadcast), every rank calls comm_init. After that set_structure/upload_cluster are given ONLY the
  * local clusters (any subset, e.g. the sets of clrsdp_partition).
- * In both modes the only collectives are the ones SURVEY §8e lists - Q (n_y^2), three n_y-vectors and the scalar
- * sum / max / min reductions per iteration - inside prepare / iterate. */
+ * In both modes the only collectives are the ones SURVEY §8e lists - Q (n_y^2), the n_y-vectors of the Schur solve and the
+ * scalar sum / max / min reductions per iteration - inside prepare / iterate, as an all-gather of every rank's planes followed
+ * by a rank-ordered combine (why not an int64-lane all-reduce). */
 int clrsdp_comm_unique_id(uint8_t id[128]);
 int clrsdp_comm_init(clrsdp_handle h, int n_ranks, int rank, const uint8_t id[128]);
 

@@ -246,3 +246,25 @@ def test_lookahead_and_cluster_panels_do_not_change_the_factorisation(signed):
         Lo, Lio = oracle_handle(prec, 2).op_cholesky(batch, n, A)
         for r in (plain, ahead):
             assert rel_err_bits(r[0], Lo) >= prec - 16 and rel_err_bits(r[1], Lio) >= prec - 16
+
+
+def test_malformed_wire_tensors_and_short_buffers_are_rejected():
+    """Boundary hygiene (advisor, round 1): an exponent outside the header word's range or a mantissa whose top bit is
+    clear is CLRSDP_ERR_BAD_ARG, not a silently wrapped number; result buffers that are too small are refused before
+    anything is written."""
+    from clrsdp.capi import ClrsdpError
+    h = solver.product_handle(256)
+    a = MpArray.from_double(np.array([1.5, -2.25, 3.0]), h.nlimb)
+    big = MpArray.from_double(np.array([1.5, -2.25, 3.0]), h.nlimb)
+    big.exp[1] = 1 << 40
+    with pytest.raises(ClrsdpError) as e:
+        h.op_elementwise("+", big, a)
+    assert e.value.code == -1
+    den = MpArray.from_double(np.array([1.5, -2.25, 3.0]), h.nlimb)
+    den.limb[h.nlimb - 1, 2] &= 0x7FFFFFFF
+    with pytest.raises(ClrsdpError) as e:
+        h.op_elementwise("*", a, den)
+    assert e.value.code == -1
+    with pytest.raises(ClrsdpError) as e:                       # 2 matrices of 4 x 4 announced, 3 numbers given
+        h.op_lambda_min(2, 4, a)
+    assert e.value.code == -1
