@@ -22,6 +22,11 @@
  *
  * Matrix layout: all matrices cross the boundary ROW-major. (X, Y, S_j, Q are symmetric; B_j is
  * dim_S[j] x n_y with rows ordered (r,s,k), k fastest, exactly as prepareabc builds it, MPMP.jl:387-395.)
+ * SURVEY §8b sketched column-major (Julia's native order) at this cut; row-major was chosen because every kernel
+ * consumes rows with the contraction index contiguous, and the Julia shim (julia/ClrsdpB200.jl: MpArr(::ArbMatrix))
+ * transposes while it converts Arb midpoints to the wire format - a copy it has to make anyway.
+ * Exponents must lie in (-2^27, 2^27) (the device header word holds 31 bits and reserves -2^28 for zero); tensors that
+ * violate this or the normalisation rule above are refused with CLRSDP_ERR_BAD_ARG on the staged upload path.
  *
  * The same set of entry points exists with the prefix `clrsdp_ref_` in oracle/ (the CPU restatement
  * used ONLY by tests / smoke / the bench's cpu_baseline leg).
