@@ -107,6 +107,7 @@ void Solver::comm_init(int n_ranks, int rank, const uint8_t* id) {
   comm_.nranks = n_ranks;
   comm_.rank = rank;
   prepared = false;
+  ntot_uploaded_ = false;
   drop_graph();
   direct_iters_ = 0;
 }
@@ -422,6 +423,7 @@ void Solver::set_structure(int J_, int n_y_, const int* m, const int* L, const i
   structure_set = true;
   drop_graph();
   direct_iters_ = 0;
+  ntot_uploaded_ = false;
   have_point = prepared = tables_ready = false;
   upload_tables();
 }
@@ -1415,18 +1417,10 @@ void Solver::dot_CY() {
   allreduce(scal, SL_CY, 1, COMB_SUM);
 }
 
-// loop initialisation (MPMP.jl:716-736)
-int Solver::prepare(clrsdp_iter_info* info) {
-  if (!have_point) return CLRSDP_ERR_STATE;
-  for (int u : uploaded_)
-    if (!u) return CLRSDP_ERR_STATE;
-  CLR_CUDA(cudaSetDevice(ctx.device));
-  double t0 = now_s();
+// loop initialisation (MPMP.jl:716-736): the device work, no host synchronisation, no host-side data dependence
+void Solver::prepare_body() {
   CLR_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int) * n_status, ctx.stream));
-  int zero2[2] = {0, 0};
-  CLR_CUDA(cudaMemcpyAsync(d_flags.p, zero2, 2 * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
-  iter = 1;
-  upload_ntot();
+  CLR_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(int), ctx.stream));
   ew_zero(ctx, nl, scal.t(), SL_ALPHA_P, 1);
   ew_zero(ctx, nl, scal.t(), SL_ALPHA_D, 1);
   reduce_dot(ctx, nl, X.t(), 0, Y.t(), 0, blkN, scal.t(), SL_DOT_XY, work.t());
@@ -1440,6 +1434,26 @@ int Solver::prepare(clrsdp_iter_info* info) {
   // the initial duality gap is computed WITHOUT b0 (MPMP.jl:725 -> :1067-1074)
   scalar_program(ctx, nl, SP_OBJECTIVES_INIT, scal.t(), d_flags.as<int>(), nullptr);
   scalar_program(ctx, nl, SP_ERRORS, scal.t(), d_flags.as<int>(), d_scal_out.as<double>());
+}
+
+int Solver::prepare(clrsdp_iter_info* info) {
+  if (!have_point) return CLRSDP_ERR_STATE;
+  for (int u : uploaded_)
+    if (!u) return CLRSDP_ERR_STATE;
+  CLR_CUDA(cudaSetDevice(ctx.device));
+  double t0 = now_s();
+  if (main_stream_) ctx.stream = main_stream_;
+  on_side_ = false;
+  join_pending_ = false;
+  iter = 1;
+  if (!ntot_uploaded_) {  // (the global size of X changes only with the structure or the communicator)
+    upload_ntot();
+    ntot_uploaded_ = true;
+  }
+  // (Replaying this body from a CUDA graph of its own - for front ends that re-upload the iterate and call prepare before
+  // every iteration, bench.py's end-to-end path - was measured: prepare 0.60 -> 0.55 ms, but alternating two graph
+  // executables on the stream cost the iteration's launch 0.3 ms. Direct launches stay.)
+  prepare_body();
   int st = check_status();
   prepared = (st == 0);
   if (info) {

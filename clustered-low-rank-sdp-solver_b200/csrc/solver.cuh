@@ -169,6 +169,7 @@ class Solver : public SolverApi {
   void mark(int bucket_begin);
   void iteration_body();
   void drop_graph();
+  void prepare_body();
 
   std::vector<std::pair<const char*, size_t>> pinned_;  // host ranges registered through pin_host
   DevBuf equil_, equil_side_;                          // equilibration exponents of chol_inverse
@@ -229,6 +230,7 @@ class Solver : public SolverApi {
   // CUDA-graph replay of the iteration body (one launch instead of ~1000)
   bool use_graph_ = true, capturing_ = false;
   cudaGraphExec_t gexec_ = nullptr;
+  bool ntot_uploaded_ = false;                       // the global size of X sits in its scalar slot (one-off per structure / communicator)
   uint64_t graph_epoch_ = 0;
   int direct_iters_ = 0;
   int64_t graph_launches_ = 0;

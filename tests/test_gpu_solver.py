@@ -235,6 +235,43 @@ def test_warm_start_roundtrip():
     assert np.array_equal(a.limb, o.limb) and np.array_equal(a.exp, o.exp)     # bit-identical
 
 
+def test_host_resident_iterate_loop_replays_prepare_bit_identically():
+    """The end-to-end pattern of bench.py: the iterate lives on the host, every step is upload_point + prepare + iterate +
+    download_point on ONE handle (the iteration replayed from its CUDA graph, the global size of X uploaded once); the
+    log row of prepare, the iteration's row and the new iterate must be bit-identical to a fresh handle that runs the
+    same step with direct launches."""
+    prec = 256
+    cons, b, _ = instances.synthetic_clustered_sdp(J=3, delta=5, K=7, n_y=4, prec=prec, seed=5)
+    bi = solver.get_block_info(cons)
+    n_x, n_X = sum(bi.dim_S), sum(s * s for row in bi.Y_blocksizes for s in row)
+    h = solver.product_handle(prec)
+    solver.load_problem(h, cons, b, bi)
+    h.set_params(solver.real_params(h.nlimb))
+    h.init_point()
+    h.prepare()
+    h.iterate()
+    st = h.download_point(n_x, n_X, bi.n_y)
+    same = lambda a, o: np.array_equal(a.limb, o.limb) and np.array_equal(a.exp, o.exp) and np.array_equal(a.sign, o.sign)
+    for step in range(4):
+        h.upload_point(*st)
+        p1 = h.prepare()
+        r1 = h.iterate()
+        out = h.download_point(n_x, n_X, bi.n_y)
+        f = solver.product_handle(prec)                       # fresh handle: everything launched directly
+        solver.load_problem(f, cons, b, bi)
+        f.set_params(solver.real_params(f.nlimb))
+        f.upload_point(*st)
+        p2 = f.prepare()
+        r2 = f.iterate()
+        ref = f.download_point(n_x, n_X, bi.n_y)
+        for k in ("mu", "p_obj", "d_obj", "gap", "P_err", "p_err", "d_err", "pd_feasible", "terminate"):
+            assert getattr(p1, k) == getattr(p2, k), (step, k)
+        for k in ("mu", "alpha_p", "alpha_d", "beta_c", "p_obj_new", "d_obj_new", "P_err", "p_err", "d_err", "terminate"):
+            assert getattr(r1, k) == getattr(r2, k), (step, k)
+        assert all(same(a, o) for a, o in zip(out, ref)), step
+        st = out
+
+
 def test_pinned_host_buffers_roundtrip_is_bit_identical():
     """clrsdp_pin_host: the direct-DMA path (limb planes by strided copy, header words converted on the device) moves
     exactly the same bits as the staged path, in both directions, including zero entries."""
