@@ -1451,8 +1451,8 @@ int Solver::prepare(clrsdp_iter_info* info) {
     ntot_uploaded_ = true;
   }
   // (Replaying this body from a CUDA graph of its own - for front ends that re-upload the iterate and call prepare before
-  // every iteration, bench.py's end-to-end path - was measured: prepare 0.60 -> 0.55 ms, but alternating two graph
-  // executables on the stream cost the iteration's launch 0.3 ms. Direct launches stay.)
+  // every iteration, bench.py's end-to-end path - was measured: 0.60 -> 0.55 ms. The call is device work plus one
+  // synchronisation, not launch overhead; a second graph to maintain is not worth 50 us.)
   prepare_body();
   int st = check_status();
   prepared = (st == 0);
