@@ -127,6 +127,31 @@ def traffic_from_profile():
     return None, "no ncu summary under profiles/"
 
 
+def tensor_pipe_from_profile(pattern):
+    """sm__pipe_tensor_cycles_active (% of peak, per launch) of the tensor kernel from the newest committed ncu summary that
+    matches `pattern` under profiles/ - the hardware's own view beside `roofline.frac`, which since the carry propagation
+    was fused into the kernel counts the epilogue's CUDA-core work (carry, normalise, round, store) in its denominator."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)), key=os.path.getmtime)
+    if not files:
+        return None
+    vals, times = [], []
+    with open(files[-1]) as f:
+        for line in f:
+            m = re.search(r"sm__pipe_tensor_cycles_active\.avg\.pct_of_peak_sustained_active\s+([0-9.]+)", line)
+            if m:
+                vals.append(round(float(m.group(1)), 1))
+            m = re.search(r"gpu__time_duration\.sum\s+([0-9.]+)\s+(\w+)", line)
+            if m:
+                times.append(round(float(m.group(1)) * {"us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "ns": 1e-3,
+                                                        "nsecond": 1e-3}.get(m.group(2), 1.0), 1))
+    # the captures hold 4 launches per product shape: one figure per shape
+    per_shape = [vals[i] for i in range(0, len(vals), 4)]
+    return dict(source=os.path.relpath(files[-1], ROOT), pct_per_product_shape=per_shape,
+                us_per_launch=[times[i] for i in range(0, len(times), 4)])
+
+
 def mma_roofline_of(name, steps, warmup, int8_peak_tops, device=0):
     """The sliced-GEMM roofline entry on another workload in the same run (one GPU): `steps` profiled iterations."""
     from clrsdp import solver
@@ -164,7 +189,7 @@ def mma_roofline_of(name, steps, warmup, int8_peak_tops, device=0):
         return dict(workload=name, config=dict(WORKLOAD), bound="tensor", kernel="mma_planes_kernel", achieved=tops, peak=int8_peak_tops,
                     unit="TOP/s (int8)", frac=tops / int8_peak_tops if int8_peak_tops else None, launches=mma["launches"],
                     ms_per_step=float(np.mean(dev)) * 1e3, steps=steps, share_of_step=mma["ms"] * 1e-3 / prof_s if prof_s else None,
-                    int8_mac_per_iter=macs)
+                    int8_mac_per_iter=macs, tensor_pipe_active_ncu=tensor_pipe_from_profile("r*_ncu_mma_planes_cfg5_full.txt"))
     finally:
         WORKLOAD.clear()
         WORKLOAD.update(saved)
@@ -473,6 +498,11 @@ def main():
     roofline = dict(bound="tensor", kernel="mma_planes_kernel", achieved=mma_tops, peak=int8_peak_tops, unit="TOP/s (int8)",
                     frac=mma_tops / int8_peak_tops if int8_peak_tops else None,
                     traffic=traffic if args.workload == "cfg3" else None, traffic_source=traffic_src,
+                    tensor_pipe_active_ncu=tensor_pipe_from_profile("r*_ncu_mma_planes_full.txt" if args.workload == "cfg3"
+                                                                    else "r*_ncu_mma_planes_cfg5_full.txt"),
+                    frac_note="algorithmic int8 MACs / event time of the whole tensor kernel / measured int8 peak; since round 2 "
+                              "the kernel's time includes the fused carry / normalise / store epilogue (a separate launch in "
+                              "round 1), so frac is not comparable with round 1's 0.13: the hardware counter beside it is",
                     peak_source="measured in this run (tcgen05.mma kind::i8 issue loop on all SMs); MEASURED_PEAKS.json has "
                                 f"no int8 entry (its bf16 figure: {peaks['bf16_tflops']} TFLOP/s, {peaks['source']})",
                     achieved_note="ALGORITHMIC int8 ops (M*N*K*s(s+1)/2 MACs per product, s = p/8; no guard digits, no tile "
