@@ -502,7 +502,7 @@ def main():
                                                                     else "r*_ncu_mma_planes_cfg5_full.txt"),
                     frac_note="algorithmic int8 MACs / event time of the whole tensor kernel / measured int8 peak; since round 2 "
                               "the kernel's time includes the fused carry / normalise / store epilogue (a separate launch in "
-                              "round 1), so frac is not comparable with round 1's 0.13: the hardware counter beside it is",
+                              "round 1), so frac is not comparable with round 1's 0.13; tensor_pipe_active_ncu is the hardware counter",
                     peak_source="measured in this run (tcgen05.mma kind::i8 issue loop on all SMs); MEASURED_PEAKS.json has "
                                 f"no int8 entry (its bf16 figure: {peaks['bf16_tflops']} TFLOP/s, {peaks['source']})",
                     achieved_note="ALGORITHMIC int8 ops (M*N*K*s(s+1)/2 MACs per product, s = p/8; no guard digits, no tile "
