@@ -1,7 +1,8 @@
-"""CPU models of two identities the CUDA kernels rely on (exact integer / rational arithmetic, no GPU):
-the balanced radix-256 digits of the slicer by one addition and one xor (csrc/gemm_i8.cu: fixed_point_digits), and the
+"""CPU models of what the CUDA kernels and their orchestration rely on (exact integer / rational arithmetic, no GPU):
+the balanced radix-256 digits of the slicer by one addition and one xor (csrc/gemm_i8.cu: fixed_point_digits), the
 algebra of the equilibrated Schur factorisation (csrc/solver.cu: chol_inverse with d_keep_scale, decomposition(),
-search_direction())."""
+search_direction()), the signed division-free elimination of panel_factor_kernel (csrc/linalg.cu), and the stream
+schedule of the blocked factorisation with lookahead (every data hazard ordered, every update applied once)."""
 import random
 from fractions import Fraction
 
@@ -92,3 +93,149 @@ def test_equilibrated_schur_algebra():
     up = [[rhs[i][0] / D[i] + sum(Bp[i][k] * dy[k][0] for k in range(ny))] for i in range(n)]
     dxp = _mul(Spi, up)
     assert dx == [[dxp[i][0] / D[i]] for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the signed, division-free elimination of panel_factor_kernel (csrc/linalg.cu) in exact rational arithmetic
+# ---------------------------------------------------------------------------------------------------------------------
+def _signed_elimination(A):
+    """[A | I] -> [R' | G'] by  row_r <- mu_k row_r - R'_k[r] row_k  (mu_k = the current pivot R'_kk; the kernel also
+    divides both factors by 2^e_k, which cancels in everything below). Returns R', G' and tau (the common scale of the
+    unpivoted rows: tau_0 = 1, tau_{k+1} = mu_k tau_k)."""
+    n = len(A)
+    R = [[Fraction(v) for v in row] for row in A]
+    G = [[Fraction(int(i == j)) for j in range(n)] for i in range(n)]
+    tau = [Fraction(1)]
+    for k in range(n - 1):
+        mu = R[k][k]
+        assert mu != 0
+        for r in range(k + 1, n):
+            gam = R[k][r]                      # by symmetry of the trailing matrix R'[r][k] = R'[k][r] (what the kernel reads)
+            R[r] = [mu * a - gam * b for a, b in zip(R[r], R[k])]
+            G[r] = [mu * a - gam * b for a, b in zip(G[r], G[k])]
+        tau.append(mu * tau[-1])
+    return R, G, tau
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_signed_division_free_factorisation_identities(seed):
+    """For symmetric A with non-zero leading minors of EITHER sign (what the Schur complements of a polynomial programme
+    look like at the precision limit): G' A G'^T = diag(tau_k d'_k) with d'_k = R'_kk, exactly. Hence
+    A^-1 = M^T Sigma M with M = diag(|tau_k d'_k|^-1/2) G', Sigma_k = sign(tau_k d'_k) - the factorisation
+    clrsdp_op_signed_factor returns - without a division or a square root inside the elimination, and with negative
+    pivots costing nothing."""
+    rng = random.Random(100 + seed)
+    n = 6
+    while True:
+        B = [[Fraction(rng.randint(-6, 6)) for _ in range(n)] for _ in range(n)]
+        sg = [rng.choice([-1, 1]) for _ in range(n)]
+        A = [[sum(B[i][k] * sg[k] * B[j][k] for k in range(n)) for j in range(n)] for i in range(n)]   # indefinite, symmetric
+        try:
+            R, G, tau = _signed_elimination(A)
+        except AssertionError:
+            continue
+        if R[n - 1][n - 1] != 0:
+            break
+    # R' is upper triangular, G' lower triangular with diagonal tau
+    assert all(R[i][j] == 0 for i in range(n) for j in range(i))
+    assert all(G[i][j] == 0 for i in range(n) for j in range(i + 1, n)) and [G[i][i] for i in range(n)] == tau
+    assert _mul(G, A) == R                                                                              # the row operations
+    D = _mul(_mul(G, A), [list(r) for r in zip(*G)])
+    assert all(D[i][j] == (tau[i] * R[i][i] if i == j else 0) for i in range(n) for j in range(n))
+    # A^-1 = G'^T diag(1 / (tau_k d'_k)) G'  (= M^T Sigma M after pulling |.|^-1/2 into M)
+    Dinv = [[(1 / (tau[i] * R[i][i]) if i == j else Fraction(0)) for j in range(n)] for i in range(n)]
+    assert _mul(_mul([list(r) for r in zip(*G)], Dinv), G) == _inv(A)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the stream schedule of the blocked factorisation with lookahead (csrc/solver.cu: chol_inverse)
+# ---------------------------------------------------------------------------------------------------------------------
+def _chol_inverse_schedule(nb, lookahead, inverse_helper=True):
+    """The launches chol_inverse issues for a matrix of nb panels, as (stream, name, reads, writes) with the event edges
+    between the streams; regions are panel-sized blocks ('U', r, c) of the work matrix and ('L', r, c) of the inverse.
+    Mirrors the control flow of Solver::chol_inverse (main = 'M', inverse-panel helper = 'H', remainder helper = 'T')."""
+    ops, edges = [], []            # edges: (index of the op after which the event is recorded, index of the op that waits)
+    last = {"M": None, "H": None, "T": None}
+    pending_waits = {"M": [], "H": [], "T": []}
+
+    def emit(stream, name, reads, writes):
+        ops.append((stream, name, frozenset(reads), frozenset(writes)))
+        i = len(ops) - 1
+        for src in pending_waits[stream]:
+            edges.append((src, i))
+        pending_waits[stream] = []
+        last[stream] = i
+        return i
+
+    def wait(stream, on_stream):                     # cudaEventRecord(on_stream) ; cudaStreamWaitEvent(stream)
+        if last[on_stream] is not None:
+            pending_waits[stream].append(last[on_stream])
+
+    trail_pending = False
+    for k in range(nb):
+        emit("M", f"panel{k}", {("U", k, k)}, {("U", k, k), ("L", k, k)})
+        if inverse_helper and nb > 2 and k >= 1:
+            wait("H", "M")
+            emit("H", f"inv{k}", {("U", r, k) for r in range(k)} | {("L", r, c) for r in range(k) for c in range(r + 1)} | {("L", k, k)},
+                 {("L", k, c) for c in range(k)})
+        rest = list(range(k + 1, nb))
+        if not rest:
+            continue
+        emit("M", f"u12_{k}", {("L", k, k)} | {("U", k, c) for c in rest}, {("U", k, c) for c in rest})
+        if trail_pending:
+            wait("M", "T")
+            trail_pending = False
+        rem = rest[1:]
+        if lookahead and rem:
+            wait("T", "M")
+            emit("T", f"rem{k}", {("U", k, c) for c in rem}, {("U", r, c) for r in rem for c in rem})
+            trail_pending = True
+            emit("M", f"row{k}", {("U", k, c) for c in rest}, {("U", rest[0], c) for c in rest})
+        else:
+            emit("M", f"trail{k}", {("U", k, c) for c in rest}, {("U", r, c) for r in rest for c in rest})
+    wait("M", "T")
+    wait("M", "H")
+    if not (inverse_helper and nb > 2):
+        for k in range(1, nb):
+            emit("M", f"inv{k}", {("U", r, k) for r in range(k)} | {("L", r, c) for r in range(k) for c in range(r + 1)} | {("L", k, k)},
+                 {("L", k, c) for c in range(k)})
+    emit("M", "join", set(), set())
+    return ops, edges
+
+
+@pytest.mark.parametrize("nb", [2, 3, 5, 8])
+@pytest.mark.parametrize("lookahead", [False, True])
+def test_lookahead_schedule_orders_every_hazard_and_applies_every_update_once(nb, lookahead):
+    ops, edges = _chol_inverse_schedule(nb, lookahead)
+    n = len(ops)
+    # happens-before: program order within a stream + event edges, transitively
+    hb = [[False] * n for _ in range(n)]
+    prev = {}
+    for i, (s, *_rest) in enumerate(ops):
+        if s in prev:
+            hb[prev[s]][i] = True
+        prev[s] = i
+    for a, b in edges:
+        hb[a][b] = True
+    for k in range(n):
+        for i in range(n):
+            if hb[i][k]:
+                row_k, row_i = hb[k], hb[i]
+                for j in range(n):
+                    if row_k[j]:
+                        row_i[j] = True
+    for i in range(n):
+        for j in range(i + 1, n):
+            _, ni, ri, wi = ops[i]
+            _, nj, rj, wj = ops[j]
+            if (wi & (rj | wj)) or (ri & wj):
+                assert hb[i][j], (ni, nj)            # issued earlier => must complete earlier when they touch the same block
+    # every trailing block (r, c), r <= c, receives the contribution of every earlier panel exactly once
+    for r in range(1, nb):
+        for c in range(r, nb):
+            for k in range(r):
+                hits = [name for _, name, _, w in ops if ("U", r, c) in w and name in (f"trail{k}", f"rem{k}", f"row{k}")]
+                assert len(hits) == 1, (k, r, c, hits)
+    # everything is joined back to the main stream before the call returns
+    join = n - 1
+    assert all(hb[i][join] for i in range(n - 1))
